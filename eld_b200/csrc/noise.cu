@@ -1,0 +1,445 @@
+// noise.cu - fused ELD noise formation kernel (scale -> shot -> read -> row -> quant -> unscale
+// -> clip), optionally fed by the raw Bayer mosaic (fused pack + de-quantise).
+//
+// Replaces NoiseModelBase.__call__ (reference noise.py:149-170), the clip of
+// SynDataset.__getitem__ (dataset/sid_dataset.py:277), RawPacker.pack_raw_bayer (noise.py:10-20)
+// and LMDBDataset's uint16 de-quantisation (dataset/lmdb_dataset.py:38-39).
+//
+// HBM-bound by design: 8 algorithmic bytes per output pixel (f32 in + f32 out); each thread owns one
+// quad position (4 consecutive columns) of all 4 planes = 16 pixels, issues its four 16-byte loads
+// up front and writes four coalesced float4 stores.  The kernel draws its own Philox counters
+// (philox.cuh) - no RNG state in memory.
+#include "common.cuh"
+#include "philox.cuh"
+
+namespace eld {
+
+constexpr int kMaxFramesPerLaunch = 48;
+constexpr uint32_t kRuntimeMask = 0xFFFFFFFFu;
+
+struct FrameConsts {
+    float K, invK, g, Gs, Gl, Rs, q, scale_in, scale_out;
+    float bias[4];
+    float pad[3];
+};  // 64 bytes
+
+struct NoiseLaunch {
+    FrameConsts fr[kMaxFramesPerLaunch];
+    uint64_t seed;
+    uint64_t frame0;  // global id of fr[0]
+    uint32_t mask;
+    int h, w;         // packed plane
+    int clip01;
+};
+
+static FrameConsts make_consts(const eld_noise_params& p)
+{
+    FrameConsts c{};
+    c.K = p.K;
+    c.invK = 1.0f / p.K;
+    c.g = fmaxf(p.g_scale, 1e-10f);
+    c.Gs = p.G_scale;
+    c.Gl = p.G_lambda;
+    c.Rs = p.R_scale;
+    c.q = p.q_step;
+    c.scale_in = p.saturation / p.ratio;
+    c.scale_out = p.ratio / p.saturation;
+    for (int i = 0; i < 4; ++i) c.bias[i] = p.color_bias[i];
+    return c;
+}
+
+// Noise for the 4 pixels of one quad of plane c.  l0 = linear index of the first pixel in the plane
+// (multiple of 4 on the aligned path), rown[k] = row-noise normal of pixel k's sensor row.
+template <uint32_t MASK>
+__device__ __forceinline__ void form_quad(const FrameConsts& fc, const Stream& s, uint32_t rt_mask,
+                                          uint32_t c, uint32_t l0, const float rown[4], int clip01,
+                                          float y[4])
+{
+    const uint32_t mask = (MASK == kRuntimeMask) ? rt_mask : MASK;
+    const uint32_t quad = l0 >> 2;
+    float z[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) z[k] = y[k] * fc.scale_in;
+
+    if (mask & ELD_NOISE_P) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) z[k] = poisson_px(s, l0 + k, c, z[k] * fc.invK) * fc.K;
+    } else if (mask & ELD_NOISE_p) {
+        float n[4];
+        quad_normals(s, quad, c, D_SHOT, n);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) z[k] = __fmaf_rn(n[k], fast_sqrt(fmaxf(fc.K * z[k], 1e-10f)), z[k]);
+    }
+    if (mask & ELD_NOISE_g) {
+        float n[4];
+        quad_normals(s, quad, c, D_READ, n);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) z[k] = __fmaf_rn(n[k], fc.g, z[k]);
+    }
+    if (mask & ELD_NOISE_G) {
+        const uint4 x = draw(s, quad, DOM_QUAD, c, D_TL);
+        const uint32_t xs[4] = { x.x, x.y, x.z, x.w };
+#pragma unroll
+        for (int k = 0; k < 4; ++k) z[k] = __fmaf_rn(tukey_lambda(u_open(xs[k]), fc.Gl), fc.Gs, z[k]);
+    }
+    if (mask & ELD_NOISE_B) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) z[k] = z[k] + fc.bias[c];
+    }
+    if (mask & ELD_NOISE_R) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) z[k] = __fmaf_rn(rown[k], fc.Rs, z[k]);
+    }
+    if (mask & ELD_NOISE_U) {
+        const uint4 x = draw(s, quad, DOM_QUAD, c, D_QUANT);
+        const uint32_t xs[4] = { x.x, x.y, x.z, x.w };
+#pragma unroll
+        for (int k = 0; k < 4; ++k) z[k] = __fmaf_rn(u_open(xs[k]) - 0.5f, fc.q, z[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        float o = z[k] * fc.scale_out;
+        if (clip01) o = fminf(fmaxf(o, 0.0f), 1.0f);
+        y[k] = o;
+    }
+}
+
+__device__ __forceinline__ float4 ldg_stream(const float4* p)
+{
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stg_stream(float4* p, const float4& v)
+{
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+__device__ __forceinline__ Stream make_stream(const NoiseLaunch& L, int f)
+{
+    const uint64_t frame = L.frame0 + (uint64_t)f;
+    return Stream{ (uint32_t)L.seed, (uint32_t)(L.seed >> 32), (uint32_t)frame, (uint32_t)(frame >> 32) };
+}
+
+__device__ __forceinline__ void row_normals(const Stream& s, uint32_t i, float& r_even, float& r_odd)
+{
+    const uint4 x = draw(s, i, DOM_ROW, 0, 0);
+    box_muller(x.x, x.y, r_even, r_odd);
+}
+
+// ---- packed in, aligned: w % 4 == 0 and 16-byte aligned planes ---------------------------------
+template <uint32_t MASK>
+__global__ void __launch_bounds__(256)
+noise_packed_vec_kernel(const float* __restrict__ clean, float* __restrict__ noisy,
+                        const __grid_constant__ NoiseLaunch L)
+{
+    const int f = blockIdx.y;
+    const uint32_t plane = (uint32_t)L.h * (uint32_t)L.w;
+    const uint32_t quads = plane >> 2;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= quads) return;
+    const uint32_t mask = (MASK == kRuntimeMask) ? L.mask : MASK;
+    const FrameConsts& fc = L.fr[f];
+    const Stream s = make_stream(L, f);
+    const size_t base = (size_t)f * 4 * plane + (size_t)t * 4;
+
+    float4 v[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) v[c] = ldg_stream(reinterpret_cast<const float4*>(clean + base + (size_t)c * plane));
+
+    float r_even = 0.f, r_odd = 0.f;
+    if (mask & ELD_NOISE_R) row_normals(s, (t * 4u) / (uint32_t)L.w, r_even, r_odd);
+
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        float y[4] = { v[c].x, v[c].y, v[c].z, v[c].w };
+        const float rr = (c < 2) ? r_even : r_odd;
+        const float rown[4] = { rr, rr, rr, rr };
+        form_quad<MASK>(fc, s, L.mask, (uint32_t)c, t * 4u, rown, L.clip01, y);
+        stg_stream(reinterpret_cast<float4*>(noisy + base + (size_t)c * plane), make_float4(y[0], y[1], y[2], y[3]));
+    }
+}
+
+// ---- packed in, generic shapes (scalar loads; quads may straddle rows) ------------------------------
+__global__ void __launch_bounds__(256)
+noise_packed_generic_kernel(const float* __restrict__ clean, float* __restrict__ noisy,
+                            const __grid_constant__ NoiseLaunch L)
+{
+    const int f = blockIdx.y;
+    const uint32_t plane = (uint32_t)L.h * (uint32_t)L.w;
+    const uint32_t quads = (plane + 3u) >> 2;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= quads) return;
+    const FrameConsts& fc = L.fr[f];
+    const Stream s = make_stream(L, f);
+    for (int c = 0; c < 4; ++c) {
+        const size_t base = ((size_t)f * 4 + c) * plane;
+        float y[4], rown[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t l = t * 4u + k;
+            y[k] = l < plane ? clean[base + l] : 0.0f;
+            rown[k] = 0.0f;
+            if ((L.mask & ELD_NOISE_R) && l < plane) {
+                float re, ro;
+                row_normals(s, l / (uint32_t)L.w, re, ro);
+                rown[k] = (c < 2) ? re : ro;
+            }
+        }
+        form_quad<kRuntimeMask>(fc, s, L.mask, (uint32_t)c, t * 4u, rown, L.clip01, y);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t l = t * 4u + k;
+            if (l < plane) noisy[base + l] = y[k];
+        }
+    }
+}
+
+// ---- mosaic in (fused Bayer pack + de-quantise), aligned: W % 8 == 0 --------------------------------
+// Thread (i, q): reads mosaic rows 2i and 2i+1, columns 8q..8q+7, writes 4 planes x float4.
+struct MosaicArgs {
+    float black, inv_range;
+    int H, W;
+    int in_dtype;
+};
+
+template <uint32_t MASK, int DT>
+__global__ void __launch_bounds__(256)
+noise_mosaic_vec_kernel(const void* __restrict__ mosaic, float* __restrict__ noisy,
+                        float* __restrict__ clean_out, const MosaicArgs M,
+                        const __grid_constant__ NoiseLaunch L)
+{
+    const int f = blockIdx.y;
+    const uint32_t w = (uint32_t)L.w, h = (uint32_t)L.h;
+    const uint32_t plane = h * w, quads = plane >> 2;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= quads) return;
+    const uint32_t mask = (MASK == kRuntimeMask) ? L.mask : MASK;
+    const uint32_t qpr = w >> 2;          // quads per packed row
+    const uint32_t i = t / qpr, q = t - i * qpr;
+    const FrameConsts& fc = L.fr[f];
+    const Stream s = make_stream(L, f);
+
+    float top[8], bot[8];
+    const size_t row0 = ((size_t)f * M.H + 2u * i) * (size_t)M.W + 8u * q;
+    if (DT == ELD_DT_U16) {
+        const uint16_t* m = static_cast<const uint16_t*>(mosaic);
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(m + row0));
+        const uint4 b = __ldg(reinterpret_cast<const uint4*>(m + row0 + M.W));
+        const uint32_t aw[4] = { a.x, a.y, a.z, a.w }, bw[4] = { b.x, b.y, b.z, b.w };
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            top[2 * k] = (float)(aw[k] & 0xFFFFu); top[2 * k + 1] = (float)(aw[k] >> 16);
+            bot[2 * k] = (float)(bw[k] & 0xFFFFu); bot[2 * k + 1] = (float)(bw[k] >> 16);
+        }
+    } else {
+        const float* m = static_cast<const float*>(mosaic);
+        const float4 a0 = __ldg(reinterpret_cast<const float4*>(m + row0));
+        const float4 a1 = __ldg(reinterpret_cast<const float4*>(m + row0 + 4));
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(m + row0 + M.W));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(m + row0 + M.W + 4));
+        top[0] = a0.x; top[1] = a0.y; top[2] = a0.z; top[3] = a0.w; top[4] = a1.x; top[5] = a1.y; top[6] = a1.z; top[7] = a1.w;
+        bot[0] = b0.x; bot[1] = b0.y; bot[2] = b0.z; bot[3] = b0.w; bot[4] = b1.x; bot[5] = b1.y; bot[6] = b1.z; bot[7] = b1.w;
+    }
+    // RGBG plane order: (0,0) (0,1) (1,1) (1,0)   (noise.py:16-19)
+    float yc[4][4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        yc[0][k] = top[2 * k];
+        yc[1][k] = top[2 * k + 1];
+        yc[2][k] = bot[2 * k + 1];
+        yc[3][k] = bot[2 * k];
+    }
+    float r_even = 0.f, r_odd = 0.f;
+    if (mask & ELD_NOISE_R) row_normals(s, i, r_even, r_odd);
+    const size_t obase = (size_t)f * 4 * plane + (size_t)t * 4;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        float y[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float v = (yc[c][k] - M.black) * M.inv_range;
+            if (L.clip01) v = fminf(fmaxf(v, 0.0f), 1.0f);
+            y[k] = v;
+        }
+        if (clean_out) stg_stream(reinterpret_cast<float4*>(clean_out + obase + (size_t)c * plane), make_float4(y[0], y[1], y[2], y[3]));
+        const float rr = (c < 2) ? r_even : r_odd;
+        const float rown[4] = { rr, rr, rr, rr };
+        form_quad<MASK>(fc, s, L.mask, (uint32_t)c, t * 4u, rown, L.clip01, y);
+        stg_stream(reinterpret_cast<float4*>(noisy + obase + (size_t)c * plane), make_float4(y[0], y[1], y[2], y[3]));
+    }
+}
+
+// ---- mosaic in, generic (any even H, W) ---------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+noise_mosaic_generic_kernel(const void* __restrict__ mosaic, float* __restrict__ noisy,
+                            float* __restrict__ clean_out, const MosaicArgs M,
+                            const __grid_constant__ NoiseLaunch L)
+{
+    const int f = blockIdx.y;
+    const uint32_t w = (uint32_t)L.w, plane = (uint32_t)L.h * w;
+    const uint32_t quads = (plane + 3u) >> 2;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= quads) return;
+    const FrameConsts& fc = L.fr[f];
+    const Stream s = make_stream(L, f);
+    const int dy[4] = { 0, 0, 1, 1 }, dx[4] = { 0, 1, 1, 0 };
+    for (int c = 0; c < 4; ++c) {
+        const size_t base = ((size_t)f * 4 + c) * plane;
+        float y[4], rown[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t l = t * 4u + k;
+            y[k] = 0.f; rown[k] = 0.f;
+            if (l < plane) {
+                const uint32_t i = l / w, j = l - i * w;
+                const size_t mi = ((size_t)f * M.H + (2u * i + dy[c])) * (size_t)M.W + (2u * j + dx[c]);
+                const float m = M.in_dtype == ELD_DT_U16 ? (float)static_cast<const uint16_t*>(mosaic)[mi]
+                                                         : static_cast<const float*>(mosaic)[mi];
+                float v = (m - M.black) * M.inv_range;
+                if (L.clip01) v = fminf(fmaxf(v, 0.0f), 1.0f);
+                y[k] = v;
+                if (clean_out) clean_out[base + l] = v;
+                if (L.mask & ELD_NOISE_R) {
+                    float re, ro;
+                    row_normals(s, i, re, ro);
+                    rown[k] = (c < 2) ? re : ro;
+                }
+            }
+        }
+        form_quad<kRuntimeMask>(fc, s, L.mask, (uint32_t)c, t * 4u, rown, L.clip01, y);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t l = t * 4u + k;
+            if (l < plane) noisy[base + l] = y[k];
+        }
+    }
+}
+
+template <uint32_t MASK>
+static void launch_packed_vec(dim3 grid, cudaStream_t st, const float* clean, float* noisy, const NoiseLaunch& L)
+{
+    noise_packed_vec_kernel<MASK><<<grid, 256, 0, st>>>(clean, noisy, L);
+}
+
+template <uint32_t MASK, int DT>
+static void launch_mosaic_vec(dim3 grid, cudaStream_t st, const void* m, float* noisy, float* clean_out,
+                              const MosaicArgs& M, const NoiseLaunch& L)
+{
+    noise_mosaic_vec_kernel<MASK, DT><<<grid, 256, 0, st>>>(m, noisy, clean_out, M, L);
+}
+
+// masks with a compiled specialisation (everything else takes the runtime-mask instance)
+#define ELD_FOR_EACH_MASK(X)                                                        \
+    X(ELD_NOISE_g)                                                                  \
+    X(ELD_NOISE_p | ELD_NOISE_g)                                                    \
+    X(ELD_NOISE_P | ELD_NOISE_g)                                                    \
+    X(ELD_NOISE_P | ELD_NOISE_G | ELD_NOISE_R | ELD_NOISE_U)                        \
+    X(ELD_NOISE_P | ELD_NOISE_G | ELD_NOISE_B | ELD_NOISE_R | ELD_NOISE_U)
+
+static int check_common(eld_ctx* ctx, const void* in, const void* out, int n, int h, int w,
+                        const eld_noise_params* params, uint32_t mask, const char* who)
+{
+    ELD_REQUIRE(ctx != nullptr, "%s: ctx is NULL", who);
+    ELD_REQUIRE(n >= 0 && h >= 0 && w >= 0, "%s: negative size n=%d h=%d w=%d", who, n, h, w);
+    ELD_REQUIRE((mask & ~0x7Fu) == 0, "%s: unknown model_mask bits 0x%x", who, mask);
+    if (n == 0 || h == 0 || w == 0) return 1;  // empty: nothing to do
+    ELD_REQUIRE(in != nullptr && out != nullptr && params != nullptr, "%s: NULL buffer", who);
+    ELD_REQUIRE((uint64_t)h * (uint64_t)w < (1ull << 32), "%s: plane of %d x %d exceeds 2^32 pixels", who, h, w);
+    for (int f = 0; f < n; ++f) {
+        ELD_REQUIRE(params[f].K > 0.f && params[f].ratio > 0.f && params[f].saturation > 0.f,
+                    "%s: params[%d] needs K, ratio, saturation > 0", who, f);
+    }
+    return 0;
+}
+
+}  // namespace eld
+
+using namespace eld;
+
+extern "C" int eld_noise_packed(eld_ctx* ctx, const float* clean, float* noisy, int n, int h, int w,
+                                const eld_noise_params* params, uint32_t model_mask,
+                                uint64_t seed, uint64_t frame_id0, int clip01, void* stream)
+{
+    int rc = check_common(ctx, clean, noisy, n, h, w, params, model_mask, "eld_noise_packed");
+    if (rc < 0) return rc;
+    if (rc == 1) return ELD_OK;
+    ELD_CHECK_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t plane = (size_t)h * w;
+    const bool aligned = (w % 4 == 0) && ((reinterpret_cast<uintptr_t>(clean) | reinterpret_cast<uintptr_t>(noisy)) % 16 == 0);
+    for (int f0 = 0; f0 < n; f0 += kMaxFramesPerLaunch) {
+        const int nf = (n - f0 < kMaxFramesPerLaunch) ? n - f0 : kMaxFramesPerLaunch;
+        NoiseLaunch L{};
+        for (int f = 0; f < nf; ++f) L.fr[f] = make_consts(params[f0 + f]);
+        L.seed = seed; L.frame0 = frame_id0 + (uint64_t)f0; L.mask = model_mask; L.h = h; L.w = w; L.clip01 = clip01;
+        const float* src = clean + (size_t)f0 * 4 * plane;
+        float* dst = noisy + (size_t)f0 * 4 * plane;
+        const uint32_t quads = (uint32_t)((plane + 3) / 4);
+        dim3 grid((quads + 255) / 256, nf);
+        if (aligned) {
+            switch (model_mask) {
+#define X(M) case (M): launch_packed_vec<(M)>(grid, st, src, dst, L); break;
+                ELD_FOR_EACH_MASK(X)
+#undef X
+                default: launch_packed_vec<kRuntimeMask>(grid, st, src, dst, L); break;
+            }
+        } else {
+            noise_packed_generic_kernel<<<grid, 256, 0, st>>>(src, dst, L);
+        }
+        ELD_CHECK_CUDA(cudaGetLastError());
+        count_launch(ctx);
+    }
+    return ELD_OK;
+}
+
+extern "C" int eld_noise_mosaic(eld_ctx* ctx, const void* mosaic, int in_dtype, float black, float white,
+                                float* noisy, float* clean_out, int n, int H, int W,
+                                const eld_noise_params* params, uint32_t model_mask,
+                                uint64_t seed, uint64_t frame_id0, int clip01, void* stream)
+{
+    ELD_REQUIRE(H >= 0 && W >= 0 && H % 2 == 0 && W % 2 == 0, "eld_noise_mosaic: H=%d W=%d must be even", H, W);
+    ELD_REQUIRE(in_dtype == ELD_DT_U16 || in_dtype == ELD_DT_F32, "eld_noise_mosaic: in_dtype %d unsupported", in_dtype);
+    ELD_REQUIRE(white != black, "eld_noise_mosaic: white == black");
+    const int h = H / 2, w = W / 2;
+    int rc = check_common(ctx, mosaic, noisy, n, h, w, params, model_mask, "eld_noise_mosaic");
+    if (rc < 0) return rc;
+    if (rc == 1) return ELD_OK;
+    ELD_CHECK_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t plane = (size_t)h * w;
+    const size_t esz = in_dtype == ELD_DT_U16 ? 2 : 4;
+    uintptr_t al = reinterpret_cast<uintptr_t>(mosaic) | reinterpret_cast<uintptr_t>(noisy) | reinterpret_cast<uintptr_t>(clean_out);
+    const bool aligned = (W % 8 == 0) && (al % 16 == 0);
+    MosaicArgs M{ black, 1.0f / (white - black), H, W, in_dtype };
+    for (int f0 = 0; f0 < n; f0 += kMaxFramesPerLaunch) {
+        const int nf = (n - f0 < kMaxFramesPerLaunch) ? n - f0 : kMaxFramesPerLaunch;
+        NoiseLaunch L{};
+        for (int f = 0; f < nf; ++f) L.fr[f] = make_consts(params[f0 + f]);
+        L.seed = seed; L.frame0 = frame_id0 + (uint64_t)f0; L.mask = model_mask; L.h = h; L.w = w; L.clip01 = clip01;
+        const void* src = static_cast<const char*>(mosaic) + (size_t)f0 * H * W * esz;
+        float* dst = noisy + (size_t)f0 * 4 * plane;
+        float* cdst = clean_out ? clean_out + (size_t)f0 * 4 * plane : nullptr;
+        const uint32_t quads = (uint32_t)((plane + 3) / 4);
+        dim3 grid((quads + 255) / 256, nf);
+        if (aligned) {
+            if (in_dtype == ELD_DT_U16) {
+                switch (model_mask) {
+#define X(Mk) case (Mk): launch_mosaic_vec<(Mk), ELD_DT_U16>(grid, st, src, dst, cdst, M, L); break;
+                    ELD_FOR_EACH_MASK(X)
+#undef X
+                    default: launch_mosaic_vec<kRuntimeMask, ELD_DT_U16>(grid, st, src, dst, cdst, M, L); break;
+                }
+            } else {
+                launch_mosaic_vec<kRuntimeMask, ELD_DT_F32>(grid, st, src, dst, cdst, M, L);
+            }
+        } else {
+            noise_mosaic_generic_kernel<<<grid, 256, 0, st>>>(src, dst, cdst, M, L);
+        }
+        ELD_CHECK_CUDA(cudaGetLastError());
+        count_launch(ctx);
+    }
+    return ELD_OK;
+}

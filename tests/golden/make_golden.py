@@ -1,0 +1,143 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures under tests/golden/ by RUNNING THE UNMODIFIED REFERENCE.
+
+Run in the authoring container only (needs /root/reference):
+
+    python tests/golden/make_golden.py
+
+It imports /root/reference/noise.py (CWD must be the reference root because of the
+relative `camera_params/release` path, noise.py:187) and loads
+/root/reference/models/arch/Unet.py by file path (``import models`` drags in
+tensorboardX/rawpy).  Nothing here is shipped to the GPU box except the
+small files it writes; the GPU-side tests read only those files.
+
+Outputs
+  noise_kat.json      _sample_params pins (seed 0, every camera) + NoiseModelBase.__call__
+                      outputs for models P+g / p+g / g on the 4x8x8 ramp, seed 123
+  pack_kat.json       RawPacker.pack_raw_bayer on the 8x6 arange mosaic
+  unet_kat.npz        UNetSeeInDark(4,4) with torch.manual_seed(2018) default init:
+                      input (seed 7, 1x4x32x32), target (seed 8), output, L1 loss and
+                      per-parameter gradient sums/abs-sums, first-16 values of every param
+  camera_params.json  the calibration dictionaries of camera_params/release/*.npy as JSON
+                      (data, not code) so the GPU box needs no pickle and no reference tree
+"""
+import importlib.util
+import json
+import os
+import sys
+
+import numpy as np
+
+REF = '/root/reference'
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(os.path.dirname(HERE))
+
+
+def _jsonable(o):
+    if isinstance(o, dict):
+        return {k: _jsonable(v) for k, v in o.items()}
+    if isinstance(o, np.ndarray):
+        return o.astype(np.float64).tolist()
+    if isinstance(o, (np.floating, np.integer)):
+        return o.item()
+    return o
+
+
+def main():
+    import torch
+    os.chdir(REF)
+    sys.path.insert(0, REF)
+    import noise as refnoise  # the reference module, unmodified
+
+    cameras = ['CanonEOS5D4', 'CanonEOS70D', 'CanonEOS700D', 'NikonD850', 'SonyA7S2']
+
+    # ---- calibration data -> JSON ------------------------------------------------------
+    cam = {}
+    for c in cameras:
+        d = np.load(os.path.join(REF, 'camera_params', 'release', c + '_params.npy'),
+                    allow_pickle=True).item()
+        cam[c] = _jsonable(d)
+    pkg_dir = os.path.join(REPO, 'eld_b200', 'camera_params')
+    os.makedirs(pkg_dir, exist_ok=True)
+    with open(os.path.join(pkg_dir, 'camera_params.json'), 'w') as f:
+        json.dump(cam, f, indent=1, sort_keys=True)
+
+    # ---- noise KATs ---------------------------------------------------------------------
+    kat = {'numpy': np.__version__, 'sample_params_seed0': {}, 'call_seed123': {}}
+    for i, c in enumerate(cameras):
+        nm = refnoise.NoiseModel('P+g', include=i)
+        np.random.seed(0)
+        K, g, sat, ratio = nm._sample_params()
+        kat['sample_params_seed0'][c] = dict(K=float(K), g_scale=float(g), sat=int(sat), ratio=float(ratio))
+    # a stream of 5 successive parameter draws (pins RNG call ORDER, noise.py:202-223)
+    nm = refnoise.NoiseModel('P+g', include=4)
+    np.random.seed(2018)
+    kat['sample_params_seed2018_x5'] = [[float(v) for v in nm._sample_params()] for _ in range(5)]
+    # multi-camera choice (include=None): which camera comes out is part of the stream
+    nm_all = refnoise.NoiseModel('g')
+    np.random.seed(11)
+    kat['sample_params_allcams_seed11_x4'] = [[float(v) for v in nm_all._sample_params()] for _ in range(4)]
+
+    p = kat['sample_params_seed0']['SonyA7S2']
+    params = (p['K'], p['g_scale'], p['sat'], p['ratio'])
+    y = (np.arange(256).reshape(4, 8, 8).astype(np.float32)) / 256
+    for model in ['P+g', 'p+g', 'g', 'P', 'p', 'Pg']:
+        nm = refnoise.NoiseModel(model, include=4)
+        np.random.seed(123)
+        z = np.asarray(nm(y, params=params))
+        kat['call_seed123'][model] = dict(dtype=str(z.dtype), sum=float(z.sum()), z=z.astype(np.float64).ravel().tolist())
+    with open(os.path.join(HERE, 'noise_kat.json'), 'w') as f:
+        json.dump(kat, f)
+
+    # ---- pack KAT -------------------------------------------------------------------------
+    rp = refnoise.RawPacker('bayer')
+    m = np.arange(48).reshape(8, 6)
+    packed = rp.pack_raw_bayer(m)
+    back = rp.unpack_raw_bayer(packed)
+    assert (back == m).all()
+    m2 = (np.arange(16 * 12).reshape(16, 12) * 7 % 251).astype(np.uint16)
+    with open(os.path.join(HERE, 'pack_kat.json'), 'w') as f:
+        json.dump({'mosaic_8x6': m.tolist(), 'packed': packed.tolist(), 'dtype': str(packed.dtype),
+                   'mosaic_16x12': m2.tolist(), 'packed_16x12': rp.pack_raw_bayer(m2).tolist()}, f)
+
+    # ---- U-Net KAT ------------------------------------------------------------------------
+    spec = importlib.util.spec_from_file_location('ref_unet', os.path.join(REF, 'models', 'arch', 'Unet.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    torch.manual_seed(2018)
+    net = mod.UNetSeeInDark(4, 4)
+    nparam = sum(p.numel() for p in net.parameters())
+    torch.manual_seed(7)
+    x = torch.rand(1, 4, 32, 32)
+    torch.manual_seed(8)
+    t = torch.rand(1, 4, 32, 32)
+    torch.set_num_threads(1)
+    out = net(x)
+    loss = torch.nn.L1Loss()(out, t)
+    loss.backward()
+    arrays = dict(x=x.numpy(), target=t.numpy(), out=out.detach().numpy(), loss=np.float64(loss.item()),
+                  nparam=np.int64(nparam))
+    names = []
+    for k, v in net.state_dict().items():
+        names.append(k)
+        arrays['head_' + k] = v.reshape(-1)[:16].numpy().copy()
+        arrays['sum_' + k] = np.float64(v.double().sum().item())
+    for k, v in net.named_parameters():
+        arrays['gsum_' + k] = np.float64(v.grad.double().sum().item())
+        arrays['gabs_' + k] = np.float64(v.grad.double().abs().sum().item())
+    arrays['names'] = np.array(names)
+    # deconv == 1x1 conv + pixel_shuffle identity measured on the reference layer
+    up = net.upv9
+    a = torch.rand(1, 64, 6, 5)
+    ref_up = up(a)
+    w = up.weight  # (Cin, Cout, 2, 2)
+    w1 = w.permute(1, 2, 3, 0).reshape(32 * 4, 64, 1, 1)
+    alt = torch.nn.functional.pixel_shuffle(
+        torch.nn.functional.conv2d(a, w1, up.bias.repeat_interleave(4)), 2)
+    arrays['deconv_identity_err'] = np.float64((ref_up - alt).abs().max().item())
+    np.savez_compressed(os.path.join(HERE, 'unet_kat.npz'), **arrays)
+    print('wrote goldens; nparam', nparam, 'loss', loss.item(), 'deconv err', arrays['deconv_identity_err'])
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,98 @@
+"""CPU tests of the boundary: libeld_b200.so loads, exports every symbol include/*.h declares,
+fails loudly without a GPU, and the host-side mirror of the reference interface behaves like
+the reference (noise.py:175-225) - no compute calls here."""
+import ctypes
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+from tests.conftest import REPO, has_gpu
+
+
+def _declared_functions():
+    names = []
+    inc = os.path.join(REPO, 'include')
+    for fn in sorted(os.listdir(inc)):
+        src = open(os.path.join(inc, fn)).read()
+        src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+        src = re.sub(r'//[^\n]*', '', src)
+        src = re.sub(r'^\s*#.*$', '', src, flags=re.M)
+        for m in re.finditer(r'\b(eld_[a-z0-9_]+)\s*\(', src):
+            if m.group(1) not in names:
+                names.append(m.group(1))
+    return names
+
+
+def test_library_exports_every_declared_symbol():
+    from eld_b200 import _lib
+    lib = _lib.load()
+    names = _declared_functions()
+    assert 'eld_noise_packed' in names and 'eld_ctx_create' in names
+    for n in names:
+        assert hasattr(lib, n), 'libeld_b200.so does not export %s' % n
+    assert lib.eld_abi_version() == 1
+
+
+@pytest.mark.skipif(has_gpu(), reason='checks the no-GPU failure mode')
+def test_no_gpu_fails_loudly():
+    from eld_b200 import _lib
+    lib = _lib.load()
+    h = ctypes.c_void_p()
+    rc = lib.eld_ctx_create(0, ctypes.byref(h))
+    assert rc != 0 and h.value is None
+    assert b'no CPU fallback' in lib.eld_last_error() or b'CUDA' in lib.eld_last_error()
+    from eld_b200.noise import NoiseModel
+    nm = NoiseModel('g', include=4, verbose=False)
+    with pytest.raises(_lib.EldError):
+        nm(np.zeros((4, 8, 8), np.float32), params=(1.0, 1.0, 15583, 100.0))
+
+
+def test_params_struct_layout():
+    from eld_b200 import _lib
+    assert ctypes.sizeof(_lib.NoiseParams) == 48
+
+
+def test_model_mask_substring_semantics():
+    """noise.py:158-166: 'P' in model wins over 'p'; '+' and order are irrelevant."""
+    from eld_b200._lib import model_mask
+    assert model_mask('P+g') == 0x05 and model_mask('Pg') == 0x05 and model_mask('g+P') == 0x05
+    assert model_mask('p+g') == 0x06 and model_mask('g') == 0x04 and model_mask('P') == 0x01
+    assert model_mask('Pp') == 0x01
+    assert model_mask('P+G+B+R+U') == 0x79
+
+
+def test_noise_model_host_side_matches_reference_golden(golden_dir):
+    """_sample_params: same numpy-RNG call order and values as the reference (golden KAT)."""
+    from eld_b200.noise import NoiseModel
+    kat = json.load(open(os.path.join(golden_dir, 'noise_kat.json')))
+    cams = ['CanonEOS5D4', 'CanonEOS70D', 'CanonEOS700D', 'NikonD850', 'SonyA7S2']
+    for i, cam in enumerate(cams):
+        nm = NoiseModel('P+g', include=i, verbose=False)
+        assert nm.cameras == [cam]
+        np.random.seed(0)
+        K, g, sat, ratio = nm._sample_params()
+        gold = kat['sample_params_seed0'][cam]
+        assert (K, g, sat, ratio) == (gold['K'], gold['g_scale'], gold['sat'], gold['ratio'])
+    nm = NoiseModel('g', verbose=False)
+    np.random.seed(11)
+    got = [[float(v) for v in nm._sample_params()] for _ in range(4)]
+    assert got == kat['sample_params_allcams_seed11_x4']
+
+
+def test_noise_model_ctor_contract():
+    from eld_b200.noise import NoiseModel
+    with pytest.raises(AssertionError):
+        NoiseModel('g', include=1, exclude=2, verbose=False)      # noise.py:178
+    with pytest.raises(AssertionError):
+        NoiseModel('g', cfa='foveon', verbose=False)              # noise.py:177
+    nm = NoiseModel('g', exclude=0, verbose=False)
+    assert 'CanonEOS5D4' not in nm.cameras and len(nm.cameras) == 4
+    nm.model = 'P+g'                                              # .model is a mutable str attribute
+    full = NoiseModel('P+G+B+R+U', include=4, verbose=False)
+    np.random.seed(3)
+    p = full._sample_params_full()
+    assert set(p) >= {'K', 'g_scale', 'G_scale', 'G_lambda', 'R_scale', 'color_bias', 'ratio', 'q_step'}
+    assert 100 <= p['ratio'] <= 300 and 0.1 <= p['K'] <= 30 and len(p['color_bias']) == 4
