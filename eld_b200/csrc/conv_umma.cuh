@@ -1,0 +1,225 @@
+// conv_umma.cuh - persistent, warp-specialised tcgen05 implicit-GEMM tile for the U-Net's
+// conv3x3 / deconv2x2 (fprop and dgrad) on NHWC bf16 activations.
+//
+//   D[128 pixels x n_tile] (f32, TMEM)  +=  A[128 pixels x K] (bf16, smem via TMA)  *  B[n_tile x K]^T
+//
+// M tile  = an 8 x 16 pixel patch of one image (TMA box {kc, 16, 8}); every filter tap is one more
+//           box at shifted coordinates - TMA zero-fills out-of-image pixels, which IS the padding.
+// K       = taps x cin, walked in chunks of kc = 32 or 64 channels (one 64 B / 128 B swizzled row per
+//           pixel), each chunk = kc/16 tcgen05.mma.kind::f16 instructions (M=128, N=n_tile, K=16).
+// roles   = warp 0: TMA producer | warp 1: MMA issuer (one elected lane) | warps 2-5: epilogue
+//           (tcgen05.ld -> bias / LeakyReLU / mask -> bf16 -> global).  Two TMEM accumulators so the
+//           epilogue of tile i overlaps the MMAs of tile i+1.
+#pragma once
+#include "umma.cuh"
+#include <cuda_bf16.h>
+
+namespace eld {
+
+enum { A_CONV = 0, A_GATHER = 1 };
+enum { EPI_STORE = 0, EPI_SHUFFLE = 1 };
+enum { ACT_NONE = 0, ACT_LRELU = 1, ACT_MASK = 2 };
+
+struct ConvGemmParams {
+    int n_img, H, W;      // output pixel grid (M space); H % 8 == 0, W % 16 == 0
+    int tiles_x, tiles_y;
+    int taps, a_mode;     // 9/1 with A_CONV, 4 with A_GATHER
+    int cin;              // K channels per tap
+    int a_c0;             // first channel inside the A tensor (concat buffers)
+    int kc;               // 32 or 64
+    int n_total, n_tile;  // GEMM N and per-CTA N (n_tile % 32 == 0, <= 256)
+    int epi_mode, act;
+    __nv_bfloat16* out;
+    int out_pitch, out_c0;
+    const float* bias;    // per GEMM column (EPI_SHUFFLE: per cout, column % cout)
+    const __nv_bfloat16* aux;
+    int aux_pitch, aux_c0;
+    int cout;             // EPI_SHUFFLE: channels per sub-pixel
+    int stages;
+    int tmem_cols;
+};
+
+constexpr int kConvThreads = 192;
+
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const ConvGemmParams p)
+{
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = ptx::smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+
+    const int a_bytes = 128 * p.kc * 2;
+    const int b_bytes = p.n_tile * p.kc * 2;
+    const int stage_bytes = a_bytes + b_bytes;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+    uint64_t* empty = full + p.stages;
+    uint64_t* tmem_full = empty + p.stages;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_tiles = p.n_total / p.n_tile;
+    const int m_tiles = p.n_img * p.tiles_y * p.tiles_x;
+    const int total_tiles = m_tiles * n_tiles;
+    const int kchunks = p.cin / p.kc;
+    const int ksteps = p.taps * kchunks;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&tmA);
+        ptx::prefetch_tmap(&tmB);
+        for (int s = 0; s < p.stages; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tmem_full[a], 1); ptx::mbar_init(&tmem_empty[a], 4); }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 2) ptx::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int m_tile = tile / n_tiles, n_t = tile - m_tile * n_tiles;
+                const int tx = m_tile % p.tiles_x;
+                const int ty = (m_tile / p.tiles_x) % p.tiles_y;
+                const int img = m_tile / (p.tiles_x * p.tiles_y);
+                const int x0 = tx * 16, y0 = ty * 8;
+                for (int tap = 0; tap < p.taps; ++tap) {
+                    for (int kcI = 0; kcI < kchunks; ++kcI, ++it) {
+                        const int s = it % p.stages;
+                        const uint32_t ph = (it / p.stages) & 1u;
+                        ptx::mbar_wait(&empty[s], ph ^ 1u);
+                        ptx::mbar_arrive_expect_tx(&full[s], (uint32_t)stage_bytes);
+                        uint8_t* sa = smem + (size_t)s * stage_bytes;
+                        uint8_t* sb = sa + a_bytes;
+                        const int c = p.a_c0 + kcI * p.kc;
+                        if (p.a_mode == A_CONV) {
+                            const int dx = (p.taps == 9) ? (tap % 3) - 1 : 0;
+                            const int dy = (p.taps == 9) ? (tap / 3) - 1 : 0;
+                            ptx::tma_load_5d(sa, &tmA, &full[s], c, x0 + dx, y0 + dy, img, 0);
+                        } else {
+                            ptx::tma_load_5d(sa, &tmA, &full[s], c, tap & 1, x0, tap >> 1, img * p.H + y0);
+                        }
+                        ptx::tma_load_2d(sb, &tmB, &full[s], tap * p.cin + kcI * p.kc, n_t * p.n_tile);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        const uint32_t idesc = ptx::make_idesc_bf16(128, (uint32_t)p.n_tile, 0, 0);
+        const uint32_t layout = (p.kc == 64) ? ptx::LAYOUT_SW128 : ptx::LAYOUT_SW64;
+        const uint32_t sbo = (p.kc == 64) ? 1024u : 512u;
+        uint32_t it = 0, tile_it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_it) {
+            const uint32_t acc = tile_it & 1u;
+            const uint32_t acc_ph = (tile_it >> 1) & 1u;
+            ptx::mbar_wait(&tmem_empty[acc], acc_ph ^ 1u);
+            ptx::tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.n_tile;
+            for (int ks = 0; ks < ksteps; ++ks, ++it) {
+                const int s = it % p.stages;
+                const uint32_t ph = (it / p.stages) & 1u;
+                ptx::mbar_wait(&full[s], ph);
+                ptx::tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t a_addr = ptx::smem_u32(smem + (size_t)s * stage_bytes);
+                    const uint32_t b_addr = a_addr + (uint32_t)a_bytes;
+                    for (int k = 0; k < p.kc / 16; ++k) {
+                        const uint64_t ad = ptx::make_smem_desc(a_addr + k * 32, 16, sbo, layout);
+                        const uint64_t bd = ptx::make_smem_desc(b_addr + k * 32, 16, sbo, layout);
+                        ptx::umma_bf16(d_tmem, ad, bd, idesc, (ks | k) != 0 ? 1u : 0u);
+                    }
+                    ptx::umma_commit(&empty[s]);
+                    if (ks == ksteps - 1) ptx::umma_commit(&tmem_full[acc]);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        const int q = warp & 3;                // TMEM lane quarter this warp may read
+        const int m = q * 32 + lane;           // pixel inside the 8x16 patch
+        const int py = m >> 4, px = m & 15;
+        uint32_t tile_it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_it) {
+            const int m_tile = tile / n_tiles, n_t = tile - m_tile * n_tiles;
+            const int tx = m_tile % p.tiles_x;
+            const int ty = (m_tile / p.tiles_x) % p.tiles_y;
+            const int img = m_tile / (p.tiles_x * p.tiles_y);
+            const int x = tx * 16 + px, y = ty * 8 + py;
+            const uint32_t acc = tile_it & 1u;
+            const uint32_t acc_ph = (tile_it >> 1) & 1u;
+            ptx::mbar_wait(&tmem_full[acc], acc_ph);
+            ptx::tc_fence_after();
+            const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)p.n_tile;
+            for (int c32 = 0; c32 < p.n_tile / 32; ++c32) {
+                uint32_t r[32];
+                ptx::tmem_ld32(t_addr + c32 * 32, r);
+                ptx::tmem_ld_wait();
+                const int col = n_t * p.n_tile + c32 * 32;    // first GEMM column of this chunk
+                __nv_bfloat16* dst;
+                int bcol;
+                if (p.epi_mode == EPI_STORE) {
+                    dst = p.out + ((size_t)(img * p.H + y) * p.W + x) * p.out_pitch + p.out_c0 + col;
+                    bcol = col;
+                } else {
+                    const int sub = col / p.cout, co = col - sub * p.cout;   // sub = kh*2 + kw
+                    const int oy = 2 * y + (sub >> 1), ox = 2 * x + (sub & 1);
+                    dst = p.out + ((size_t)(img * 2 * p.H + oy) * (2 * p.W) + ox) * p.out_pitch + p.out_c0 + co;
+                    bcol = co;
+                }
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                if (p.bias) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] += __ldg(p.bias + bcol + j);
+                }
+                if (p.act == ACT_LRELU) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.2f * v[j]);
+                } else if (p.act == ACT_MASK) {
+                    const uint4* ap = reinterpret_cast<const uint4*>(
+                        p.aux + ((size_t)(img * p.H + y) * p.W + x) * p.aux_pitch + p.aux_c0 + col);
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        const uint4 a = __ldg(ap + g);
+                        const uint32_t aw[4] = { a.x, a.y, a.z, a.w };
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            // bf16 sign bits: activation > 0 <=> pre-activation > 0 (LeakyReLU keeps sign)
+                            const bool pos_lo = !(aw[j] & 0x8000u) && (aw[j] & 0x7FFFu);
+                            const bool pos_hi = !(aw[j] & 0x80000000u) && (aw[j] & 0x7FFF0000u);
+                            v[g * 8 + 2 * j] *= pos_lo ? 1.0f : 0.2f;
+                            v[g * 8 + 2 * j + 1] *= pos_hi ? 1.0f : 0.2f;
+                        }
+                    }
+                }
+                uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    uint32_t w[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const __nv_bfloat162 h = __floats2bfloat162_rn(v[g * 8 + 2 * j], v[g * 8 + 2 * j + 1]);
+                        w[j] = *reinterpret_cast<const uint32_t*>(&h);
+                    }
+                    d4[g] = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+}  // namespace eld

@@ -1,0 +1,186 @@
+// unet_prims.cu - host side of the tcgen05 conv/deconv tiles: TMA tensor-map construction, launch
+// geometry, weight packing, and the C-ABI primitives (include/eld_b200_unet.h).
+#include "common.cuh"
+#include "conv_umma.cuh"
+#include "unet_prims.h"
+
+namespace eld {
+
+static int encode(eld_ctx* ctx, CUtensorMap* map, const void* ptr, int rank, const cuuint64_t* dims,
+                  const cuuint64_t* strides_bytes, const cuuint32_t* box, int inner_bytes)
+{
+    cuuint32_t estr[5] = { 1, 1, 1, 1, 1 };
+    CUtensorMapSwizzle sw = inner_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                          : inner_bytes == 64  ? CU_TENSOR_MAP_SWIZZLE_64B
+                          : inner_bytes == 32  ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
+    CUresult r = ctx->encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr),
+                                   dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d): rank %d dims %llu,%llu,%llu box %u,%u,%u inner %d B",
+                  (int)r, rank, (unsigned long long)dims[0], (unsigned long long)dims[1],
+                  (unsigned long long)(rank > 2 ? dims[2] : 0), box[0], box[1], rank > 2 ? box[2] : 0, inner_bytes);
+        return ELD_E_CUDA;
+    }
+    return ELD_OK;
+}
+
+int launch_conv_gemm(eld_ctx* ctx, const GemmOp& op, cudaStream_t st)
+{
+    ELD_REQUIRE(op.H % 8 == 0 && op.W % 16 == 0, "conv tile: H=%d must be a multiple of 8 and W=%d of 16", op.H, op.W);
+    ELD_REQUIRE(op.cin % 32 == 0, "conv tile: cin=%d must be a multiple of 32", op.cin);
+    ELD_REQUIRE(op.n_total % 32 == 0, "conv tile: GEMM N=%d must be a multiple of 32", op.n_total);
+    ELD_REQUIRE(op.a_pitch % 8 == 0 && op.out_pitch % 8 == 0, "conv tile: pitches must be multiples of 8 channels");
+    ConvGemmParams p{};
+    p.n_img = op.n_img; p.H = op.H; p.W = op.W;
+    p.tiles_x = op.W / 16; p.tiles_y = op.H / 8;
+    p.taps = op.taps; p.a_mode = op.a_mode; p.cin = op.cin; p.a_c0 = op.a_c0;
+    p.kc = (op.cin % 64 == 0) ? 64 : 32;
+    p.n_total = op.n_total;
+    p.n_tile = op.n_total <= 256 ? op.n_total : 256;
+    ELD_REQUIRE(op.n_total % p.n_tile == 0, "conv tile: N=%d not divisible by tile %d", op.n_total, p.n_tile);
+    p.epi_mode = op.epi_mode; p.act = op.act;
+    p.out = static_cast<__nv_bfloat16*>(op.out); p.out_pitch = op.out_pitch; p.out_c0 = op.out_c0;
+    p.bias = op.bias;
+    p.aux = static_cast<const __nv_bfloat16*>(op.aux); p.aux_pitch = op.aux_pitch; p.aux_c0 = op.aux_c0;
+    p.cout = op.cout;
+    const int stage_bytes = (128 + p.n_tile) * p.kc * 2;
+    int stages = (200 * 1024) / stage_bytes;
+    if (stages > 8) stages = 8;
+    if (stages < 2) stages = 2;
+    p.stages = stages;
+    int cols = 32;
+    while (cols < 2 * p.n_tile) cols *= 2;
+    p.tmem_cols = cols;
+
+    CUtensorMap tmA, tmB;
+    const cuuint64_t eb = 2;  // bf16
+    if (op.a_mode == A_CONV) {
+        cuuint64_t dims[5] = { (cuuint64_t)op.a_pitch, (cuuint64_t)op.W, (cuuint64_t)op.H, (cuuint64_t)op.n_img, 1 };
+        cuuint64_t str[4] = { op.a_pitch * eb, (cuuint64_t)op.W * op.a_pitch * eb,
+                              (cuuint64_t)op.H * op.W * op.a_pitch * eb,
+                              (cuuint64_t)op.n_img * op.H * op.W * op.a_pitch * eb };
+        cuuint32_t box[5] = { (cuuint32_t)p.kc, 16, 8, 1, 1 };
+        int rc = encode(ctx, &tmA, op.a, 5, dims, str, box, p.kc * 2);
+        if (rc) return rc;
+    } else {
+        // fine tensor [n][2H][2W][pitch] viewed as (c, kw, x, kh, n*H + y)
+        cuuint64_t dims[5] = { (cuuint64_t)op.a_pitch, 2, (cuuint64_t)op.W, 2, (cuuint64_t)op.n_img * op.H };
+        cuuint64_t str[4] = { op.a_pitch * eb, 2 * op.a_pitch * eb, (cuuint64_t)2 * op.W * op.a_pitch * eb,
+                              (cuuint64_t)4 * op.W * op.a_pitch * eb };
+        cuuint32_t box[5] = { (cuuint32_t)p.kc, 1, 16, 1, 8 };
+        int rc = encode(ctx, &tmA, op.a, 5, dims, str, box, p.kc * 2);
+        if (rc) return rc;
+    }
+    {
+        const cuuint64_t ktot = (cuuint64_t)op.taps * op.cin;
+        cuuint64_t dims[2] = { ktot, (cuuint64_t)op.n_total };
+        cuuint64_t str[1] = { ktot * eb };
+        cuuint32_t box[2] = { (cuuint32_t)p.kc, (cuuint32_t)p.n_tile };
+        int rc = encode(ctx, &tmB, op.b, 2, dims, str, box, p.kc * 2);
+        if (rc) return rc;
+    }
+    const size_t smem = (size_t)stages * stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    ELD_CHECK_CUDA(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int total_tiles = op.n_img * p.tiles_x * p.tiles_y * (p.n_total / p.n_tile);
+    const int grid = total_tiles < ctx->num_sms ? total_tiles : ctx->num_sms;
+    conv_umma_kernel<<<grid, kConvThreads, smem, st>>>(tmA, tmB, p);
+    ELD_CHECK_CUDA(cudaGetLastError());
+    count_launch(ctx);
+    return ELD_OK;
+}
+
+// ---- weight packing: fp32 master (PyTorch layout) -> bf16 K-major GEMM operand -------------------
+__global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out,
+                                    int cout, int cin, int kind)
+{
+    const int ksz = (kind == PACK_CONV_FPROP || kind == PACK_CONV_DGRAD) ? 9 : 4;
+    const size_t total = (size_t)cout * cin * ksz;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        float v;
+        if (kind == PACK_CONV_FPROP) {            // out[co][t*cin + ci] = W[co][ci][kh][kw], t = kh*3+kw
+            const int ci = i % cin, t = (i / cin) % 9, co = i / ((size_t)cin * 9);
+            v = w[((size_t)co * cin + ci) * 9 + t];
+        } else if (kind == PACK_CONV_DGRAD) {     // out[ci][t'*cout + co] = W[co][ci][2-kh'][2-kw'] = W[..][8-t']
+            const int co = i % cout, t = (i / cout) % 9, ci = i / ((size_t)cout * 9);
+            v = w[((size_t)co * cin + ci) * 9 + (8 - t)];
+        } else if (kind == PACK_DECONV_FPROP) {   // out[(s*cout + co)][ci] = Wt[ci][co][kh][kw], s = kh*2+kw
+            const int ci = i % cin, co = (i / cin) % cout, s = i / ((size_t)cin * cout);
+            v = w[((size_t)ci * cout + co) * 4 + s];
+        } else {                                  // PACK_DECONV_DGRAD: out[ci][s*cout + co] = Wt[ci][co][s]
+            const int co = i % cout, s = (i / cout) % 4, ci = i / ((size_t)cout * 4);
+            v = w[((size_t)ci * cout + co) * 4 + s];
+        }
+        out[i] = __float2bfloat16_rn(v);
+    }
+}
+
+int launch_pack_weights(eld_ctx* ctx, const float* w, void* out, int cout, int cin, int kind, cudaStream_t st)
+{
+    const size_t total = (size_t)cout * cin * ((kind == PACK_CONV_FPROP || kind == PACK_CONV_DGRAD) ? 9 : 4);
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 4 * ctx->num_sms) blocks = 4 * ctx->num_sms;
+    pack_weights_kernel<<<blocks, 256, 0, st>>>(w, static_cast<__nv_bfloat16*>(out), cout, cin, kind);
+    ELD_CHECK_CUDA(cudaGetLastError());
+    count_launch(ctx);
+    return ELD_OK;
+}
+
+}  // namespace eld
+
+using namespace eld;
+
+extern "C" int eld_pack_weights(eld_ctx* ctx, const float* w, void* packed, int cout, int cin, int kind, void* stream)
+{
+    ELD_REQUIRE(ctx && w && packed, "eld_pack_weights: NULL argument");
+    ELD_REQUIRE(kind >= 0 && kind <= 3 && cout > 0 && cin > 0, "eld_pack_weights: bad kind/shape");
+    ELD_CHECK_CUDA(cudaSetDevice(ctx->device));
+    return launch_pack_weights(ctx, w, packed, cout, cin, kind, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int eld_conv3x3_bf16(eld_ctx* ctx, const void* x, int x_pitch, int x_c0, int cin, const void* w_packed,
+                                const float* bias, void* y, int y_pitch, int y_c0, int cout, int n, int h, int w,
+                                int act, const void* aux, int aux_pitch, int aux_c0, void* stream)
+{
+    ELD_REQUIRE(ctx && x && w_packed && y, "eld_conv3x3_bf16: NULL argument");
+    ELD_REQUIRE(act >= 0 && act <= 2 && (act != ACT_MASK || aux), "eld_conv3x3_bf16: bad act / missing aux");
+    ELD_CHECK_CUDA(cudaSetDevice(ctx->device));
+    GemmOp op{};
+    op.a = x; op.a_pitch = x_pitch; op.a_c0 = x_c0; op.a_mode = A_CONV; op.taps = 9; op.cin = cin;
+    op.n_img = n; op.H = h; op.W = w;
+    op.b = w_packed; op.n_total = cout; op.cout = cout;
+    op.epi_mode = EPI_STORE; op.act = act; op.out = y; op.out_pitch = y_pitch; op.out_c0 = y_c0; op.bias = bias;
+    op.aux = aux; op.aux_pitch = aux_pitch; op.aux_c0 = aux_c0;
+    return launch_conv_gemm(ctx, op, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int eld_deconv2x2_bf16(eld_ctx* ctx, const void* x, int x_pitch, int x_c0, int cin, const void* w_packed,
+                                  const float* bias, void* y, int y_pitch, int y_c0, int cout, int n, int h, int w,
+                                  void* stream)
+{
+    ELD_REQUIRE(ctx && x && w_packed && y, "eld_deconv2x2_bf16: NULL argument");
+    ELD_CHECK_CUDA(cudaSetDevice(ctx->device));
+    GemmOp op{};
+    op.a = x; op.a_pitch = x_pitch; op.a_c0 = x_c0; op.a_mode = A_CONV; op.taps = 1; op.cin = cin;
+    op.n_img = n; op.H = h; op.W = w;
+    op.b = w_packed; op.n_total = 4 * cout; op.cout = cout;
+    op.epi_mode = EPI_SHUFFLE; op.act = ACT_NONE; op.out = y; op.out_pitch = y_pitch; op.out_c0 = y_c0; op.bias = bias;
+    return launch_conv_gemm(ctx, op, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int eld_deconv2x2_dgrad_bf16(eld_ctx* ctx, const void* dy, int dy_pitch, int dy_c0, int cout,
+                                        const void* w_packed, void* dx, int dx_pitch, int dx_c0, int cin,
+                                        int n, int h, int w, int act, const void* aux, int aux_pitch, int aux_c0,
+                                        void* stream)
+{
+    ELD_REQUIRE(ctx && dy && w_packed && dx, "eld_deconv2x2_dgrad_bf16: NULL argument");
+    ELD_REQUIRE(act == ACT_NONE || (act == ACT_MASK && aux), "eld_deconv2x2_dgrad_bf16: act must be 0 or 2 (+aux)");
+    ELD_CHECK_CUDA(cudaSetDevice(ctx->device));
+    GemmOp op{};
+    op.a = dy; op.a_pitch = dy_pitch; op.a_c0 = dy_c0; op.a_mode = A_GATHER; op.taps = 4; op.cin = cout;
+    op.n_img = n; op.H = h; op.W = w;
+    op.b = w_packed; op.n_total = cin; op.cout = cin;
+    op.epi_mode = EPI_STORE; op.act = act; op.out = dx; op.out_pitch = dx_pitch; op.out_c0 = dx_c0; op.bias = nullptr;
+    op.aux = aux; op.aux_pitch = aux_pitch; op.aux_c0 = aux_c0;
+    return launch_conv_gemm(ctx, op, static_cast<cudaStream_t>(stream));
+}

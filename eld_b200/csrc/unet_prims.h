@@ -1,0 +1,28 @@
+// unet_prims.h - internal (C++) interface of the tcgen05 tiles, shared by the C-ABI primitives and
+// the U-Net engine.
+#pragma once
+#include "common.cuh"
+
+namespace eld {
+
+enum { PACK_CONV_FPROP = 0, PACK_CONV_DGRAD = 1, PACK_DECONV_FPROP = 2, PACK_DECONV_DGRAD = 3 };
+
+struct GemmOp {
+    const void* a;      // bf16 NHWC activation (or gradient) tensor
+    int a_pitch, a_c0;  // channels per pixel in memory, first channel used
+    int a_mode, taps, cin;
+    int n_img, H, W;    // M space (output pixel grid)
+    const void* b;      // bf16 packed weights [n_total][taps*cin]
+    int n_total, cout;
+    int epi_mode, act;
+    void* out;
+    int out_pitch, out_c0;
+    const float* bias;
+    const void* aux;
+    int aux_pitch, aux_c0;
+};
+
+int launch_conv_gemm(eld_ctx* ctx, const GemmOp& op, cudaStream_t st);
+int launch_pack_weights(eld_ctx* ctx, const float* w, void* out, int cout, int cin, int kind, cudaStream_t st);
+
+}  // namespace eld

@@ -1,5 +1,43 @@
-/* eld_b200_unet.h - U-Net part of the C ABI (included by eld_b200.h). */
+/* eld_b200_unet.h - U-Net part of the C ABI (included by eld_b200.h).
+ *
+ * Replaces what PyTorch-eager dispatches to cuDNN/ATen for UNetSeeInDark (reference
+ * models/arch/Unet.py:6-91) and ELDModel.optimize_parameters (models/ELD_model.py:469-475).
+ * Activations are NHWC bf16 with an explicit channel pitch (so a concat buffer is just a wider
+ * pitch: torch.cat at Unet.py:69,74,79,84 disappears); weights are bf16 K-major GEMM operands
+ * packed from the fp32 PyTorch-layout master copy by eld_pack_weights.
+ */
 #ifndef ELD_B200_UNET_H
 #define ELD_B200_UNET_H
-/* filled in below as the U-Net kernels land */
+
+/* kinds for eld_pack_weights: source layout is PyTorch's (Conv2d OIHW, ConvTranspose2d IOHW) */
+#define ELD_PACK_CONV_FPROP    0  /* [cout][ (kh*3+kw)*cin + ci ]            <- W[co][ci][kh][kw]      */
+#define ELD_PACK_CONV_DGRAD    1  /* [cin ][ (kh*3+kw)*cout + co ]           <- W[co][ci][2-kh][2-kw]  */
+#define ELD_PACK_DECONV_FPROP  2  /* [(kh*2+kw)*cout + co][ci]               <- Wt[ci][co][kh][kw]     */
+#define ELD_PACK_DECONV_DGRAD  3  /* [ci][(kh*2+kw)*cout + co]               <- Wt[ci][co][kh][kw]     */
+int eld_pack_weights(eld_ctx* ctx, const float* w, void* packed_bf16, int cout, int cin, int kind, void* stream);
+
+#define ELD_ACT_NONE  0
+#define ELD_ACT_LRELU 1  /* max(0.2x, x)  (Unet.py:102-104), fused into the producing tile           */
+#define ELD_ACT_MASK  2  /* multiply by d lrelu/dx of `aux` (1 if aux>0 else 0.2): backward of lrelu */
+
+/* y[n,h,w,y_c0:y_c0+cout] = act( conv3x3_pad1(x[n,h,w,x_c0:x_c0+cin]) + bias )   nn.Conv2d(k=3,p=1), Unet.py:11-44.
+ * With ELD_PACK_CONV_DGRAD weights (cin/cout swapped) the same tile is the data gradient.
+ * h % 8 == 0, w % 16 == 0, cin % 32 == 0, cout % 32 == 0.  bias may be NULL. */
+int eld_conv3x3_bf16(eld_ctx* ctx, const void* x, int x_pitch, int x_c0, int cin, const void* w_packed,
+                     const float* bias, void* y, int y_pitch, int y_c0, int cout, int n, int h, int w,
+                     int act, const void* aux, int aux_pitch, int aux_c0, void* stream);
+
+/* nn.ConvTranspose2d(cin, cout, 2, stride=2) (Unet.py:30,34,38,42) as GEMM + pixel-shuffle epilogue:
+ * y[n, 2h+kh, 2w+kw, y_c0+co] = sum_ci x[n,h,w,ci] Wt[ci][co][kh][kw] + bias[co].  (h, w) = INPUT grid. */
+int eld_deconv2x2_bf16(eld_ctx* ctx, const void* x, int x_pitch, int x_c0, int cin, const void* w_packed,
+                       const float* bias, void* y, int y_pitch, int y_c0, int cout, int n, int h, int w,
+                       void* stream);
+
+/* data gradient of the above: dx[n,h,w,ci] = sum_{kh,kw,co} dy[n,2h+kh,2w+kw,co] Wt[ci][co][kh][kw],
+ * optionally times the LeakyReLU derivative of aux (the deconv input activation). */
+int eld_deconv2x2_dgrad_bf16(eld_ctx* ctx, const void* dy, int dy_pitch, int dy_c0, int cout,
+                             const void* w_packed, void* dx, int dx_pitch, int dx_c0, int cin,
+                             int n, int h, int w, int act, const void* aux, int aux_pitch, int aux_c0,
+                             void* stream);
+
 #endif

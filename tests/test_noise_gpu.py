@@ -51,7 +51,7 @@ def _sigma(y, p, mask):
         extra = 0.0
     ydn = np.maximum(y, 0) * sat / ratio
     var = (K * ydn if mask & 3 else 0) + (g * g if mask & 4 else 0) + extra
-    return np.sqrt(var + 1e-12) * ratio / sat
+    return np.broadcast_to(np.sqrt(var + 1e-12) * ratio / sat, y.shape)
 
 
 def _compare(gpu, ref, y, p, mask):
