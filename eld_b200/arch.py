@@ -1,0 +1,181 @@
+"""Drop-in for the reference's netG factory seam: `arch.unet(in_channels, out_channels) -> nn.Module`
+(reference models/arch/__init__.py:6-7, models/arch/Unet.py:6-91).
+
+The module keeps the reference's parameter names / shapes / default init (state_dict keys
+conv{1..9}_{1,2}.{weight,bias}, upv{6..9}.*, conv10_1.*; Conv2d OIHW, ConvTranspose2d IOHW) so
+released checkpoints load, but all parameters are views into ONE flat fp32 buffer and the forward
+runs the tcgen05 engine behind the C ABI (csrc/unet_engine.cu) on NHWC bf16 activations.
+"""
+import ctypes
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+_SPEC = [('conv1_1', 'c', 4, 32), ('conv1_2', 'c', 32, 32), ('conv2_1', 'c', 32, 64), ('conv2_2', 'c', 64, 64),
+         ('conv3_1', 'c', 64, 128), ('conv3_2', 'c', 128, 128), ('conv4_1', 'c', 128, 256), ('conv4_2', 'c', 256, 256),
+         ('conv5_1', 'c', 256, 512), ('conv5_2', 'c', 512, 512), ('upv6', 'd', 512, 256), ('conv6_1', 'c', 512, 256),
+         ('conv6_2', 'c', 256, 256), ('upv7', 'd', 256, 128), ('conv7_1', 'c', 256, 128), ('conv7_2', 'c', 128, 128),
+         ('upv8', 'd', 128, 64), ('conv8_1', 'c', 128, 64), ('conv8_2', 'c', 64, 64), ('upv9', 'd', 64, 32),
+         ('conv9_1', 'c', 64, 32), ('conv9_2', 'c', 32, 32), ('conv10_1', 'o', 32, 4)]
+
+
+def _st():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class UNetSeeInDark(nn.Module):
+    """B200-native UNetSeeInDark.  Only (in_channels, out_channels) = (4, 4) - the raw->raw path
+    train_syn.py uses (--channels 4, stage_in = stage_out = raw) - is built."""
+
+    def __init__(self, in_channels=4, out_channels=4):
+        super().__init__()
+        if (in_channels, out_channels) != (4, 4):
+            raise NotImplementedError('the B200 engine implements the raw Bayer path: in=out=4 channels')
+        # real torch layers, constructed in the reference ORDER, only to reproduce the default init
+        # and the state_dict keys; they are never called.
+        for name, kind, cin, cout in _SPEC:
+            if kind == 'c':
+                m = nn.Conv2d(cin, cout, kernel_size=3, stride=1, padding=1)
+            elif kind == 'd':
+                m = nn.ConvTranspose2d(cin, cout, 2, stride=2)
+            else:
+                m = nn.Conv2d(cin, cout, kernel_size=1, stride=1)
+            setattr(self, name, m)
+        self._flat = None
+        self._flat_grad = None
+        self._engines = {}
+        self._flatten()
+
+    # ---- flat parameter storage --------------------------------------------------------------------
+    def _flatten(self):
+        params = list(self.parameters())
+        dev = params[0].device
+        total = sum(p.numel() for p in params)
+        flat = torch.empty(total, dtype=torch.float32, device=dev)
+        grad = torch.zeros(total, dtype=torch.float32, device=dev)
+        off = 0
+        for p in params:
+            n = p.numel()
+            flat[off:off + n].copy_(p.data.reshape(-1).float())
+            p.data = flat[off:off + n].view(p.shape)
+            p.grad = grad[off:off + n].view(p.shape)
+            off += n
+        self._flat, self._flat_grad = flat, grad
+        self._engines = {}
+
+    def _apply(self, fn, *a, **k):
+        out = super()._apply(fn, *a, **k)
+        self._flatten()
+        return out
+
+    def load_state_dict(self, *a, **k):
+        out = super().load_state_dict(*a, **k)   # copy_ into the views keeps the flat buffer
+        return out
+
+    @property
+    def flat_params(self):
+        return self._flat
+
+    @property
+    def flat_grads(self):
+        return self._flat_grad
+
+    # ---- engine ------------------------------------------------------------------------------------
+    def _engine(self, n, h, w, train):
+        key = (n, h, w, bool(train))
+        if key not in self._engines:
+            lib = _lib.load()
+            dev = self._flat.device
+            assert dev.type == 'cuda', 'the B200 engine has no CPU path'
+            assert lib.eld_unet_param_count() == self._flat.numel()
+            nbytes = lib.eld_unet_workspace_bytes(n, h, w, int(train))
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            handle = ctypes.c_void_p()
+            _lib.check(lib.eld_unet_create(_lib.ctx(dev.index or 0), n, h, w, int(train), ws.data_ptr(), nbytes,
+                                           ctypes.byref(handle)), 'eld_unet_create')
+            self._engines[key] = (handle, ws)
+        return self._engines[key][0]
+
+    def forward(self, x):
+        """x: cuda float32 NCHW [n,4,h,w] -> float32 NCHW [n,4,h,w]  (inference; no autograd graph)."""
+        assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.shape[1] == 4
+        x = x.contiguous()
+        n, _, h, w = x.shape
+        out = torch.empty_like(x)
+        _lib.check(_lib.load().eld_unet_forward(self._engine(n, h, w, False), self._flat.data_ptr(), x.data_ptr(),
+                                               out.data_ptr(), _st()), 'eld_unet_forward')
+        return out
+
+    def train_step(self, x, target, loss_out=None):
+        """forward + L1 loss + backward in one launch sequence.  Fills self.flat_grads (== every
+        parameter's .grad) and returns (out, loss) with loss a 0-dim cuda tensor (no host sync)."""
+        assert x.is_cuda and x.dtype == torch.float32 and x.shape == target.shape
+        x, target = x.contiguous(), target.contiguous()
+        n, _, h, w = x.shape
+        out = torch.empty_like(x)
+        loss = loss_out if loss_out is not None else torch.empty((), dtype=torch.float32, device=x.device)
+        _lib.check(_lib.load().eld_unet_train_step(self._engine(n, h, w, True), self._flat.data_ptr(), x.data_ptr(),
+                                                   target.data_ptr(), out.data_ptr(), self._flat_grad.data_ptr(),
+                                                   loss.data_ptr(), _st()), 'eld_unet_train_step')
+        return out, loss
+
+
+class FusedAdam(torch.optim.Optimizer):
+    """torch.optim.Adam semantics (ELD_model.py:400-401) as ONE kernel over the flat buffers.
+    Keeps `param_groups` so Engine.set_learning_rate / util.set_opt_param keep working."""
+
+    def __init__(self, net, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        super().__init__(list(net.parameters()), dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        self.net = net
+        self.m = torch.zeros_like(net.flat_params)
+        self.v = torch.zeros_like(net.flat_params)
+        self.t = 0
+
+    @torch.no_grad()
+    def step(self, closure=None, grad_scale=1.0):
+        g = self.param_groups[0]
+        if self.m.data_ptr() == 0 or self.m.device != self.net.flat_params.device:
+            self.m = torch.zeros_like(self.net.flat_params)
+            self.v = torch.zeros_like(self.net.flat_params)
+        self.t += 1
+        p = self.net.flat_params
+        _lib.check(_lib.load().eld_adam_step(_lib.ctx(p.device.index or 0), p.data_ptr(), self.net.flat_grads.data_ptr(),
+                                             self.m.data_ptr(), self.v.data_ptr(), p.numel(), float(g['lr']),
+                                             float(g['betas'][0]), float(g['betas'][1]), float(g['eps']),
+                                             float(g['weight_decay']), self.t, float(grad_scale), _st()), 'eld_adam_step')
+
+    def zero_grad(self, set_to_none=False):
+        self.net.flat_grads.zero_()
+
+    # checkpoint format of torch.optim.Adam ('opt_g' in ELD_model.py:516-523)
+    def state_dict(self):
+        state, off = {}, 0
+        for i, p in enumerate(self.net.parameters()):
+            n = p.numel()
+            state[i] = {'step': torch.tensor(float(self.t)), 'exp_avg': self.m[off:off + n].view(p.shape).clone(),
+                        'exp_avg_sq': self.v[off:off + n].view(p.shape).clone()}
+            off += n
+        groups = [dict((k, v) for k, v in self.param_groups[0].items() if k != 'params')]
+        groups[0]['params'] = list(range(len(state)))
+        return {'state': state, 'param_groups': groups}
+
+    def load_state_dict(self, sd):
+        off = 0
+        for i, p in enumerate(self.net.parameters()):
+            n = p.numel()
+            st = sd['state'].get(i)
+            if st is not None:
+                self.m[off:off + n].copy_(st['exp_avg'].reshape(-1))
+                self.v[off:off + n].copy_(st['exp_avg_sq'].reshape(-1))
+                self.t = int(float(st['step']))
+            off += n
+        for k, v in sd['param_groups'][0].items():
+            if k != 'params':
+                self.param_groups[0][k] = v
+
+
+def unet(in_channels, out_channels, **kwargs):
+    """models/arch/__init__.py:6-7"""
+    return UNetSeeInDark(in_channels, out_channels)

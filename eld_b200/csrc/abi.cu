@@ -1,5 +1,6 @@
 // abi.cu - context management and error channel of the C ABI (include/eld_b200.h).
 #include "common.cuh"
+#include "unet_prims.h"
 #include <cstring>
 #include <new>
 
@@ -58,6 +59,7 @@ int eld_ctx_create(int device, eld_ctx** out)
         return ELD_E_CUDA;
     }
     ctx->encode_tiled = (eld::PFN_encodeTiled)fn;
+    { int rc = eld::init_gemm_kernels(ctx); if (rc != ELD_OK) { delete ctx; return rc; } }
     *out = ctx;
     return ELD_OK;
 }

@@ -12,13 +12,11 @@
 //           epilogue of tile i overlaps the MMAs of tile i+1.
 #pragma once
 #include "umma.cuh"
+#include "unet_prims.h"
 #include <cuda_bf16.h>
 
 namespace eld {
 
-enum { A_CONV = 0, A_GATHER = 1 };
-enum { EPI_STORE = 0, EPI_SHUFFLE = 1 };
-enum { ACT_NONE = 0, ACT_LRELU = 1, ACT_MASK = 2 };
 
 struct ConvGemmParams {
     int n_img, H, W;      // output pixel grid (M space); H % 8 == 0, W % 16 == 0

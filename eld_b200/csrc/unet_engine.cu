@@ -1,0 +1,418 @@
+// unet_engine.cu - the UNetSeeInDark training / inference step as a fixed launch sequence over the
+// tcgen05 tiles (unet_prims.cu) and the HBM-bound helpers (unet_ew.cu).
+//
+// Reference: models/arch/Unet.py:48-91 (forward), models/ELD_model.py:411-420,469-475 (L1 loss,
+// backward, Adam).  Activations NHWC bf16; torch.cat (Unet.py:69,74,79,84) is free: the deconv and
+// the encoder conv write disjoint channel ranges of one "cat" buffer.  Parameters and gradients are
+// flat fp32 buffers in state_dict order (so released checkpoints map 1:1 and DDP all-reduces one buffer).
+#include "common.cuh"
+#include "unet_prims.h"
+#include "unet_ew.h"
+#include <cuda_bf16.h>
+#include <cstring>
+#include <vector>
+#include <new>
+
+namespace eld {
+
+enum { L_CONV3 = 0, L_DECONV = 1, L_CONV1 = 2 };
+struct Layer { const char* name; int type, cin, cout; size_t w_off, b_off, wf_off, wd_off; };
+
+// state_dict order of UNetSeeInDark (Unet.py:11-46)
+static const struct { const char* name; int type, cin, cout; } kLayers[] = {
+    { "conv1_1", L_CONV3, 4, 32 },    { "conv1_2", L_CONV3, 32, 32 },   { "conv2_1", L_CONV3, 32, 64 },
+    { "conv2_2", L_CONV3, 64, 64 },   { "conv3_1", L_CONV3, 64, 128 },  { "conv3_2", L_CONV3, 128, 128 },
+    { "conv4_1", L_CONV3, 128, 256 }, { "conv4_2", L_CONV3, 256, 256 }, { "conv5_1", L_CONV3, 256, 512 },
+    { "conv5_2", L_CONV3, 512, 512 }, { "upv6", L_DECONV, 512, 256 },   { "conv6_1", L_CONV3, 512, 256 },
+    { "conv6_2", L_CONV3, 256, 256 }, { "upv7", L_DECONV, 256, 128 },   { "conv7_1", L_CONV3, 256, 128 },
+    { "conv7_2", L_CONV3, 128, 128 }, { "upv8", L_DECONV, 128, 64 },    { "conv8_1", L_CONV3, 128, 64 },
+    { "conv8_2", L_CONV3, 64, 64 },   { "upv9", L_DECONV, 64, 32 },     { "conv9_1", L_CONV3, 64, 32 },
+    { "conv9_2", L_CONV3, 32, 32 },   { "conv10_1", L_CONV1, 32, 4 },
+};
+constexpr int kNumLayers = sizeof(kLayers) / sizeof(kLayers[0]);
+enum { I_C11 = 0, I_C12, I_C21, I_C22, I_C31, I_C32, I_C41, I_C42, I_C51, I_C52, I_UP6, I_C61, I_C62, I_UP7,
+       I_C71, I_C72, I_UP8, I_C81, I_C82, I_UP9, I_C91, I_C92, I_C10 };
+
+struct PackEntry { unsigned long long src, dst_f, dst_d; int cout, cin, type; int pad; };
+struct PackTable { PackEntry e[kNumLayers]; int n; };
+
+// one launch packs every layer's fp32 master weights into both bf16 GEMM operands (fprop + dgrad)
+__global__ void __launch_bounds__(256)
+pack_all_kernel(const float* __restrict__ params, __nv_bfloat16* __restrict__ packed, const __grid_constant__ PackTable T)
+{
+    const PackEntry& e = T.e[blockIdx.y];
+    const float* w = params + e.src;
+    const int ksz = e.type == L_CONV3 ? 9 : 4;
+    const size_t total = (size_t)e.cout * e.cin * ksz;
+    __nv_bfloat16* of = packed + e.dst_f;
+    __nv_bfloat16* od = packed + e.dst_d;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const float v = w[i];
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        if (e.type == L_CONV3) {          // w[co][ci][t]
+            const int t = i % 9, ci = (i / 9) % e.cin, co = i / ((size_t)9 * e.cin);
+            of[((size_t)co * 9 + t) * e.cin + ci] = h;
+            od[((size_t)ci * 9 + (8 - t)) * e.cout + co] = h;
+        } else {                          // wt[ci][co][s]
+            const int s = i % 4, co = (i / 4) % e.cout, ci = i / ((size_t)4 * e.cout);
+            of[((size_t)s * e.cout + co) * e.cin + ci] = h;
+            od[((size_t)ci * 4 + s) * e.cout + co] = h;
+        }
+    }
+}
+
+}  // namespace eld
+
+using namespace eld;
+
+struct eld_unet {
+    eld_ctx* ctx;
+    int n, H, W;
+    Layer L[kNumLayers];
+    size_t n_params;
+    char* ws;
+    size_t ws_bytes;
+    // activations / gradients (bf16), offsets in bytes into ws
+    __nv_bfloat16 *a1_1, *cat9, *p1, *a2_1, *cat8, *p2, *a3_1, *cat7, *p3, *a4_1, *cat6, *p4, *a5_1, *a5_2,
+        *a6_1, *a6_2, *a7_1, *a7_2, *a8_1, *a8_2, *a9_1, *a9_2;
+    __nv_bfloat16 *dz9_2, *dz9_1, *dcat9, *dz8_2, *dz8_1, *dcat8, *dz7_2, *dz7_1, *dcat7, *dz6_2, *dz6_1, *dcat6,
+        *dz5_2, *dz5_1, *dp4, *dz4_2, *dz4_1, *dp3, *dz3_2, *dz3_1, *dp2, *dz2_2, *dz2_1, *dp1, *dz1_2, *dz1_1;
+    __nv_bfloat16* packed;
+    PackTable table;
+};
+
+static size_t layout(eld_unet* u, char* base, bool train)
+{
+    size_t off = 0;
+    const size_t n = u->n;
+    auto take = [&](__nv_bfloat16** p, int lvl, int ch) {
+        const size_t h = u->H >> lvl, w = u->W >> lvl;
+        const size_t bytes = (n * h * w * ch * 2 + 1023) & ~(size_t)1023;
+        if (p) *p = reinterpret_cast<__nv_bfloat16*>(base + off);
+        off += bytes;
+    };
+    take(&u->a1_1, 0, 32); take(&u->cat9, 0, 64); take(&u->p1, 1, 32);
+    take(&u->a2_1, 1, 64); take(&u->cat8, 1, 128); take(&u->p2, 2, 64);
+    take(&u->a3_1, 2, 128); take(&u->cat7, 2, 256); take(&u->p3, 3, 128);
+    take(&u->a4_1, 3, 256); take(&u->cat6, 3, 512); take(&u->p4, 4, 256);
+    take(&u->a5_1, 4, 512); take(&u->a5_2, 4, 512);
+    take(&u->a6_1, 3, 256); take(&u->a6_2, 3, 256); take(&u->a7_1, 2, 128); take(&u->a7_2, 2, 128);
+    take(&u->a8_1, 1, 64); take(&u->a8_2, 1, 64); take(&u->a9_1, 0, 32); take(&u->a9_2, 0, 32);
+    if (train) {
+        take(&u->dz9_2, 0, 32); take(&u->dz9_1, 0, 32); take(&u->dcat9, 0, 64);
+        take(&u->dz8_2, 1, 64); take(&u->dz8_1, 1, 64); take(&u->dcat8, 1, 128);
+        take(&u->dz7_2, 2, 128); take(&u->dz7_1, 2, 128); take(&u->dcat7, 2, 256);
+        take(&u->dz6_2, 3, 256); take(&u->dz6_1, 3, 256); take(&u->dcat6, 3, 512);
+        take(&u->dz5_2, 4, 512); take(&u->dz5_1, 4, 512); take(&u->dp4, 4, 256);
+        take(&u->dz4_2, 3, 256); take(&u->dz4_1, 3, 256); take(&u->dp3, 3, 128);
+        take(&u->dz3_2, 2, 128); take(&u->dz3_1, 2, 128); take(&u->dp2, 2, 64);
+        take(&u->dz2_2, 1, 64); take(&u->dz2_1, 1, 64); take(&u->dp1, 1, 32);
+        take(&u->dz1_2, 0, 32); take(&u->dz1_1, 0, 32);
+    }
+    // packed weights
+    size_t pk = 0;
+    for (int i = 0; i < kNumLayers; ++i) {
+        Layer& l = u->L[i];
+        if (i == I_C11 || l.type == L_CONV1) continue;
+        const size_t cnt = (size_t)l.cin * l.cout * (l.type == L_CONV3 ? 9 : 4);
+        l.wf_off = pk; pk += cnt;
+        l.wd_off = pk; pk += cnt;
+    }
+    u->packed = reinterpret_cast<__nv_bfloat16*>(base + off);
+    off += (pk * 2 + 1023) & ~(size_t)1023;
+    return off;
+}
+
+static void init_layers(eld_unet* u)
+{
+    size_t off = 0;
+    for (int i = 0; i < kNumLayers; ++i) {
+        Layer& l = u->L[i];
+        l.name = kLayers[i].name; l.type = kLayers[i].type; l.cin = kLayers[i].cin; l.cout = kLayers[i].cout;
+        const size_t ksz = l.type == L_CONV3 ? 9 : (l.type == L_DECONV ? 4 : 1);
+        l.w_off = off; off += (size_t)l.cin * l.cout * ksz;
+        l.b_off = off; off += l.cout;
+        l.wf_off = l.wd_off = 0;
+    }
+    u->n_params = off;
+}
+
+extern "C" size_t eld_unet_param_count(void)
+{
+    eld_unet tmp{};
+    init_layers(&tmp);
+    return tmp.n_params;
+}
+
+extern "C" int eld_unet_param_offset(const char* name, int is_bias, size_t* offset, size_t* count)
+{
+    eld_unet tmp{};
+    init_layers(&tmp);
+    for (int i = 0; i < kNumLayers; ++i) {
+        if (strcmp(name, tmp.L[i].name) == 0) {
+            const Layer& l = tmp.L[i];
+            const size_t ksz = l.type == L_CONV3 ? 9 : (l.type == L_DECONV ? 4 : 1);
+            if (offset) *offset = is_bias ? l.b_off : l.w_off;
+            if (count) *count = is_bias ? (size_t)l.cout : (size_t)l.cin * l.cout * ksz;
+            return ELD_OK;
+        }
+    }
+    set_error("eld_unet_param_offset: unknown layer '%s'", name);
+    return ELD_E_ARG;
+}
+
+extern "C" size_t eld_unet_workspace_bytes(int n, int h, int w, int train)
+{
+    eld_unet tmp{};
+    tmp.n = n; tmp.H = h; tmp.W = w;
+    init_layers(&tmp);
+    return layout(&tmp, nullptr, train != 0) + 1024;
+}
+
+extern "C" int eld_unet_create(eld_ctx* ctx, int n, int h, int w, int train, void* workspace, size_t bytes, eld_unet** out)
+{
+    ELD_REQUIRE(ctx && out && workspace, "eld_unet_create: NULL argument");
+    ELD_REQUIRE(n > 0 && h > 0 && w > 0, "eld_unet_create: bad shape");
+    ELD_REQUIRE(h % 128 == 0 && w % 256 == 0,
+                "eld_unet_create: the tcgen05 tiles need H %% 128 == 0 and W %% 256 == 0 (8x16 patches at 1/16 scale); got %dx%d", h, w);
+    eld_unet* u = new (std::nothrow) eld_unet();
+    ELD_REQUIRE(u, "eld_unet_create: out of host memory");
+    u->ctx = ctx; u->n = n; u->H = h; u->W = w;
+    init_layers(u);
+    char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023);
+    const size_t need = layout(u, base, train != 0) + (base - static_cast<char*>(workspace));
+    if (need > bytes) {
+        set_error("eld_unet_create: workspace %zu bytes < required %zu", bytes, need);
+        delete u;
+        return ELD_E_WORKSPACE;
+    }
+    u->ws = base; u->ws_bytes = bytes;
+    if (!train) u->dz9_2 = nullptr;
+    int k = 0;
+    for (int i = 0; i < kNumLayers; ++i) {
+        const Layer& l = u->L[i];
+        if (i == I_C11 || l.type == L_CONV1) continue;
+        u->table.e[k++] = PackEntry{ l.w_off, l.wf_off, l.wd_off, l.cout, l.cin, l.type, 0 };
+    }
+    u->table.n = k;
+    // opt in to large dynamic shared memory once (not inside a captured region)
+    { int rc = init_gemm_kernels(ctx); if (rc != ELD_OK) { delete u; return rc; } }
+    *out = u;
+    return ELD_OK;
+}
+
+extern "C" void eld_unet_destroy(eld_unet* u) { delete u; }
+
+#define TRY(expr) do { int _rc = (expr); if (_rc != ELD_OK) return _rc; } while (0)
+
+namespace {
+
+struct Runner {
+    eld_unet* u;
+    const float* params;
+    cudaStream_t st;
+    eld_ctx* ctx() const { return u->ctx; }
+    const __nv_bfloat16* wf(int i) const { return u->packed + u->L[i].wf_off; }
+    const __nv_bfloat16* wd(int i) const { return u->packed + u->L[i].wd_off; }
+    const float* bias(int i) const { return params + u->L[i].b_off; }
+
+    int conv(int li, const void* x, int xp, int xc0, void* y, int yp, int yc0, int lvl) const
+    {
+        const Layer& l = u->L[li];
+        GemmOp op{};
+        op.a = x; op.a_pitch = xp; op.a_c0 = xc0; op.a_mode = A_CONV; op.taps = 9; op.cin = l.cin;
+        op.n_img = u->n; op.H = u->H >> lvl; op.W = u->W >> lvl;
+        op.b = wf(li); op.n_total = l.cout; op.cout = l.cout;
+        op.epi_mode = EPI_STORE; op.act = ACT_LRELU; op.out = y; op.out_pitch = yp; op.out_c0 = yc0; op.bias = bias(li);
+        return launch_conv_gemm(ctx(), op, st);
+    }
+    int deconv(int li, const void* x, int xp, void* y, int yp, int lvl_in) const
+    {
+        const Layer& l = u->L[li];
+        GemmOp op{};
+        op.a = x; op.a_pitch = xp; op.a_c0 = 0; op.a_mode = A_CONV; op.taps = 1; op.cin = l.cin;
+        op.n_img = u->n; op.H = u->H >> lvl_in; op.W = u->W >> lvl_in;
+        op.b = wf(li); op.n_total = 4 * l.cout; op.cout = l.cout;
+        op.epi_mode = EPI_SHUFFLE; op.act = ACT_NONE; op.out = y; op.out_pitch = yp; op.out_c0 = 0; op.bias = bias(li);
+        return launch_conv_gemm(ctx(), op, st);
+    }
+    // data gradient of a conv: dz [cout] -> d(input) [cin channels at dxc0], optional lrelu' mask from `act_src`
+    int conv_dgrad(int li, const void* dz, void* dx, int dxp, int dxc0, const void* act_src, int asp, int asc0, int lvl) const
+    {
+        const Layer& l = u->L[li];
+        GemmOp op{};
+        op.a = dz; op.a_pitch = l.cout; op.a_c0 = 0; op.a_mode = A_CONV; op.taps = 9; op.cin = l.cout;
+        op.n_img = u->n; op.H = u->H >> lvl; op.W = u->W >> lvl;
+        op.b = wd(li); op.n_total = l.cin; op.cout = l.cin;
+        op.epi_mode = EPI_STORE; op.act = act_src ? ACT_MASK : ACT_NONE;
+        op.out = dx; op.out_pitch = dxp; op.out_c0 = dxc0; op.bias = nullptr;
+        op.aux = act_src; op.aux_pitch = asp; op.aux_c0 = asc0;
+        return launch_conv_gemm(ctx(), op, st);
+    }
+    int deconv_dgrad(int li, const void* dy, int dyp, void* dx, const void* act_src, int lvl_in) const
+    {
+        const Layer& l = u->L[li];
+        GemmOp op{};
+        op.a = dy; op.a_pitch = dyp; op.a_c0 = 0; op.a_mode = A_GATHER; op.taps = 4; op.cin = l.cout;
+        op.n_img = u->n; op.H = u->H >> lvl_in; op.W = u->W >> lvl_in;
+        op.b = wd(li); op.n_total = l.cin; op.cout = l.cin;
+        op.epi_mode = EPI_STORE; op.act = ACT_MASK; op.out = dx; op.out_pitch = l.cin; op.out_c0 = 0;
+        op.aux = act_src; op.aux_pitch = l.cin; op.aux_c0 = 0;
+        return launch_conv_gemm(ctx(), op, st);
+    }
+    int conv_wgrad(int li, const void* x, int xp, int xc0, const void* dz, float* grads, int lvl) const
+    {
+        const Layer& l = u->L[li];
+        WgradOp op{};
+        op.mode = WG_CONV; op.p = x; op.p_pitch = xp; op.p_c0 = xc0; op.p_ch = l.cin;
+        op.q = dz; op.q_pitch = l.cout; op.q_c0 = 0; op.q_ch = l.cout;
+        op.n_img = u->n; op.H = u->H >> lvl; op.W = u->W >> lvl; op.dw = grads + l.w_off;
+        TRY(launch_wgrad(ctx(), op, st));
+        return launch_colsum(ctx(), dz, l.cout, 0, l.cout, (size_t)u->n * op.H * op.W, grads + l.b_off, st);
+    }
+    int deconv_wgrad(int li, const void* x, const void* dy, int dyp, float* grads, int lvl_in) const
+    {
+        const Layer& l = u->L[li];
+        WgradOp op{};
+        op.mode = WG_DECONV; op.p = dy; op.p_pitch = dyp; op.p_c0 = 0; op.p_ch = l.cout;
+        op.q = x; op.q_pitch = l.cin; op.q_c0 = 0; op.q_ch = l.cin;
+        op.n_img = u->n; op.H = u->H >> lvl_in; op.W = u->W >> lvl_in; op.dw = grads + l.w_off;
+        TRY(launch_wgrad(ctx(), op, st));
+        return launch_colsum(ctx(), dy, dyp, 0, l.cout, (size_t)u->n * op.H * op.W * 4, grads + l.b_off, st);
+    }
+    int pool(const void* in, int pitch, int c0, void* out, int C, int lvl_out) const
+    {
+        return launch_maxpool(ctx(), in, pitch, c0, out, C, u->n, u->H >> lvl_out, u->W >> lvl_out, st);
+    }
+    int pool_bwd(const void* A, const void* dskip, int pitch, int c0, const void* dP, void* dZ, int C, int lvl_out) const
+    {
+        return launch_maxpool_bwd(ctx(), A, dskip, pitch, c0, dP, dZ, C, u->n, u->H >> lvl_out, u->W >> lvl_out, st);
+    }
+
+    int pack() const
+    {
+        dim3 grid(64, u->table.n);
+        pack_all_kernel<<<grid, 256, 0, st>>>(params, u->packed, u->table);
+        ELD_CHECK_CUDA(cudaGetLastError());
+        count_launch(ctx());
+        return ELD_OK;
+    }
+
+    int forward(const float* x) const
+    {
+        eld_unet* U = u;
+        TRY(pack());
+        TRY(launch_first_conv(ctx(), x, params + U->L[I_C11].w_off, bias(I_C11), U->a1_1, U->n, U->H, U->W, st));
+        TRY(conv(I_C12, U->a1_1, 32, 0, U->cat9, 64, 32, 0));  TRY(pool(U->cat9, 64, 32, U->p1, 32, 1));
+        TRY(conv(I_C21, U->p1, 32, 0, U->a2_1, 64, 0, 1));
+        TRY(conv(I_C22, U->a2_1, 64, 0, U->cat8, 128, 64, 1)); TRY(pool(U->cat8, 128, 64, U->p2, 64, 2));
+        TRY(conv(I_C31, U->p2, 64, 0, U->a3_1, 128, 0, 2));
+        TRY(conv(I_C32, U->a3_1, 128, 0, U->cat7, 256, 128, 2)); TRY(pool(U->cat7, 256, 128, U->p3, 128, 3));
+        TRY(conv(I_C41, U->p3, 128, 0, U->a4_1, 256, 0, 3));
+        TRY(conv(I_C42, U->a4_1, 256, 0, U->cat6, 512, 256, 3)); TRY(pool(U->cat6, 512, 256, U->p4, 256, 4));
+        TRY(conv(I_C51, U->p4, 256, 0, U->a5_1, 512, 0, 4));
+        TRY(conv(I_C52, U->a5_1, 512, 0, U->a5_2, 512, 0, 4));
+        TRY(deconv(I_UP6, U->a5_2, 512, U->cat6, 512, 4));
+        TRY(conv(I_C61, U->cat6, 512, 0, U->a6_1, 256, 0, 3)); TRY(conv(I_C62, U->a6_1, 256, 0, U->a6_2, 256, 0, 3));
+        TRY(deconv(I_UP7, U->a6_2, 256, U->cat7, 256, 3));
+        TRY(conv(I_C71, U->cat7, 256, 0, U->a7_1, 128, 0, 2)); TRY(conv(I_C72, U->a7_1, 128, 0, U->a7_2, 128, 0, 2));
+        TRY(deconv(I_UP8, U->a7_2, 128, U->cat8, 128, 2));
+        TRY(conv(I_C81, U->cat8, 128, 0, U->a8_1, 64, 0, 1));  TRY(conv(I_C82, U->a8_1, 64, 0, U->a8_2, 64, 0, 1));
+        TRY(deconv(I_UP9, U->a8_2, 64, U->cat9, 64, 1));
+        TRY(conv(I_C91, U->cat9, 64, 0, U->a9_1, 32, 0, 0));   TRY(conv(I_C92, U->a9_1, 32, 0, U->a9_2, 32, 0, 0));
+        return ELD_OK;
+    }
+
+    int backward(const float* x, float* g) const
+    {
+        eld_unet* U = u;
+        // decoder
+        TRY(conv_wgrad(I_C92, U->a9_1, 32, 0, U->dz9_2, g, 0));
+        TRY(conv_dgrad(I_C92, U->dz9_2, U->dz9_1, 32, 0, U->a9_1, 32, 0, 0));
+        TRY(conv_wgrad(I_C91, U->cat9, 64, 0, U->dz9_1, g, 0));
+        TRY(conv_dgrad(I_C91, U->dz9_1, U->dcat9, 64, 0, nullptr, 0, 0, 0));
+        TRY(deconv_wgrad(I_UP9, U->a8_2, U->dcat9, 64, g, 1));
+        TRY(deconv_dgrad(I_UP9, U->dcat9, 64, U->dz8_2, U->a8_2, 1));
+        TRY(conv_wgrad(I_C82, U->a8_1, 64, 0, U->dz8_2, g, 1));
+        TRY(conv_dgrad(I_C82, U->dz8_2, U->dz8_1, 64, 0, U->a8_1, 64, 0, 1));
+        TRY(conv_wgrad(I_C81, U->cat8, 128, 0, U->dz8_1, g, 1));
+        TRY(conv_dgrad(I_C81, U->dz8_1, U->dcat8, 128, 0, nullptr, 0, 0, 1));
+        TRY(deconv_wgrad(I_UP8, U->a7_2, U->dcat8, 128, g, 2));
+        TRY(deconv_dgrad(I_UP8, U->dcat8, 128, U->dz7_2, U->a7_2, 2));
+        TRY(conv_wgrad(I_C72, U->a7_1, 128, 0, U->dz7_2, g, 2));
+        TRY(conv_dgrad(I_C72, U->dz7_2, U->dz7_1, 128, 0, U->a7_1, 128, 0, 2));
+        TRY(conv_wgrad(I_C71, U->cat7, 256, 0, U->dz7_1, g, 2));
+        TRY(conv_dgrad(I_C71, U->dz7_1, U->dcat7, 256, 0, nullptr, 0, 0, 2));
+        TRY(deconv_wgrad(I_UP7, U->a6_2, U->dcat7, 256, g, 3));
+        TRY(deconv_dgrad(I_UP7, U->dcat7, 256, U->dz6_2, U->a6_2, 3));
+        TRY(conv_wgrad(I_C62, U->a6_1, 256, 0, U->dz6_2, g, 3));
+        TRY(conv_dgrad(I_C62, U->dz6_2, U->dz6_1, 256, 0, U->a6_1, 256, 0, 3));
+        TRY(conv_wgrad(I_C61, U->cat6, 512, 0, U->dz6_1, g, 3));
+        TRY(conv_dgrad(I_C61, U->dz6_1, U->dcat6, 512, 0, nullptr, 0, 0, 3));
+        TRY(deconv_wgrad(I_UP6, U->a5_2, U->dcat6, 512, g, 4));
+        TRY(deconv_dgrad(I_UP6, U->dcat6, 512, U->dz5_2, U->a5_2, 4));
+        // bottleneck + encoder
+        TRY(conv_wgrad(I_C52, U->a5_1, 512, 0, U->dz5_2, g, 4));
+        TRY(conv_dgrad(I_C52, U->dz5_2, U->dz5_1, 512, 0, U->a5_1, 512, 0, 4));
+        TRY(conv_wgrad(I_C51, U->p4, 256, 0, U->dz5_1, g, 4));
+        TRY(conv_dgrad(I_C51, U->dz5_1, U->dp4, 256, 0, nullptr, 0, 0, 4));
+        TRY(pool_bwd(U->cat6, U->dcat6, 512, 256, U->dp4, U->dz4_2, 256, 4));
+        TRY(conv_wgrad(I_C42, U->a4_1, 256, 0, U->dz4_2, g, 3));
+        TRY(conv_dgrad(I_C42, U->dz4_2, U->dz4_1, 256, 0, U->a4_1, 256, 0, 3));
+        TRY(conv_wgrad(I_C41, U->p3, 128, 0, U->dz4_1, g, 3));
+        TRY(conv_dgrad(I_C41, U->dz4_1, U->dp3, 128, 0, nullptr, 0, 0, 3));
+        TRY(pool_bwd(U->cat7, U->dcat7, 256, 128, U->dp3, U->dz3_2, 128, 3));
+        TRY(conv_wgrad(I_C32, U->a3_1, 128, 0, U->dz3_2, g, 2));
+        TRY(conv_dgrad(I_C32, U->dz3_2, U->dz3_1, 128, 0, U->a3_1, 128, 0, 2));
+        TRY(conv_wgrad(I_C31, U->p2, 64, 0, U->dz3_1, g, 2));
+        TRY(conv_dgrad(I_C31, U->dz3_1, U->dp2, 64, 0, nullptr, 0, 0, 2));
+        TRY(pool_bwd(U->cat8, U->dcat8, 128, 64, U->dp2, U->dz2_2, 64, 2));
+        TRY(conv_wgrad(I_C22, U->a2_1, 64, 0, U->dz2_2, g, 1));
+        TRY(conv_dgrad(I_C22, U->dz2_2, U->dz2_1, 64, 0, U->a2_1, 64, 0, 1));
+        TRY(conv_wgrad(I_C21, U->p1, 32, 0, U->dz2_1, g, 1));
+        TRY(conv_dgrad(I_C21, U->dz2_1, U->dp1, 32, 0, nullptr, 0, 0, 1));
+        TRY(pool_bwd(U->cat9, U->dcat9, 64, 32, U->dp1, U->dz1_2, 32, 1));
+        TRY(conv_wgrad(I_C12, U->a1_1, 32, 0, U->dz1_2, g, 0));
+        TRY(conv_dgrad(I_C12, U->dz1_2, U->dz1_1, 32, 0, U->a1_1, 32, 0, 0));
+        TRY(launch_first_conv_wgrad(ctx(), x, U->dz1_1, g + U->L[I_C11].w_off, g + U->L[I_C11].b_off, U->n, U->H, U->W, st));
+        return ELD_OK;
+    }
+};
+
+}  // namespace
+
+extern "C" int eld_unet_forward(eld_unet* u, const float* params, const float* x, float* out, void* stream)
+{
+    ELD_REQUIRE(u && params && x && out, "eld_unet_forward: NULL argument");
+    ELD_CHECK_CUDA(cudaSetDevice(u->ctx->device));
+    Runner r{ u, params, static_cast<cudaStream_t>(stream) };
+    TRY(r.forward(x));
+    return launch_head(u->ctx, u->a9_2, params + u->L[I_C10].w_off, params + u->L[I_C10].b_off, out, nullptr, nullptr,
+                       nullptr, nullptr, nullptr, u->n, (size_t)u->H * u->W, r.st);
+}
+
+extern "C" int eld_unet_train_step(eld_unet* u, const float* params, const float* x, const float* target,
+                                   float* out, float* grads, float* loss, void* stream)
+{
+    ELD_REQUIRE(u && params && x && target && out && grads && loss, "eld_unet_train_step: NULL argument");
+    ELD_REQUIRE(u->dz9_2 != nullptr, "eld_unet_train_step: the eld_unet was created with train = 0");
+    ELD_CHECK_CUDA(cudaSetDevice(u->ctx->device));
+    Runner r{ u, params, static_cast<cudaStream_t>(stream) };
+    ELD_CHECK_CUDA(cudaMemsetAsync(grads, 0, u->n_params * sizeof(float), r.st));
+    ELD_CHECK_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), r.st));
+    TRY(r.forward(x));
+    TRY(launch_head(u->ctx, u->a9_2, params + u->L[I_C10].w_off, params + u->L[I_C10].b_off, out, target, u->dz9_2,
+                    grads + u->L[I_C10].w_off, grads + u->L[I_C10].b_off, loss, u->n, (size_t)u->H * u->W, r.st));
+    return r.backward(x, grads);
+}
+
+extern "C" int eld_adam_step(eld_ctx* ctx, float* params, const float* grads, float* m, float* v, size_t n,
+                             float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                             float grad_scale, void* stream)
+{
+    ELD_REQUIRE(ctx && params && grads && m && v, "eld_adam_step: NULL argument");
+    ELD_REQUIRE(step >= 1, "eld_adam_step: step counts from 1");
+    ELD_CHECK_CUDA(cudaSetDevice(ctx->device));
+    return launch_adam(ctx, params, grads, m, v, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale,
+                       static_cast<cudaStream_t>(stream));
+}

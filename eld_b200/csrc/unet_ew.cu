@@ -1,0 +1,473 @@
+// unet_ew.cu - the non-GEMM kernels of the U-Net step (all HBM-bound, CUDA cores):
+//   first conv (4->32 on the fp32 NCHW noise output), 2x2 max-pool fwd / bwd(+skip add + LeakyReLU'),
+//   1x1 head + L1 loss + its whole backward, bias gradients, first-layer wgrad, fused Adam.
+#include "common.cuh"
+#include "unet_ew.h"
+#include <cuda_bf16.h>
+
+namespace eld {
+
+__device__ __forceinline__ float lrelu(float v) { return fmaxf(v, 0.2f * v); }
+__device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
+__device__ __forceinline__ uint32_t pack_bf2(float a, float b)
+{
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// conv1_1: x f32 NCHW [n][4][H][W] -> y bf16 NHWC [n][H][W][32] = lrelu(conv3x3(x) + b)   (Unet.py:11,49)
+// block = 16x16 pixels, halo tile in smem, weights in smem as [tap*4+ci][32].
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+first_conv_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                  __nv_bfloat16* __restrict__ y, int H, int W)
+{
+    __shared__ float xs[4][18][18];
+    __shared__ __align__(16) float ws[36][32];
+    __shared__ float bs[32];
+    const int n = blockIdx.z, x0 = blockIdx.x * 16, y0 = blockIdx.y * 16;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 36 * 32; i += 256) {
+        const int co = i & 31, k = i >> 5;          // k = tap*4 + ci
+        const int tap = k >> 2, ci = k & 3;
+        ws[k][co] = w[(co * 4 + ci) * 9 + tap];
+    }
+    if (tid < 32) bs[tid] = b[tid];
+    const size_t plane = (size_t)H * W;
+    for (int i = tid; i < 4 * 18 * 18; i += 256) {
+        const int c = i / 324, r = (i % 324) / 18, q = i % 18;
+        const int yy = y0 + r - 1, xx = x0 + q - 1;
+        xs[c][r][q] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? x[((size_t)n * 4 + c) * plane + (size_t)yy * W + xx] : 0.0f;
+    }
+    __syncthreads();
+    const int px = tid & 15, py = tid >> 4;
+    if (y0 + py >= H || x0 + px >= W) return;
+    float acc[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] = bs[j];
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci) {
+            const float v = xs[ci][py + tap / 3][px + tap % 3];
+            const float4* wr = reinterpret_cast<const float4*>(&ws[tap * 4 + ci][0]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float4 w4 = wr[j];
+                acc[4 * j] = fmaf(v, w4.x, acc[4 * j]);
+                acc[4 * j + 1] = fmaf(v, w4.y, acc[4 * j + 1]);
+                acc[4 * j + 2] = fmaf(v, w4.z, acc[4 * j + 2]);
+                acc[4 * j + 3] = fmaf(v, w4.w, acc[4 * j + 3]);
+            }
+        }
+    }
+    uint4* dst = reinterpret_cast<uint4*>(y + (((size_t)n * H + (y0 + py)) * W + (x0 + px)) * 32);
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+        dst[g] = make_uint4(pack_bf2(lrelu(acc[8 * g]), lrelu(acc[8 * g + 1])), pack_bf2(lrelu(acc[8 * g + 2]), lrelu(acc[8 * g + 3])),
+                            pack_bf2(lrelu(acc[8 * g + 4]), lrelu(acc[8 * g + 5])), pack_bf2(lrelu(acc[8 * g + 6]), lrelu(acc[8 * g + 7])));
+}
+
+// conv1_1 weight/bias gradient: dW[32][4][3][3] += sum_p dz[p][co] x[p+tap][ci], db[co] += sum_p dz[p][co].
+// Persistent blocks over 16x16 tiles; thread (co = t&31, g = t>>5) owns k = g, g+8, ... (<36) and,
+// for g == 0, the bias.  One global atomic per accumulator per block at the end.
+__global__ void __launch_bounds__(256)
+first_conv_wgrad_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dz,
+                        float* __restrict__ dw, float* __restrict__ db, int n_img, int H, int W)
+{
+    __shared__ float xs[4][18][18];
+    __shared__ __nv_bfloat16 dzs[256][32 + 2];   // +2: pad the row to 68 B to spread banks
+    const int tid = threadIdx.x, co = tid & 31, g = tid >> 5;
+    const int tiles_x = W / 16, tiles_y = H / 16;
+    const int total = n_img * tiles_x * tiles_y;
+    const size_t plane = (size_t)H * W;
+    float acc[5] = { 0.f, 0.f, 0.f, 0.f, 0.f }, accb = 0.f;
+    int kk[5], koff[5];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        const int k = g + 8 * j;                     // k = tap*4 + ci
+        kk[j] = k;
+        const int tap = (k < 36 ? k : 0) >> 2, ci = k & 3;
+        koff[j] = ci * 324 + (tap / 3) * 18 + (tap % 3);
+    }
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, n = tile / (tiles_x * tiles_y);
+        const int x0 = tx * 16, y0 = ty * 16;
+        __syncthreads();
+        for (int i = tid; i < 4 * 324; i += 256) {
+            const int c = i / 324, r = (i % 324) / 18, q = i % 18;
+            const int yy = y0 + r - 1, xx = x0 + q - 1;
+            xs[c][r][q] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? x[((size_t)n * 4 + c) * plane + (size_t)yy * W + xx] : 0.0f;
+        }
+        for (int i = tid; i < 256 * 16; i += 256) {   // 256 px x 16 words (32 ch)
+            const int p = i >> 4, wv = i & 15;
+            const uint32_t v = reinterpret_cast<const uint32_t*>(dz + (((size_t)n * H + (y0 + (p >> 4))) * W + (x0 + (p & 15))) * 32)[wv];
+            reinterpret_cast<uint32_t*>(&dzs[p][0])[wv] = v;
+        }
+        __syncthreads();
+        const float* xflat = &xs[0][0][0];
+        for (int p = 0; p < 256; ++p) {
+            const float d = __bfloat162float(dzs[p][co]);
+            const int pbase = (p >> 4) * 18 + (p & 15);
+            accb += d;
+#pragma unroll
+            for (int j = 0; j < 5; ++j) acc[j] = fmaf(d, xflat[koff[j] + pbase], acc[j]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        if (kk[j] < 36) {
+            const int tap = kk[j] >> 2, ci = kk[j] & 3;
+            atomicAdd(dw + (co * 4 + ci) * 9 + tap, acc[j]);
+        }
+    }
+    if (g == 0) atomicAdd(db + co, accb);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// 2x2 max pool, NHWC bf16, 8 channels (16 B) per thread                                 (Unet.py:51-63)
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 ld16(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+
+__global__ void __launch_bounds__(256)
+maxpool_kernel(const __nv_bfloat16* __restrict__ in, int in_pitch, int in_c0, __nv_bfloat16* __restrict__ out,
+               int C, int n_img, int Ho, int Wo)
+{
+    const int groups = C / 8;
+    const size_t total = (size_t)n_img * Ho * Wo * groups;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int gch = i % groups;
+        size_t r = i / groups;
+        const int xo = r % Wo; r /= Wo;
+        const int yo = r % Ho;
+        const int n = r / Ho;
+        const __nv_bfloat16* p00 = in + (((size_t)n * 2 * Ho + 2 * yo) * (2 * Wo) + 2 * xo) * in_pitch + in_c0 + gch * 8;
+        const uint4 a = ld16(p00), b = ld16(p00 + in_pitch), c = ld16(p00 + (size_t)2 * Wo * in_pitch), d = ld16(p00 + (size_t)(2 * Wo + 1) * in_pitch);
+        const uint32_t aw[4] = { a.x, a.y, a.z, a.w }, bw[4] = { b.x, b.y, b.z, b.w }, cw[4] = { c.x, c.y, c.z, c.w }, dw[4] = { d.x, d.y, d.z, d.w };
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float lo = fmaxf(fmaxf(bf_lo(aw[j]), bf_lo(bw[j])), fmaxf(bf_lo(cw[j]), bf_lo(dw[j])));
+            const float hi = fmaxf(fmaxf(bf_hi(aw[j]), bf_hi(bw[j])), fmaxf(bf_hi(cw[j]), bf_hi(dw[j])));
+            o[j] = pack_bf2(lo, hi);
+        }
+        *reinterpret_cast<uint4*>(out + (((size_t)n * Ho + yo) * Wo + xo) * C + gch * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+// dZ[full res] = ( dskip + (first arg-max of the window ? dP : 0) ) * lrelu'(A)
+//   A     : activation that was pooled (lives in a concat buffer: pitch a_pitch, offset a_c0)
+//   dskip : gradient that reached A through the skip connection (d_cat buffer, same pitch/offset)
+//   dP    : gradient of the pooled tensor (compact)
+// PyTorch's max_pool2d backward routes to the FIRST maximum in window scan order; so do we.
+__global__ void __launch_bounds__(256)
+maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restrict__ dskip, int a_pitch, int a_c0,
+                   const __nv_bfloat16* __restrict__ dP, __nv_bfloat16* __restrict__ dZ, int C, int n_img, int Ho, int Wo)
+{
+    const int groups = C / 8;
+    const size_t total = (size_t)n_img * Ho * Wo * groups;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int gch = i % groups;
+        size_t r = i / groups;
+        const int xo = r % Wo; r /= Wo;
+        const int yo = r % Ho;
+        const int n = r / Ho;
+        const size_t pix00 = ((size_t)n * 2 * Ho + 2 * yo) * (2 * Wo) + 2 * xo;
+        const size_t offs[4] = { pix00, pix00 + 1, pix00 + (size_t)2 * Wo, pix00 + (size_t)2 * Wo + 1 };
+        uint32_t a[4][4], s[4][4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint4 av = ld16(A + offs[k] * a_pitch + a_c0 + gch * 8);
+            const uint4 sv = ld16(dskip + offs[k] * a_pitch + a_c0 + gch * 8);
+            a[k][0] = av.x; a[k][1] = av.y; a[k][2] = av.z; a[k][3] = av.w;
+            s[k][0] = sv.x; s[k][1] = sv.y; s[k][2] = sv.z; s[k][3] = sv.w;
+        }
+        const uint4 dpv = ld16(dP + (((size_t)n * Ho + yo) * Wo + xo) * C + gch * 8);
+        const uint32_t dp[4] = { dpv.x, dpv.y, dpv.z, dpv.w };
+        uint32_t o[4][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                float av[4], sv[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    av[k] = half ? bf_hi(a[k][j]) : bf_lo(a[k][j]);
+                    sv[k] = half ? bf_hi(s[k][j]) : bf_lo(s[k][j]);
+                }
+                const float g = half ? bf_hi(dp[j]) : bf_lo(dp[j]);
+                int arg = 0;
+                float m = av[0];
+#pragma unroll
+                for (int k = 1; k < 4; ++k) if (av[k] > m) { m = av[k]; arg = k; }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float v = (sv[k] + (k == arg ? g : 0.0f)) * (av[k] > 0.0f ? 1.0f : 0.2f);
+                    const uint32_t bits = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v));
+                    if (half) o[k][j] |= bits << 16; else o[k][j] = bits;
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            *reinterpret_cast<uint4*>(dZ + offs[k] * C + gch * 8) = make_uint4(o[k][0], o[k][1], o[k][2], o[k][3]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// bias gradient: out[c] += sum over pixels of g[p][c0 + c]   (NHWC bf16, C % 8 == 0, C <= 512)
+// thread handles 8 channels of a pixel; block = (C/8) x (256/(C/8)) ; smem reduce; atomics per block.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+colsum_kernel(const __nv_bfloat16* __restrict__ g, int pitch, int c0, int C, size_t npix, float* __restrict__ out)
+{
+    __shared__ float red[256][8 + 1];
+    const int groups = C / 8;                 // <= 64
+    const int lanes = 256 / groups;           // pixel lanes per block
+    const int gch = threadIdx.x % groups, pl = threadIdx.x / groups;
+    float acc[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+    if (pl < lanes) {
+        for (size_t p = (size_t)blockIdx.x * lanes + pl; p < npix; p += (size_t)gridDim.x * lanes) {
+            const uint4 v = ld16(g + p * pitch + c0 + gch * 8);
+            const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { acc[2 * j] += bf_lo(w[j]); acc[2 * j + 1] += bf_hi(w[j]); }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[threadIdx.x][j] = acc[j];
+    __syncthreads();
+    if (threadIdx.x < C) {
+        const int c = threadIdx.x, gq = c / 8, j = c % 8;
+        float s = 0.f;
+        for (int l = 0; l < lanes; ++l) s += red[l * groups + gq][j];
+        atomicAdd(out + c, s);
+    }
+    if (C > 256 && threadIdx.x + 256 < C) {
+        const int c = threadIdx.x + 256, gq = c / 8, j = c % 8;
+        float s = 0.f;
+        for (int l = 0; l < lanes; ++l) s += red[l * groups + gq][j];
+        atomicAdd(out + c, s);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// head: conv10_1 (1x1, 32 -> 4, no activation; Unet.py:46,88) + L1 loss (losses.py:32) + its backward.
+//   out[n][co][y][x] (f32 NCHW) = b[co] + sum_ci a[p][ci] w[co][ci]
+//   loss += sum |out - t| / numel ;  dout = sign(out - t)/numel
+//   dz[p][ci] = (sum_co dout[co] w[co][ci]) * lrelu'(a[p][ci])     (bf16 NHWC, feeds conv9_2's backward)
+//   dw[co][ci] += dout[co] a[p][ci] ; db[co] += dout[co]
+// One pixel per thread per iteration, persistent blocks; per-thread partial dW in registers.
+// ---------------------------------------------------------------------------------------------------
+template <bool TRAIN>
+__global__ void __launch_bounds__(256)
+head_kernel(const __nv_bfloat16* __restrict__ a, const float* __restrict__ w, const float* __restrict__ b,
+            float* __restrict__ out, const float* __restrict__ target, __nv_bfloat16* __restrict__ dz,
+            float* __restrict__ dw, float* __restrict__ db, float* __restrict__ loss,
+            int n_img, size_t plane, float inv_numel)
+{
+    __shared__ float ws[4][32];
+    __shared__ float bs[4];
+    __shared__ float red[4 * 32 + 4 + 1];
+    const int tid = threadIdx.x;
+    if (tid < 128) ws[tid >> 5][tid & 31] = w[tid];
+    if (tid < 4) bs[tid] = b[tid];
+    if (TRAIN && tid < 133) red[tid] = 0.f;
+    __syncthreads();
+    float pdw[4][32];
+    float pdb[4] = { 0, 0, 0, 0 }, ploss = 0.f;
+    if (TRAIN) {
+#pragma unroll
+        for (int co = 0; co < 4; ++co)
+#pragma unroll
+            for (int ci = 0; ci < 32; ++ci) pdw[co][ci] = 0.f;
+    }
+    const size_t total = (size_t)n_img * plane;
+    for (size_t p = blockIdx.x * (size_t)blockDim.x + tid; p < total; p += (size_t)gridDim.x * blockDim.x) {
+        const size_t n = p / plane, l = p - n * plane;
+        float av[32];
+        const uint4* ap = reinterpret_cast<const uint4*>(a + p * 32);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const uint4 v = __ldg(ap + g);
+            const uint32_t wv[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { av[g * 8 + 2 * j] = bf_lo(wv[j]); av[g * 8 + 2 * j + 1] = bf_hi(wv[j]); }
+        }
+        float o[4];
+#pragma unroll
+        for (int co = 0; co < 4; ++co) {
+            float s = bs[co];
+#pragma unroll
+            for (int ci = 0; ci < 32; ++ci) s = fmaf(av[ci], ws[co][ci], s);
+            o[co] = s;
+            out[(n * 4 + co) * plane + l] = s;
+        }
+        if (TRAIN) {
+            float d[4];
+#pragma unroll
+            for (int co = 0; co < 4; ++co) {
+                const float e = o[co] - __ldg(target + (n * 4 + co) * plane + l);
+                ploss += fabsf(e);
+                d[co] = (e > 0.f ? inv_numel : (e < 0.f ? -inv_numel : 0.f));
+                pdb[co] += d[co];
+            }
+            uint32_t zo[16];
+#pragma unroll
+            for (int ci = 0; ci < 32; ci += 2) {
+                float g0 = 0.f, g1 = 0.f;
+#pragma unroll
+                for (int co = 0; co < 4; ++co) { g0 = fmaf(d[co], ws[co][ci], g0); g1 = fmaf(d[co], ws[co][ci + 1], g1); }
+                g0 *= (av[ci] > 0.f ? 1.0f : 0.2f);
+                g1 *= (av[ci + 1] > 0.f ? 1.0f : 0.2f);
+                zo[ci >> 1] = pack_bf2(g0, g1);
+            }
+            uint4* zp = reinterpret_cast<uint4*>(dz + p * 32);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) zp[g] = make_uint4(zo[4 * g], zo[4 * g + 1], zo[4 * g + 2], zo[4 * g + 3]);
+#pragma unroll
+            for (int co = 0; co < 4; ++co)
+#pragma unroll
+                for (int ci = 0; ci < 32; ++ci) pdw[co][ci] = fmaf(d[co], av[ci], pdw[co][ci]);
+        }
+    }
+    if (TRAIN) {
+        // warp reduce then shared atomics then one global atomic per block per value
+#pragma unroll
+        for (int co = 0; co < 4; ++co) {
+#pragma unroll
+            for (int ci = 0; ci < 32; ++ci) {
+                float v = pdw[co][ci];
+#pragma unroll
+                for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+                if ((tid & 31) == 0) atomicAdd(&red[co * 32 + ci], v);
+            }
+            float v = pdb[co];
+#pragma unroll
+            for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+            if ((tid & 31) == 0) atomicAdd(&red[128 + co], v);
+        }
+        float v = ploss;
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+        if ((tid & 31) == 0) atomicAdd(&red[132], v);
+        __syncthreads();
+        if (tid < 128) atomicAdd(dw + tid, red[tid]);
+        else if (tid < 132) atomicAdd(db + (tid - 128), red[tid]);
+        else if (tid == 132) atomicAdd(loss, red[132] * inv_numel);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Adam (torch.optim.Adam semantics, ELD_model.py:400-401): one pass over the flat parameter buffer.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+            size_t n, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt, float gscale)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float gi = g[i] * gscale;
+        const float pi = p[i];
+        if (wd != 0.f) gi = fmaf(wd, pi, gi);
+        const float mi = fmaf(b1, m[i], (1.f - b1) * gi);
+        const float vi = fmaf(b2, v[i], (1.f - b2) * gi * gi);
+        m[i] = mi;
+        v[i] = vi;
+        const float denom = sqrtf(vi) / bc2_sqrt + eps;
+        p[i] = pi - (lr / bc1) * (mi / denom);
+    }
+}
+
+// ---- launch helpers ---------------------------------------------------------------------------------
+static inline int grid_for(size_t work, int per_block, int cap)
+{
+    size_t b = (work + per_block - 1) / per_block;
+    if (b > (size_t)cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+int launch_first_conv(eld_ctx* ctx, const float* x, const float* w, const float* b, void* y, int n, int H, int W, cudaStream_t st)
+{
+    dim3 grid((W + 15) / 16, (H + 15) / 16, n);
+    first_conv_kernel<<<grid, 256, 0, st>>>(x, w, b, static_cast<__nv_bfloat16*>(y), H, W);
+    ELD_CHECK_CUDA(cudaGetLastError());
+    count_launch(ctx);
+    return ELD_OK;
+}
+
+int launch_first_conv_wgrad(eld_ctx* ctx, const float* x, const void* dz, float* dw, float* db, int n, int H, int W, cudaStream_t st)
+{
+    ELD_REQUIRE(H % 16 == 0 && W % 16 == 0, "first-layer wgrad: H, W must be multiples of 16");
+    const int tiles = n * (H / 16) * (W / 16);
+    const int grid = tiles < 2 * ctx->num_sms ? tiles : 2 * ctx->num_sms;
+    first_conv_wgrad_kernel<<<grid, 256, 0, st>>>(x, static_cast<const __nv_bfloat16*>(dz), dw, db, n, H, W);
+    ELD_CHECK_CUDA(cudaGetLastError());
+    count_launch(ctx);
+    return ELD_OK;
+}
+
+int launch_maxpool(eld_ctx* ctx, const void* in, int in_pitch, int in_c0, void* out, int C, int n, int Ho, int Wo, cudaStream_t st)
+{
+    const size_t work = (size_t)n * Ho * Wo * (C / 8);
+    maxpool_kernel<<<grid_for(work, 256, 16 * ctx->num_sms), 256, 0, st>>>(
+        static_cast<const __nv_bfloat16*>(in), in_pitch, in_c0, static_cast<__nv_bfloat16*>(out), C, n, Ho, Wo);
+    ELD_CHECK_CUDA(cudaGetLastError());
+    count_launch(ctx);
+    return ELD_OK;
+}
+
+int launch_maxpool_bwd(eld_ctx* ctx, const void* A, const void* dskip, int a_pitch, int a_c0, const void* dP, void* dZ,
+                       int C, int n, int Ho, int Wo, cudaStream_t st)
+{
+    const size_t work = (size_t)n * Ho * Wo * (C / 8);
+    maxpool_bwd_kernel<<<grid_for(work, 256, 16 * ctx->num_sms), 256, 0, st>>>(
+        static_cast<const __nv_bfloat16*>(A), static_cast<const __nv_bfloat16*>(dskip), a_pitch, a_c0,
+        static_cast<const __nv_bfloat16*>(dP), static_cast<__nv_bfloat16*>(dZ), C, n, Ho, Wo);
+    ELD_CHECK_CUDA(cudaGetLastError());
+    count_launch(ctx);
+    return ELD_OK;
+}
+
+int launch_colsum(eld_ctx* ctx, const void* g, int pitch, int c0, int C, size_t npix, float* out, cudaStream_t st)
+{
+    ELD_REQUIRE(C % 8 == 0 && C <= 512, "colsum: C=%d must be a multiple of 8 and <= 512", C);
+    const int lanes = 256 / (C / 8);
+    colsum_kernel<<<grid_for(npix, lanes * 8, 4 * ctx->num_sms), 256, 0, st>>>(
+        static_cast<const __nv_bfloat16*>(g), pitch, c0, C, npix, out);
+    ELD_CHECK_CUDA(cudaGetLastError());
+    count_launch(ctx);
+    return ELD_OK;
+}
+
+int launch_head(eld_ctx* ctx, const void* a, const float* w, const float* b, float* out, const float* target, void* dz,
+                float* dw, float* db, float* loss, int n, size_t plane, cudaStream_t st)
+{
+    const size_t total = (size_t)n * plane;
+    const float inv = 1.0f / (float)(total * 4);
+    if (target) {
+        head_kernel<true><<<grid_for(total, 256 * 8, 2 * ctx->num_sms), 256, 0, st>>>(
+            static_cast<const __nv_bfloat16*>(a), w, b, out, target, static_cast<__nv_bfloat16*>(dz), dw, db, loss, n, plane, inv);
+    } else {
+        head_kernel<false><<<grid_for(total, 256, 8 * ctx->num_sms), 256, 0, st>>>(
+            static_cast<const __nv_bfloat16*>(a), w, b, out, nullptr, nullptr, nullptr, nullptr, nullptr, n, plane, inv);
+    }
+    ELD_CHECK_CUDA(cudaGetLastError());
+    count_launch(ctx);
+    return ELD_OK;
+}
+
+int launch_adam(eld_ctx* ctx, float* p, const float* g, float* m, float* v, size_t n, float lr, float b1, float b2,
+                float eps, float wd, int step, float gscale, cudaStream_t st)
+{
+    const float bc1 = 1.0f - powf(b1, (float)step);
+    const float bc2 = 1.0f - powf(b2, (float)step);
+    adam_kernel<<<grid_for(n, 256 * 4, 8 * ctx->num_sms), 256, 0, st>>>(p, g, m, v, n, lr, b1, b2, eps, wd, bc1, sqrtf(bc2), gscale);
+    ELD_CHECK_CUDA(cudaGetLastError());
+    count_launch(ctx);
+    return ELD_OK;
+}
+
+}  // namespace eld

@@ -2,6 +2,7 @@
 // geometry, weight packing, and the C-ABI primitives (include/eld_b200_unet.h).
 #include "common.cuh"
 #include "conv_umma.cuh"
+#include "wgrad_umma.cuh"
 #include "unet_prims.h"
 
 namespace eld {
@@ -81,10 +82,83 @@ int launch_conv_gemm(eld_ctx* ctx, const GemmOp& op, cudaStream_t st)
         if (rc) return rc;
     }
     const size_t smem = (size_t)stages * stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/;
-    ELD_CHECK_CUDA(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int total_tiles = op.n_img * p.tiles_x * p.tiles_y * (p.n_total / p.n_tile);
     const int grid = total_tiles < ctx->num_sms ? total_tiles : ctx->num_sms;
     conv_umma_kernel<<<grid, kConvThreads, smem, st>>>(tmA, tmB, p);
+    ELD_CHECK_CUDA(cudaGetLastError());
+    count_launch(ctx);
+    return ELD_OK;
+}
+
+int init_gemm_kernels(eld_ctx* ctx)
+{
+    ELD_CHECK_CUDA(cudaSetDevice(ctx->device));
+    ELD_CHECK_CUDA(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    ELD_CHECK_CUDA(cudaFuncSetAttribute(wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    return ELD_OK;
+}
+
+int launch_wgrad(eld_ctx* ctx, const WgradOp& op, cudaStream_t st)
+{
+    ELD_REQUIRE(op.H % 4 == 0 && op.W % 16 == 0, "wgrad tile: H=%d must be a multiple of 4 and W=%d of 16", op.H, op.W);
+    ELD_REQUIRE(op.p_ch % 32 == 0 && op.q_ch % 32 == 0, "wgrad tile: channel counts must be multiples of 32");
+    WgradParams p{};
+    p.n_img = op.n_img; p.H = op.H; p.W = op.W;
+    p.chunks_x = op.W / 16; p.chunks_y = op.H / 4;
+    p.mode = op.mode; p.taps = op.mode == WG_CONV ? 9 : 4;
+    p.p_ch = op.p_ch; p.p_c0 = op.p_c0;
+    p.box_ch = (op.p_ch % 64 == 0) ? 64 : 32;
+    p.boxes_per_mtile = 128 / p.box_ch;
+    const int total_boxes = p.taps * (op.p_ch / p.box_ch);
+    p.m_tiles = (total_boxes + p.boxes_per_mtile - 1) / p.boxes_per_mtile;
+    p.q_ch = op.q_ch; p.q_c0 = op.q_c0;
+    p.q_box_ch = (op.q_ch % 64 == 0) ? 64 : 32;
+    p.n_tile = op.q_ch <= 256 ? op.q_ch : 256;
+    ELD_REQUIRE(op.q_ch % p.n_tile == 0, "wgrad tile: N=%d not divisible by %d", op.q_ch, p.n_tile);
+    p.n_tiles = op.q_ch / p.n_tile;
+    const int total_chunks = op.n_img * p.chunks_x * p.chunks_y;
+    int ksplit = (2 * ctx->num_sms) / (p.m_tiles * p.n_tiles);
+    if (ksplit < 1) ksplit = 1;
+    if (ksplit > total_chunks) ksplit = total_chunks;
+    p.ksplit = ksplit;
+    const int stage_bytes = kWgradKP * (256 + 2 * p.n_tile);
+    int stages = (200 * 1024) / stage_bytes;
+    if (stages > 8) stages = 8;
+    if (stages < 2) stages = 2;
+    p.stages = stages;
+    int cols = 32;
+    while (cols < p.n_tile) cols *= 2;
+    p.tmem_cols = cols;
+    p.dw = op.dw;
+
+    CUtensorMap tmP, tmQ;
+    const cuuint64_t eb = 2;
+    if (op.mode == WG_CONV) {
+        cuuint64_t dims[5] = { (cuuint64_t)op.p_pitch, (cuuint64_t)op.W, (cuuint64_t)op.H, (cuuint64_t)op.n_img, 1 };
+        cuuint64_t str[4] = { op.p_pitch * eb, (cuuint64_t)op.W * op.p_pitch * eb, (cuuint64_t)op.H * op.W * op.p_pitch * eb,
+                              (cuuint64_t)op.n_img * op.H * op.W * op.p_pitch * eb };
+        cuuint32_t box[5] = { (cuuint32_t)p.box_ch, 16, 4, 1, 1 };
+        int rc = encode(ctx, &tmP, op.p, 5, dims, str, box, p.box_ch * 2);
+        if (rc) return rc;
+    } else {
+        cuuint64_t dims[5] = { (cuuint64_t)op.p_pitch, 2, (cuuint64_t)op.W, 2, (cuuint64_t)op.n_img * op.H };
+        cuuint64_t str[4] = { op.p_pitch * eb, 2 * op.p_pitch * eb, (cuuint64_t)2 * op.W * op.p_pitch * eb,
+                              (cuuint64_t)4 * op.W * op.p_pitch * eb };
+        cuuint32_t box[5] = { (cuuint32_t)p.box_ch, 1, 16, 1, 4 };
+        int rc = encode(ctx, &tmP, op.p, 5, dims, str, box, p.box_ch * 2);
+        if (rc) return rc;
+    }
+    {
+        cuuint64_t dims[5] = { (cuuint64_t)op.q_pitch, (cuuint64_t)op.W, (cuuint64_t)op.H, (cuuint64_t)op.n_img, 1 };
+        cuuint64_t str[4] = { op.q_pitch * eb, (cuuint64_t)op.W * op.q_pitch * eb, (cuuint64_t)op.H * op.W * op.q_pitch * eb,
+                              (cuuint64_t)op.n_img * op.H * op.W * op.q_pitch * eb };
+        cuuint32_t box[5] = { (cuuint32_t)p.q_box_ch, 16, 4, 1, 1 };
+        int rc = encode(ctx, &tmQ, op.q, 5, dims, str, box, p.q_box_ch * 2);
+        if (rc) return rc;
+    }
+    const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
+    const int grid = p.m_tiles * p.n_tiles * p.ksplit;
+    wgrad_umma_kernel<<<grid, kWgradThreads, smem, st>>>(tmP, tmQ, p);
     ELD_CHECK_CUDA(cudaGetLastError());
     count_launch(ctx);
     return ELD_OK;
@@ -183,4 +257,30 @@ extern "C" int eld_deconv2x2_dgrad_bf16(eld_ctx* ctx, const void* dy, int dy_pit
     op.epi_mode = EPI_STORE; op.act = act; op.out = dx; op.out_pitch = dx_pitch; op.out_c0 = dx_c0; op.bias = nullptr;
     op.aux = aux; op.aux_pitch = aux_pitch; op.aux_c0 = aux_c0;
     return launch_conv_gemm(ctx, op, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int eld_conv3x3_wgrad_bf16(eld_ctx* ctx, const void* x, int x_pitch, int x_c0, int cin,
+                                      const void* dz, int dz_pitch, int dz_c0, int cout,
+                                      float* dw, int n, int h, int w, void* stream)
+{
+    ELD_REQUIRE(ctx && x && dz && dw, "eld_conv3x3_wgrad_bf16: NULL argument");
+    ELD_CHECK_CUDA(cudaSetDevice(ctx->device));
+    WgradOp op{};
+    op.mode = WG_CONV; op.p = x; op.p_pitch = x_pitch; op.p_c0 = x_c0; op.p_ch = cin;
+    op.q = dz; op.q_pitch = dz_pitch; op.q_c0 = dz_c0; op.q_ch = cout;
+    op.n_img = n; op.H = h; op.W = w; op.dw = dw;
+    return launch_wgrad(ctx, op, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int eld_deconv2x2_wgrad_bf16(eld_ctx* ctx, const void* x, int x_pitch, int x_c0, int cin,
+                                        const void* dy, int dy_pitch, int dy_c0, int cout,
+                                        float* dw, int n, int h, int w, void* stream)
+{
+    ELD_REQUIRE(ctx && x && dy && dw, "eld_deconv2x2_wgrad_bf16: NULL argument");
+    ELD_CHECK_CUDA(cudaSetDevice(ctx->device));
+    WgradOp op{};
+    op.mode = WG_DECONV; op.p = dy; op.p_pitch = dy_pitch; op.p_c0 = dy_c0; op.p_ch = cout;
+    op.q = x; op.q_pitch = x_pitch; op.q_c0 = x_c0; op.q_ch = cin;
+    op.n_img = n; op.H = h; op.W = w; op.dw = dw;
+    return launch_wgrad(ctx, op, static_cast<cudaStream_t>(stream));
 }

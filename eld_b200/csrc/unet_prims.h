@@ -5,6 +5,10 @@
 
 namespace eld {
 
+enum { A_CONV = 0, A_GATHER = 1 };
+enum { EPI_STORE = 0, EPI_SHUFFLE = 1 };
+enum { ACT_NONE = 0, ACT_LRELU = 1, ACT_MASK = 2 };
+enum { WG_CONV = 0, WG_DECONV = 1 };
 enum { PACK_CONV_FPROP = 0, PACK_CONV_DGRAD = 1, PACK_DECONV_FPROP = 2, PACK_DECONV_DGRAD = 3 };
 
 struct GemmOp {
@@ -22,6 +26,17 @@ struct GemmOp {
     int aux_pitch, aux_c0;
 };
 
+struct WgradOp {
+    int mode;            // WG_CONV / WG_DECONV
+    const void* p;       // conv: layer input X ; deconv: d(up) on the fine grid
+    int p_pitch, p_c0, p_ch;
+    const void* q;       // conv: dZ ; deconv: deconv input X (coarse grid)
+    int q_pitch, q_c0, q_ch;
+    int n_img, H, W;     // pixel grid of the reduction (deconv: coarse)
+    float* dw;           // f32, PyTorch layout, accumulated into (zero it first)
+};
+int init_gemm_kernels(eld_ctx* ctx);   // opt in to large dynamic smem (call once, outside graph capture)
+int launch_wgrad(eld_ctx* ctx, const WgradOp& op, cudaStream_t st);
 int launch_conv_gemm(eld_ctx* ctx, const GemmOp& op, cudaStream_t st);
 int launch_pack_weights(eld_ctx* ctx, const float* w, void* out, int cout, int cin, int kind, cudaStream_t st);
 

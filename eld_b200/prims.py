@@ -66,3 +66,21 @@ def deconv2x2_dgrad(dy, dy_c0, cout, w_packed, dx, dx_c0, cin, act=ACT_NONE, aux
                                               aux.shape[3] if aux is not None else 0, aux_c0, _st())
     _lib.check(rc, 'eld_deconv2x2_dgrad_bf16')
     return dx
+
+
+def conv3x3_wgrad(x, x_c0, cin, dz, dz_c0, cout, dw):
+    """dw: f32 [cout,cin,3,3], accumulated into."""
+    n, h, w, xp = x.shape
+    rc = _lib.load().eld_conv3x3_wgrad_bf16(_ctx(x), x.data_ptr(), xp, x_c0, cin, dz.data_ptr(), dz.shape[3], dz_c0,
+                                            cout, dw.data_ptr(), n, h, w, _st())
+    _lib.check(rc, 'eld_conv3x3_wgrad_bf16')
+    return dw
+
+
+def deconv2x2_wgrad(x, x_c0, cin, dy, dy_c0, cout, dw):
+    """x coarse [n,h,w,*], dy fine [n,2h,2w,*]; dw: f32 [cin,cout,2,2], accumulated into."""
+    n, h, w, xp = x.shape
+    rc = _lib.load().eld_deconv2x2_wgrad_bf16(_ctx(x), x.data_ptr(), xp, x_c0, cin, dy.data_ptr(), dy.shape[3], dy_c0,
+                                              cout, dw.data_ptr(), n, h, w, _st())
+    _lib.check(rc, 'eld_deconv2x2_wgrad_bf16')
+    return dw

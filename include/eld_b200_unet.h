@@ -40,4 +40,38 @@ int eld_deconv2x2_dgrad_bf16(eld_ctx* ctx, const void* dy, int dy_pitch, int dy_
                              int n, int h, int w, int act, const void* aux, int aux_pitch, int aux_c0,
                              void* stream);
 
+/* Weight gradients, accumulated (+=) in f32 into the PyTorch-layout gradient `dw` (zero it once per
+ * step): conv dW[co][ci][kh][kw] += sum_pixels dz[.,co] * x[. + (kh-1,kw-1), ci]   (autograd of Unet.py:11-44);
+ * deconv dWt[ci][co][kh][kw] += sum_pixels x[n,h,w,ci] * dy[n,2h+kh,2w+kw,co].  (h, w) = x's grid. */
+int eld_conv3x3_wgrad_bf16(eld_ctx* ctx, const void* x, int x_pitch, int x_c0, int cin,
+                           const void* dz, int dz_pitch, int dz_c0, int cout,
+                           float* dw, int n, int h, int w, void* stream);
+int eld_deconv2x2_wgrad_bf16(eld_ctx* ctx, const void* x, int x_pitch, int x_c0, int cin,
+                             const void* dy, int dy_pitch, int dy_c0, int cout,
+                             float* dw, int n, int h, int w, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Whole-network step.  Parameters / gradients / Adam moments are FLAT fp32 device buffers in the
+ * reference's state_dict order (conv1_1.weight, conv1_1.bias, ... conv10_1.bias; Unet.py:11-46), conv
+ * weights OIHW, deconv weights IOHW - so released checkpoints copy in 1:1 and DDP all-reduces one buffer.
+ */
+typedef struct eld_unet eld_unet;
+size_t eld_unet_param_count(void);                                   /* 7,760,484 for UNetSeeInDark(4,4) */
+int    eld_unet_param_offset(const char* layer, int is_bias, size_t* offset, size_t* count);
+size_t eld_unet_workspace_bytes(int n, int h, int w, int train);     /* activations (+gradients) + packed weights */
+/* h % 128 == 0, w % 256 == 0.  The caller owns `workspace` (device memory) for the lifetime of the object. */
+int    eld_unet_create(eld_ctx* ctx, int n, int h, int w, int train, void* workspace, size_t bytes, eld_unet** out);
+void   eld_unet_destroy(eld_unet* u);
+/* ELDModel.forward (ELD_model.py:422-432): x f32 NCHW [n][4][h][w] -> out f32 NCHW [n][4][h][w] */
+int    eld_unet_forward(eld_unet* u, const float* params, const float* x, float* out, void* stream);
+/* forward + L1 loss (mean |out-target|, losses.py:32) + backward (ELD_model.py:411-420): grads is zeroed
+ * and filled; *loss (device float) receives the mean absolute error.  No optimizer step, no host sync. */
+int    eld_unet_train_step(eld_unet* u, const float* params, const float* x, const float* target,
+                           float* out, float* grads, float* loss, void* stream);
+/* torch.optim.Adam step (ELD_model.py:400-401,475) on the flat buffers; grads are multiplied by
+ * grad_scale first (1/world_size after a SUM all-reduce).  step counts from 1. */
+int    eld_adam_step(eld_ctx* ctx, float* params, const float* grads, float* m, float* v, size_t n,
+                     float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                     float grad_scale, void* stream);
+
 #endif

@@ -97,3 +97,49 @@ def test_deconv2x2_fprop_and_dgrad(torch, case):
                                        Wt.bfloat16().float().permute(0, 1, 2, 3), stride=2)
     refdx = refdx * torch.where(x.float().permute(0, 3, 1, 2) > 0, 1.0, 0.2)
     _close(torch, dx.permute(0, 3, 1, 2), refdx)
+
+
+def _close_w(torch, got, ref):
+    rms = ref.pow(2).mean().sqrt().item()
+    err = (got - ref).abs().max().item()
+    assert err <= 5e-3 * rms + 1e-6, 'wgrad max err %g vs rms %g' % (err, rms)
+
+
+WGRAD_CASES = [  # n, h, w, cin, cout, x_c0, x_pitch
+    (1, 8, 16, 32, 32, 0, 32), (2, 16, 32, 32, 64, 0, 32), (1, 16, 16, 64, 64, 0, 64), (2, 16, 16, 64, 32, 32, 128),
+    (1, 8, 32, 128, 128, 0, 128), (1, 8, 16, 256, 256, 0, 256), (1, 8, 16, 512, 512, 0, 512), (2, 8, 16, 512, 256, 0, 512),
+    (3, 32, 32, 128, 64, 0, 128), (1, 64, 64, 32, 32, 0, 32),
+]
+
+
+@pytest.mark.parametrize('case', WGRAD_CASES)
+def test_conv3x3_wgrad(torch, case):
+    """tcgen05 wgrad (pixels are the GEMM K dimension, MN-major operands) vs autograd of F.conv2d."""
+    from eld_b200 import prims
+    n, h, w, cin, cout, x_c0, xp = case
+    g = torch.Generator(device='cuda').manual_seed(17)
+    x = torch.randn(n, h, w, xp, device='cuda', generator=g).bfloat16()
+    dz = torch.randn(n, h, w, cout, device='cuda', generator=g).bfloat16()
+    dw = torch.zeros(cout, cin, 3, 3, device='cuda')
+    prims.conv3x3_wgrad(x, x_c0, cin, dz, 0, cout, dw)
+    xin = x[..., x_c0:x_c0 + cin].float().permute(0, 3, 1, 2).contiguous()
+    ref = torch.nn.grad.conv2d_weight(xin, (cout, cin, 3, 3), dz.float().permute(0, 3, 1, 2).contiguous(), padding=1)
+    _close_w(torch, dw, ref)
+    prims.conv3x3_wgrad(x, x_c0, cin, dz, 0, cout, dw)      # accumulates
+    _close_w(torch, dw, 2 * ref)
+
+
+@pytest.mark.parametrize('case', [(1, 8, 16, 64, 32), (2, 16, 16, 128, 64), (1, 8, 16, 256, 128), (2, 8, 16, 512, 256)])
+def test_deconv2x2_wgrad(torch, case):
+    from eld_b200 import prims
+    n, h, w, cin, cout = case
+    g = torch.Generator(device='cuda').manual_seed(23)
+    x = torch.randn(n, h, w, cin, device='cuda', generator=g).bfloat16()
+    dy = torch.randn(n, 2 * h, 2 * w, 2 * cout, device='cuda', generator=g).bfloat16()
+    dw = torch.zeros(cin, cout, 2, 2, device='cuda')
+    prims.deconv2x2_wgrad(x, 0, cin, dy, 0, cout, dw)
+    xin = x.float().permute(0, 3, 1, 2).contiguous().requires_grad_(False)
+    wt = torch.zeros(cin, cout, 2, 2, device='cuda', requires_grad=True)
+    out = torch.nn.functional.conv_transpose2d(xin, wt, stride=2)
+    out.backward(dy[..., :cout].float().permute(0, 3, 1, 2).contiguous())
+    _close_w(torch, dw, wt.grad)

@@ -1,0 +1,153 @@
+"""GPU parity of the whole tcgen05 U-Net step (through the C ABI) against the CPU oracle
+(oracle/unet_ref.py, pinned to the reference by tests/golden/unet_kat.npz).
+
+Stated tolerances (bf16 activations / bf16 GEMM operands, fp32 accumulation, fp32 master weights):
+  forward   : rel-L2(out, oracle fp32) <= 2e-2 ; |PSNR(out,target) - PSNR(oracle,target)| <= 0.05 dB
+  loss      : |loss - oracle| <= 1e-2 * oracle
+  gradients : per tensor cosine >= 0.99 and norm ratio in [0.95, 1.05] vs the fp32 oracle autograd
+  vs a bf16-EMULATED torch reference (same rounding points): rel-L2 <= 3e-3 - this is the bug detector.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+H, W = 128, 256          # smallest shape the tiles accept (8x16 patches at 1/16 scale)
+
+
+@pytest.fixture(scope='module')
+def torch():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip('no GPU')
+    return torch
+
+
+@pytest.fixture(scope='module')
+def nets(torch):
+    from eld_b200 import arch
+    from oracle.unet_ref import UNetSeeInDarkRef
+    torch.manual_seed(2018)
+    ours = arch.unet(4, 4).cuda()
+    torch.manual_seed(2018)
+    ref = UNetSeeInDarkRef(4, 4)
+    # the default init gives tiny outputs; scale the biases a little so every LeakyReLU branch is exercised
+    return ours, ref
+
+
+def _rel(a, b):
+    return ((a.double() - b.double()).norm() / (b.double().norm() + 1e-30)).item()
+
+
+def _q(t):
+    return t.bfloat16().float()
+
+
+def _emulated_forward(torch, net, x):
+    """fp32 torch math with the engine's rounding points: bf16 GEMM operands and bf16 activations."""
+    F = torch.nn.functional
+    lre = lambda v: torch.max(0.2 * v, v)
+    c = lambda name, v: _q(lre(F.conv2d(v, _q(getattr(net, name).weight), getattr(net, name).bias, padding=1)))
+    up = lambda name, v: _q(F.conv_transpose2d(v, _q(getattr(net, name).weight), getattr(net, name).bias, stride=2))
+    a = _q(lre(F.conv2d(x, net.conv1_1.weight, net.conv1_1.bias, padding=1)))      # first layer: fp32 weights
+    c1 = c('conv1_2', a)
+    c2 = c('conv2_2', c('conv2_1', F.max_pool2d(c1, 2)))
+    c3 = c('conv3_2', c('conv3_1', F.max_pool2d(c2, 2)))
+    c4 = c('conv4_2', c('conv4_1', F.max_pool2d(c3, 2)))
+    c5 = c('conv5_2', c('conv5_1', F.max_pool2d(c4, 2)))
+    c6 = c('conv6_2', c('conv6_1', torch.cat([up('upv6', c5), c4], 1)))
+    c7 = c('conv7_2', c('conv7_1', torch.cat([up('upv7', c6), c3], 1)))
+    c8 = c('conv8_2', c('conv8_1', torch.cat([up('upv8', c7), c2], 1)))
+    c9 = c('conv9_2', c('conv9_1', torch.cat([up('upv9', c8), c1], 1)))
+    return F.conv2d(c9, net.conv10_1.weight, net.conv10_1.bias)
+
+
+def test_forward_parity(torch, nets):
+    from oracle import ref_numpy
+    ours, ref = nets
+    torch.manual_seed(7)
+    x = torch.rand(2, 4, H, W)
+    t = torch.rand(2, 4, H, W)
+    with torch.no_grad():
+        want = ref(x)
+        emu = _emulated_forward(torch, ref.cuda(), x.cuda()).cpu()
+        ref.cpu()
+    got = ours(x.cuda()).cpu()
+    assert torch.isfinite(got).all()
+    assert _rel(got, emu) <= 3e-3, _rel(got, emu)
+    assert _rel(got, want) <= 2e-2, _rel(got, want)
+    d = abs(ref_numpy.psnr255(got.numpy(), t.numpy()) - ref_numpy.psnr255(want.numpy(), t.numpy()))
+    assert d <= 0.05, d
+
+
+def test_train_step_parity(torch, nets):
+    ours, ref = nets
+    torch.manual_seed(11)
+    x = torch.rand(2, 4, H, W)
+    t = torch.rand(2, 4, H, W)
+    ref.zero_grad()
+    out_ref = ref(x)
+    loss_ref = torch.nn.functional.l1_loss(out_ref, t)
+    loss_ref.backward()
+    out, loss = ours.train_step(x.cuda(), t.cuda())
+    assert abs(loss.item() - loss_ref.item()) <= 1e-2 * loss_ref.item()
+    assert _rel(out.cpu(), out_ref.detach()) <= 2e-2
+    bad = []
+    for (k, p), (k2, q) in zip(ref.named_parameters(), ours.named_parameters()):
+        assert k == k2
+        g, h = p.grad.double().reshape(-1), q.grad.double().cpu().reshape(-1)
+        cos = (g @ h / (g.norm() * h.norm() + 1e-300)).item()
+        ratio = (h.norm() / (g.norm() + 1e-300)).item()
+        if not (cos >= 0.99 and 0.95 <= ratio <= 1.05):
+            bad.append((k, cos, ratio))
+    assert not bad, bad
+    # .grad views and the flat buffer are the same memory
+    assert ours.conv1_1.weight.grad.data_ptr() == ours.flat_grads.data_ptr()
+
+
+def test_train_step_deterministic_forward_and_grad_reset(torch, nets):
+    ours, _ = nets
+    torch.manual_seed(3)
+    x = torch.rand(1, 4, H, W, device='cuda')
+    t = torch.rand(1, 4, H, W, device='cuda')
+    o1, l1 = ours.train_step(x, t)
+    g1 = ours.flat_grads.clone()
+    o2, l2 = ours.train_step(x, t)
+    assert torch.equal(o1, o2)
+    # gradients are re-zeroed every step; fp32 atomics make the sum order vary -> tiny tolerance
+    assert _rel(ours.flat_grads, g1) <= 1e-4
+
+
+def test_adam_matches_torch(torch, nets):
+    from eld_b200.arch import FusedAdam
+    ours, _ = nets
+    p0 = ours.flat_params.clone()
+    g = torch.randn_like(p0) * 1e-3
+    ours.flat_grads.copy_(g)
+    opt = FusedAdam(ours, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0)
+    tp = p0.clone().requires_grad_(True)
+    topt = torch.optim.Adam([tp], lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0)
+    for _ in range(3):
+        opt.step()
+        tp.grad = g.clone()
+        topt.step()
+    assert (ours.flat_params - tp.detach()).abs().max().item() <= 1e-6
+    sd = opt.state_dict()
+    assert set(sd['state'][0].keys()) == {'step', 'exp_avg', 'exp_avg_sq'}       # torch.optim.Adam checkpoint format
+    ours.flat_params.copy_(p0)
+
+
+def test_state_dict_roundtrip_keeps_flat_storage(torch, nets):
+    ours, ref = nets
+    sd = {k: v.clone() + 0.01 for k, v in ref.state_dict().items()}
+    ptr = ours.flat_params.data_ptr()
+    ours.load_state_dict(sd)
+    assert ours.flat_params.data_ptr() == ptr
+    assert torch.equal(ours.conv5_2.weight.detach().cpu(), sd['conv5_2.weight'])
+    ours.load_state_dict(ref.state_dict())
+
+
+def test_shape_contract(torch, nets):
+    from eld_b200 import _lib
+    ours, _ = nets
+    with pytest.raises(_lib.EldError):
+        ours(torch.rand(1, 4, 64, 64, device='cuda'))
