@@ -122,6 +122,40 @@ class UNetSeeInDark(nn.Module):
         return out, loss
 
 
+    def profile(self, x, target, steps=3):
+        """Per-launch CUDA-event timings of `steps` training steps: list of dicts
+        {name, ms (mean), flops, bytes} in launch order (see eld_unet_profile in the C ABI)."""
+        import numpy as np
+        lib = _lib.load()
+        n, _, h, w = x.shape
+        eng = self._engine(n, h, w, True)
+        self.train_step(x, target)
+        acc = None
+        for _ in range(steps):
+            lib.eld_unet_profile(eng, 1)
+            self.train_step(x, target)
+            cap = 512
+            names = ctypes.create_string_buffer(32 * cap)
+            ms = np.zeros(cap, np.float32)
+            fl = np.zeros(cap, np.float64)
+            by = np.zeros(cap, np.float64)
+            cnt = ctypes.c_int(0)
+            _lib.check(lib.eld_unet_profile_read(eng, cap, names, ms.ctypes.data, fl.ctypes.data, by.ctypes.data,
+                                                 ctypes.byref(cnt)), 'eld_unet_profile_read')
+            k = cnt.value
+            recs = [dict(name=names.raw[32 * i:32 * i + 32].split(b'\0')[0].decode(), ms=float(ms[i]),
+                         flops=float(fl[i]), bytes=float(by[i])) for i in range(k)]
+            if acc is None:
+                acc = recs
+            else:
+                for a, r in zip(acc, recs):
+                    a['ms'] += r['ms']
+        lib.eld_unet_profile(eng, 0)
+        for a in acc:
+            a['ms'] /= steps
+        return acc
+
+
 class FusedAdam(torch.optim.Optimizer):
     """torch.optim.Adam semantics (ELD_model.py:400-401) as ONE kernel over the flat buffers.
     Keeps `param_groups` so Engine.set_learning_rate / util.set_opt_param keep working."""

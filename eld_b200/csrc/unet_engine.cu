@@ -79,6 +79,11 @@ struct eld_unet {
         *dz5_2, *dz5_1, *dp4, *dz4_2, *dz4_1, *dp3, *dz3_2, *dz3_1, *dp2, *dz2_2, *dz2_1, *dp1, *dz1_2, *dz1_1;
     __nv_bfloat16* packed;
     PackTable table;
+    // optional per-launch profile (CUDA events on the launch stream)
+    bool profile = false;
+    struct Rec { char name[32]; double flops, bytes; cudaEvent_t e0, e1; };
+    std::vector<Rec> recs;
+    size_t rec_used = 0;
 };
 
 static size_t layout(eld_unet* u, char* base, bool train)
@@ -207,6 +212,24 @@ extern "C" void eld_unet_destroy(eld_unet* u) { delete u; }
 
 namespace {
 
+struct Scope {
+    eld_unet* u; cudaStream_t st; eld_unet::Rec* r = nullptr;
+    Scope(eld_unet* u_, cudaStream_t st_, const char* layer, const char* what, double flops, double bytes) : u(u_), st(st_)
+    {
+        if (!u->profile) return;
+        if (u->rec_used == u->recs.size()) {
+            eld_unet::Rec n{};
+            cudaEventCreate(&n.e0); cudaEventCreate(&n.e1);
+            u->recs.push_back(n);
+        }
+        r = &u->recs[u->rec_used++];
+        snprintf(r->name, sizeof(r->name), "%s.%s", layer, what);
+        r->flops = flops; r->bytes = bytes;
+        cudaEventRecord(r->e0, st);
+    }
+    ~Scope() { if (r) cudaEventRecord(r->e1, st); }
+};
+
 struct Runner {
     eld_unet* u;
     const float* params;
@@ -224,6 +247,8 @@ struct Runner {
         op.n_img = u->n; op.H = u->H >> lvl; op.W = u->W >> lvl;
         op.b = wf(li); op.n_total = l.cout; op.cout = l.cout;
         op.epi_mode = EPI_STORE; op.act = ACT_LRELU; op.out = y; op.out_pitch = yp; op.out_c0 = yc0; op.bias = bias(li);
+        const double px = (double)u->n * op.H * op.W;
+        Scope sc(u, st, l.name, "fprop", 2.0 * px * l.cout * 9 * l.cin, px * 2 * (l.cin + l.cout) + 18.0 * l.cin * l.cout);
         return launch_conv_gemm(ctx(), op, st);
     }
     int deconv(int li, const void* x, int xp, void* y, int yp, int lvl_in) const
@@ -234,6 +259,8 @@ struct Runner {
         op.n_img = u->n; op.H = u->H >> lvl_in; op.W = u->W >> lvl_in;
         op.b = wf(li); op.n_total = 4 * l.cout; op.cout = l.cout;
         op.epi_mode = EPI_SHUFFLE; op.act = ACT_NONE; op.out = y; op.out_pitch = yp; op.out_c0 = 0; op.bias = bias(li);
+        const double px = (double)u->n * op.H * op.W;
+        Scope sc(u, st, l.name, "fprop", 2.0 * px * 4 * l.cout * l.cin, px * 2 * (l.cin + 4 * l.cout) + 8.0 * l.cin * l.cout);
         return launch_conv_gemm(ctx(), op, st);
     }
     // data gradient of a conv: dz [cout] -> d(input) [cin channels at dxc0], optional lrelu' mask from `act_src`
@@ -247,6 +274,8 @@ struct Runner {
         op.epi_mode = EPI_STORE; op.act = act_src ? ACT_MASK : ACT_NONE;
         op.out = dx; op.out_pitch = dxp; op.out_c0 = dxc0; op.bias = nullptr;
         op.aux = act_src; op.aux_pitch = asp; op.aux_c0 = asc0;
+        const double px = (double)u->n * op.H * op.W;
+        Scope sc(u, st, l.name, "dgrad", 2.0 * px * l.cout * 9 * l.cin, px * 2 * (l.cin * (act_src ? 2 : 1) + l.cout) + 18.0 * l.cin * l.cout);
         return launch_conv_gemm(ctx(), op, st);
     }
     int deconv_dgrad(int li, const void* dy, int dyp, void* dx, const void* act_src, int lvl_in) const
@@ -258,6 +287,8 @@ struct Runner {
         op.b = wd(li); op.n_total = l.cin; op.cout = l.cin;
         op.epi_mode = EPI_STORE; op.act = ACT_MASK; op.out = dx; op.out_pitch = l.cin; op.out_c0 = 0;
         op.aux = act_src; op.aux_pitch = l.cin; op.aux_c0 = 0;
+        const double px = (double)u->n * op.H * op.W;
+        Scope sc(u, st, l.name, "dgrad", 2.0 * px * 4 * l.cout * l.cin, px * 2 * (2 * l.cin + 4 * l.cout) + 8.0 * l.cin * l.cout);
         return launch_conv_gemm(ctx(), op, st);
     }
     int conv_wgrad(int li, const void* x, int xp, int xc0, const void* dz, float* grads, int lvl) const
@@ -267,7 +298,12 @@ struct Runner {
         op.mode = WG_CONV; op.p = x; op.p_pitch = xp; op.p_c0 = xc0; op.p_ch = l.cin;
         op.q = dz; op.q_pitch = l.cout; op.q_c0 = 0; op.q_ch = l.cout;
         op.n_img = u->n; op.H = u->H >> lvl; op.W = u->W >> lvl; op.dw = grads + l.w_off;
-        TRY(launch_wgrad(ctx(), op, st));
+        const double px = (double)u->n * op.H * op.W;
+        {
+            Scope sc(u, st, l.name, "wgrad", 2.0 * px * l.cout * 9 * l.cin, px * 2 * (l.cin + l.cout) + 36.0 * l.cin * l.cout);
+            TRY(launch_wgrad(ctx(), op, st));
+        }
+        Scope sc(u, st, l.name, "bgrad", 0.0, px * 2 * l.cout);
         return launch_colsum(ctx(), dz, l.cout, 0, l.cout, (size_t)u->n * op.H * op.W, grads + l.b_off, st);
     }
     int deconv_wgrad(int li, const void* x, const void* dy, int dyp, float* grads, int lvl_in) const
@@ -277,20 +313,30 @@ struct Runner {
         op.mode = WG_DECONV; op.p = dy; op.p_pitch = dyp; op.p_c0 = 0; op.p_ch = l.cout;
         op.q = x; op.q_pitch = l.cin; op.q_c0 = 0; op.q_ch = l.cin;
         op.n_img = u->n; op.H = u->H >> lvl_in; op.W = u->W >> lvl_in; op.dw = grads + l.w_off;
-        TRY(launch_wgrad(ctx(), op, st));
+        const double px = (double)u->n * op.H * op.W;
+        {
+            Scope sc(u, st, l.name, "wgrad", 2.0 * px * 4 * l.cout * l.cin, px * 2 * (l.cin + 4 * l.cout) + 16.0 * l.cin * l.cout);
+            TRY(launch_wgrad(ctx(), op, st));
+        }
+        Scope sc(u, st, l.name, "bgrad", 0.0, px * 8 * l.cout);
         return launch_colsum(ctx(), dy, dyp, 0, l.cout, (size_t)u->n * op.H * op.W * 4, grads + l.b_off, st);
     }
     int pool(const void* in, int pitch, int c0, void* out, int C, int lvl_out) const
     {
+        const double pxo = (double)u->n * (u->H >> lvl_out) * (u->W >> lvl_out);
+        Scope sc(u, st, "pool", "fwd", 0.0, pxo * C * 2 * 5);
         return launch_maxpool(ctx(), in, pitch, c0, out, C, u->n, u->H >> lvl_out, u->W >> lvl_out, st);
     }
     int pool_bwd(const void* A, const void* dskip, int pitch, int c0, const void* dP, void* dZ, int C, int lvl_out) const
     {
+        const double pxo = (double)u->n * (u->H >> lvl_out) * (u->W >> lvl_out);
+        Scope sc(u, st, "pool", "bwd", 0.0, pxo * C * 2 * 13);
         return launch_maxpool_bwd(ctx(), A, dskip, pitch, c0, dP, dZ, C, u->n, u->H >> lvl_out, u->W >> lvl_out, st);
     }
 
     int pack() const
     {
+        Scope sc(u, st, "weights", "pack", 0.0, (double)u->n_params * 8);
         dim3 grid(64, u->table.n);
         pack_all_kernel<<<grid, 256, 0, st>>>(params, u->packed, u->table);
         ELD_CHECK_CUDA(cudaGetLastError());
@@ -302,7 +348,11 @@ struct Runner {
     {
         eld_unet* U = u;
         TRY(pack());
-        TRY(launch_first_conv(ctx(), x, params + U->L[I_C11].w_off, bias(I_C11), U->a1_1, U->n, U->H, U->W, st));
+        {
+            const double px = (double)U->n * U->H * U->W;
+            Scope sc(u, st, "conv1_1", "fprop", 2.0 * px * 32 * 36, px * (16 + 64));
+            TRY(launch_first_conv(ctx(), x, params + U->L[I_C11].w_off, bias(I_C11), U->a1_1, U->n, U->H, U->W, st));
+        }
         TRY(conv(I_C12, U->a1_1, 32, 0, U->cat9, 64, 32, 0));  TRY(pool(U->cat9, 64, 32, U->p1, 32, 1));
         TRY(conv(I_C21, U->p1, 32, 0, U->a2_1, 64, 0, 1));
         TRY(conv(I_C22, U->a2_1, 64, 0, U->cat8, 128, 64, 1)); TRY(pool(U->cat8, 128, 64, U->p2, 64, 2));
@@ -374,6 +424,8 @@ struct Runner {
         TRY(pool_bwd(U->cat9, U->dcat9, 64, 32, U->dp1, U->dz1_2, 32, 1));
         TRY(conv_wgrad(I_C12, U->a1_1, 32, 0, U->dz1_2, g, 0));
         TRY(conv_dgrad(I_C12, U->dz1_2, U->dz1_1, 32, 0, U->a1_1, 32, 0, 0));
+        const double px = (double)U->n * U->H * U->W;
+        Scope sc(u, st, "conv1_1", "wgrad", 2.0 * px * 32 * 36, px * (16 + 64));
         TRY(launch_first_conv_wgrad(ctx(), x, U->dz1_1, g + U->L[I_C11].w_off, g + U->L[I_C11].b_off, U->n, U->H, U->W, st));
         return ELD_OK;
     }
@@ -387,6 +439,8 @@ extern "C" int eld_unet_forward(eld_unet* u, const float* params, const float* x
     ELD_CHECK_CUDA(cudaSetDevice(u->ctx->device));
     Runner r{ u, params, static_cast<cudaStream_t>(stream) };
     TRY(r.forward(x));
+    const double hpx = (double)u->n * u->H * u->W;
+    Scope sc(u, r.st, "conv10_1", "fprop", 2.0 * hpx * 128, hpx * (64 + 16));
     return launch_head(u->ctx, u->a9_2, params + u->L[I_C10].w_off, params + u->L[I_C10].b_off, out, nullptr, nullptr,
                        nullptr, nullptr, nullptr, u->n, (size_t)u->H * u->W, r.st);
 }
@@ -401,8 +455,12 @@ extern "C" int eld_unet_train_step(eld_unet* u, const float* params, const float
     ELD_CHECK_CUDA(cudaMemsetAsync(grads, 0, u->n_params * sizeof(float), r.st));
     ELD_CHECK_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), r.st));
     TRY(r.forward(x));
-    TRY(launch_head(u->ctx, u->a9_2, params + u->L[I_C10].w_off, params + u->L[I_C10].b_off, out, target, u->dz9_2,
-                    grads + u->L[I_C10].w_off, grads + u->L[I_C10].b_off, loss, u->n, (size_t)u->H * u->W, r.st));
+    {
+        const double hpx = (double)u->n * u->H * u->W;
+        Scope sc(u, r.st, "conv10_1", "fwd+loss+bwd", 6.0 * hpx * 128, hpx * (64 + 16 + 16 + 64));
+        TRY(launch_head(u->ctx, u->a9_2, params + u->L[I_C10].w_off, params + u->L[I_C10].b_off, out, target, u->dz9_2,
+                        grads + u->L[I_C10].w_off, grads + u->L[I_C10].b_off, loss, u->n, (size_t)u->H * u->W, r.st));
+    }
     return r.backward(x, grads);
 }
 
@@ -415,4 +473,31 @@ extern "C" int eld_adam_step(eld_ctx* ctx, float* params, const float* grads, fl
     ELD_CHECK_CUDA(cudaSetDevice(ctx->device));
     return launch_adam(ctx, params, grads, m, v, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale,
                        static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int eld_unet_profile(eld_unet* u, int enable)
+{
+    ELD_REQUIRE(u, "eld_unet_profile: NULL");
+    u->profile = enable != 0;
+    u->rec_used = 0;
+    return ELD_OK;
+}
+
+/* Synchronises the device; fills up to `max` records of the launches since eld_unet_profile(u, 1). */
+extern "C" int eld_unet_profile_read(eld_unet* u, int max, char* names32, float* ms, double* flops, double* bytes, int* count)
+{
+    ELD_REQUIRE(u && count, "eld_unet_profile_read: NULL");
+    ELD_CHECK_CUDA(cudaDeviceSynchronize());
+    int n = (int)u->rec_used < max ? (int)u->rec_used : max;
+    for (int i = 0; i < n; ++i) {
+        float t = 0.f;
+        ELD_CHECK_CUDA(cudaEventElapsedTime(&t, u->recs[i].e0, u->recs[i].e1));
+        if (names32) memcpy(names32 + 32 * i, u->recs[i].name, 32);
+        if (ms) ms[i] = t;
+        if (flops) flops[i] = u->recs[i].flops;
+        if (bytes) bytes[i] = u->recs[i].bytes;
+    }
+    *count = n;
+    u->rec_used = 0;
+    return ELD_OK;
 }

@@ -70,6 +70,11 @@ int    eld_unet_train_step(eld_unet* u, const float* params, const float* x, con
                            float* out, float* grads, float* loss, void* stream);
 /* torch.optim.Adam step (ELD_model.py:400-401,475) on the flat buffers; grads are multiplied by
  * grad_scale first (1/world_size after a SUM all-reduce).  step counts from 1. */
+/* Per-launch timing (CUDA events on the launch stream) of the steps issued after eld_unet_profile(u, 1);
+ * eld_unet_profile_read synchronises, returns name[32] / ms / algorithmic FLOPs / algorithmic bytes per
+ * launch and clears the log.  Used by bench.py for the live roofline numbers. */
+int    eld_unet_profile(eld_unet* u, int enable);
+int    eld_unet_profile_read(eld_unet* u, int max, char* names32, float* ms, double* flops, double* bytes, int* count);
 int    eld_adam_step(eld_ctx* ctx, float* params, const float* grads, float* m, float* v, size_t n,
                      float lr, float beta1, float beta2, float eps, float weight_decay, int step,
                      float grad_scale, void* stream);
