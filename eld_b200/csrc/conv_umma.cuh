@@ -79,30 +79,38 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            uint32_t it = 0;
+            int s = 0;
+            uint32_t ph = 0;
+            uint8_t* sa = smem;
+            const int tiles_xy = p.tiles_x * p.tiles_y;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int m_tile = tile / n_tiles, n_t = tile - m_tile * n_tiles;
-                const int tx = m_tile % p.tiles_x;
-                const int ty = (m_tile / p.tiles_x) % p.tiles_y;
-                const int img = m_tile / (p.tiles_x * p.tiles_y);
+                const int img = m_tile / tiles_xy;
+                const int rem = m_tile - img * tiles_xy;
+                const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
                 const int x0 = tx * 16, y0 = ty * 8;
+                const int n0 = n_t * p.n_tile;
+                const int gy = img * p.H + y0;
+                int kb = 0;                                   // K coordinate in the weight matrix
                 for (int tap = 0; tap < p.taps; ++tap) {
-                    for (int kcI = 0; kcI < kchunks; ++kcI, ++it) {
-                        const int s = it % p.stages;
-                        const uint32_t ph = (it / p.stages) & 1u;
+                    int c1, c2, c3, c4;
+                    if (p.a_mode == A_CONV) {
+                        const int t3 = tap / 3;
+                        c1 = x0 + ((p.taps == 9) ? (tap - 3 * t3) - 1 : 0);
+                        c2 = y0 + ((p.taps == 9) ? t3 - 1 : 0);
+                        c3 = img; c4 = 0;
+                    } else {
+                        c1 = tap & 1; c2 = x0; c3 = tap >> 1; c4 = gy;
+                    }
+                    int c = p.a_c0;
+                    for (int kcI = 0; kcI < kchunks; ++kcI) {
                         ptx::mbar_wait(&empty[s], ph ^ 1u);
                         ptx::mbar_arrive_expect_tx(&full[s], (uint32_t)stage_bytes);
-                        uint8_t* sa = smem + (size_t)s * stage_bytes;
-                        uint8_t* sb = sa + a_bytes;
-                        const int c = p.a_c0 + kcI * p.kc;
-                        if (p.a_mode == A_CONV) {
-                            const int dx = (p.taps == 9) ? (tap % 3) - 1 : 0;
-                            const int dy = (p.taps == 9) ? (tap / 3) - 1 : 0;
-                            ptx::tma_load_5d(sa, &tmA, &full[s], c, x0 + dx, y0 + dy, img, 0);
-                        } else {
-                            ptx::tma_load_5d(sa, &tmA, &full[s], c, tap & 1, x0, tap >> 1, img * p.H + y0);
-                        }
-                        ptx::tma_load_2d(sb, &tmB, &full[s], tap * p.cin + kcI * p.kc, n_t * p.n_tile);
+                        ptx::tma_load_5d(sa, &tmA, &full[s], c, c1, c2, c3, c4);
+                        ptx::tma_load_2d(sa + a_bytes, &tmB, &full[s], kb, n0);
+                        c += p.kc; kb += p.kc;
+                        sa += stage_bytes;
+                        if (++s == p.stages) { s = 0; ph ^= 1u; sa = smem; }
                     }
                 }
             }
@@ -112,30 +120,34 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const uint32_t idesc = ptx::make_idesc_bf16(128, (uint32_t)p.n_tile, 0, 0);
         const uint32_t layout = (p.kc == 64) ? ptx::LAYOUT_SW128 : ptx::LAYOUT_SW64;
         const uint32_t sbo = (p.kc == 64) ? 1024u : 512u;
-        uint32_t it = 0, tile_it = 0;
+        const uint64_t desc_hi = ptx::make_smem_desc(0, 16, sbo, layout);   // everything but the address
+        const uint32_t smem_base = ptx::smem_u32(smem);
+        const int ksub = p.kc / 16;
+        int s = 0;
+        uint32_t ph = 0, tile_it = 0;
+        uint32_t a_addr = smem_base;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_it) {
             const uint32_t acc = tile_it & 1u;
             const uint32_t acc_ph = (tile_it >> 1) & 1u;
             ptx::mbar_wait(&tmem_empty[acc], acc_ph ^ 1u);
             ptx::tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.n_tile;
-            for (int ks = 0; ks < ksteps; ++ks, ++it) {
-                const int s = it % p.stages;
-                const uint32_t ph = (it / p.stages) & 1u;
+            for (int ks = 0; ks < ksteps; ++ks) {
                 ptx::mbar_wait(&full[s], ph);
                 ptx::tc_fence_after();
                 if (lane == 0) {
-                    const uint32_t a_addr = ptx::smem_u32(smem + (size_t)s * stage_bytes);
-                    const uint32_t b_addr = a_addr + (uint32_t)a_bytes;
-                    for (int k = 0; k < p.kc / 16; ++k) {
-                        const uint64_t ad = ptx::make_smem_desc(a_addr + k * 32, 16, sbo, layout);
-                        const uint64_t bd = ptx::make_smem_desc(b_addr + k * 32, 16, sbo, layout);
+                    uint64_t ad = desc_hi | (uint64_t)((a_addr & 0x3FFFFu) >> 4);
+                    uint64_t bd = desc_hi | (uint64_t)(((a_addr + (uint32_t)a_bytes) & 0x3FFFFu) >> 4);
+                    for (int k = 0; k < ksub; ++k) {
                         ptx::umma_bf16(d_tmem, ad, bd, idesc, (ks | k) != 0 ? 1u : 0u);
+                        ad += 2; bd += 2;                       // +32 bytes along K inside the swizzle atom
                     }
                     ptx::umma_commit(&empty[s]);
                     if (ks == ksteps - 1) ptx::umma_commit(&tmem_full[acc]);
                 }
                 __syncwarp();
+                a_addr += (uint32_t)stage_bytes;
+                if (++s == p.stages) { s = 0; ph ^= 1u; a_addr = smem_base; }
             }
         }
     } else {
@@ -146,9 +158,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         uint32_t tile_it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_it) {
             const int m_tile = tile / n_tiles, n_t = tile - m_tile * n_tiles;
-            const int tx = m_tile % p.tiles_x;
-            const int ty = (m_tile / p.tiles_x) % p.tiles_y;
             const int img = m_tile / (p.tiles_x * p.tiles_y);
+            const int rem = m_tile - img * (p.tiles_x * p.tiles_y);
+            const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
             const int x = tx * 16 + px, y = ty * 8 + py;
             const uint32_t acc = tile_it & 1u;
             const uint32_t acc_ph = (tile_it >> 1) & 1u;

@@ -86,55 +86,73 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (lane == 0 && nchunks > 0) {
+            // per-box constants (tap shift, channel) do not depend on the chunk: hoist them
+            int bc[4], bdx[4], bdy[4];
+            for (int b = 0; b < p.boxes_per_mtile; ++b) {
+                const int gb = mt * p.boxes_per_mtile + b;
+                int tap = gb / boxes_per_tap;
+                bc[b] = p.p_c0 + (gb - tap * boxes_per_tap) * p.box_ch;
+                if (tap >= p.taps) tap = p.taps - 1;            // dummy rows: load something valid, result ignored
+                if (p.mode == WG_CONV) { bdx[b] = (tap % 3) - 1; bdy[b] = (tap / 3) - 1; }
+                else { bdx[b] = tap & 1; bdy[b] = tap >> 1; }
+            }
+            const int qc0 = p.q_c0 + nt * p.n_tile;
+            const int cxy = p.chunks_x * p.chunks_y;
+            int img = ch_begin / cxy;
+            int rem = ch_begin - img * cxy;
+            int cy = rem / p.chunks_x, cx = rem - cy * p.chunks_x;
+            int s = 0;
+            uint32_t ph = 0;
+            uint8_t* sa = smem;
             for (int i = 0; i < nchunks; ++i) {
-                const int chunk = ch_begin + i;
-                const int cx = chunk % p.chunks_x;
-                const int cy = (chunk / p.chunks_x) % p.chunks_y;
-                const int img = chunk / (p.chunks_x * p.chunks_y);
                 const int x0 = cx * 16, y0 = cy * 4;
-                const int s = i % p.stages;
-                const uint32_t ph = (i / p.stages) & 1u;
                 ptx::mbar_wait(&empty[s], ph ^ 1u);
                 ptx::mbar_arrive_expect_tx(&full[s], (uint32_t)stage_bytes);
-                uint8_t* sa = smem + (size_t)s * stage_bytes;
-                for (int b = 0; b < p.boxes_per_mtile; ++b) {
-                    const int gb = mt * p.boxes_per_mtile + b;
-                    int tap = gb / boxes_per_tap;
-                    const int c = p.p_c0 + (gb - tap * boxes_per_tap) * p.box_ch;
-                    if (tap >= p.taps) tap = p.taps - 1;          // dummy rows: load something valid, result ignored
-                    if (p.mode == WG_CONV)
-                        ptx::tma_load_5d(sa + b * p_box, &tmP, &full[s], c, x0 + (tap % 3) - 1, y0 + (tap / 3) - 1, img, 0);
-                    else
-                        ptx::tma_load_5d(sa + b * p_box, &tmP, &full[s], c, tap & 1, x0, tap >> 1, img * p.H + y0);
+                if (p.mode == WG_CONV) {
+                    for (int b = 0; b < p.boxes_per_mtile; ++b)
+                        ptx::tma_load_5d(sa + b * p_box, &tmP, &full[s], bc[b], x0 + bdx[b], y0 + bdy[b], img, 0);
+                } else {
+                    for (int b = 0; b < p.boxes_per_mtile; ++b)
+                        ptx::tma_load_5d(sa + b * p_box, &tmP, &full[s], bc[b], bdx[b], x0, bdy[b], img * p.H + y0);
                 }
                 uint8_t* sq = sa + a_bytes;
                 for (int b = 0; b < q_boxes; ++b)
-                    ptx::tma_load_5d(sq + b * q_box, &tmQ, &full[s], p.q_c0 + nt * p.n_tile + b * p.q_box_ch, x0, y0, img, 0);
+                    ptx::tma_load_5d(sq + b * q_box, &tmQ, &full[s], qc0 + b * p.q_box_ch, x0, y0, img, 0);
+                sa += stage_bytes;
+                if (++s == p.stages) { s = 0; ph ^= 1u; sa = smem; }
+                if (++cx == p.chunks_x) { cx = 0; if (++cy == p.chunks_y) { cy = 0; ++img; } }
             }
         }
     } else if (warp == 1) {
         const uint32_t idesc = ptx::make_idesc_bf16(128, (uint32_t)p.n_tile, 1, 1);   // both MN-major
         const uint32_t a_layout = p.box_ch == 64 ? ptx::LAYOUT_SW128 : ptx::LAYOUT_SW64;
         const uint32_t b_layout = p.q_box_ch == 64 ? ptx::LAYOUT_SW128 : ptx::LAYOUT_SW64;
+        // MN-major: LBO = distance between channel blocks (one TMA box), SBO = 8 pixel rows
+        const uint64_t a_hi = ptx::make_smem_desc(0, (uint32_t)p_box, 8u * p_row, a_layout);
+        const uint64_t b_hi = ptx::make_smem_desc(0, (uint32_t)q_box, 8u * q_row, b_layout);
+        const uint32_t a_step = (16u * p_row) >> 4, b_step = (16u * q_row) >> 4;       // 16 pixel rows per MMA
+        const uint32_t smem_base = ptx::smem_u32(smem);
+        uint32_t a_addr = smem_base;
+        int s = 0;
+        uint32_t ph = 0;
         for (int i = 0; i < nchunks; ++i) {
-            const int s = i % p.stages;
-            const uint32_t ph = (i / p.stages) & 1u;
             ptx::mbar_wait(&full[s], ph);
             ptx::tc_fence_after();
             if (lane == 0) {
-                const uint32_t a_addr = ptx::smem_u32(smem + (size_t)s * stage_bytes);
-                const uint32_t b_addr = a_addr + (uint32_t)a_bytes;
+                uint64_t ad = a_hi | (uint64_t)((a_addr & 0x3FFFFu) >> 4);
+                uint64_t bd = b_hi | (uint64_t)(((a_addr + (uint32_t)a_bytes) & 0x3FFFFu) >> 4);
+#pragma unroll
                 for (int k = 0; k < kWgradKP / 16; ++k) {
-                    // MN-major: LBO = distance between channel blocks (one TMA box), SBO = 8 pixel rows
-                    const uint64_t ad = ptx::make_smem_desc(a_addr + k * 16 * p_row, (uint32_t)p_box, 8u * p_row, a_layout);
-                    const uint64_t bd = ptx::make_smem_desc(b_addr + k * 16 * q_row, (uint32_t)q_box, 8u * q_row, b_layout);
                     ptx::umma_bf16(tmem_base, ad, bd, idesc, (i | k) != 0 ? 1u : 0u);
+                    ad += a_step; bd += b_step;
                 }
                 ptx::umma_commit(&empty[s]);
                 if (i == nchunks - 1) ptx::umma_commit(acc_full);
             }
             __syncwarp();
+            a_addr += (uint32_t)stage_bytes;
+            if (++s == p.stages) { s = 0; ph ^= 1u; a_addr = smem_base; }
         }
     } else if (nchunks > 0) {
         const int q = warp & 3;
