@@ -1,0 +1,237 @@
+"""Drop-in for the reference's model factory seam: `models.__dict__[opt.model]()`
+-> object with initialize / set_input / optimize_parameters / get_current_errors / save / load ...
+Reference: models/ELD_model.py:172-200 (set_input), :352-523 (ELDModel), models/base_model.py.
+
+Differences that are the point of this repo
+  * netG is eld_b200.arch.unet (tcgen05 engine); forward+L1+backward is ONE C-ABI call, Adam another;
+  * noise can be synthesised ON THE TRAINING STREAM (opt.noise_on_gpu / a batch without 'input'):
+    only the clean frame crosses PCIe, the fused CUDA kernel makes the noisy input;
+  * data parallel: if torch.distributed is initialised the flat gradient buffer is all-reduced
+    (NCCL over NVLink) between backward and Adam - one collective, U-Net weights only;
+  * get_current_errors() keeps the reference's `.item()` host sync but can be told to defer it.
+"""
+import os
+from collections import OrderedDict
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import arch
+
+
+def default_opt(**kw):
+    """The flags the hot path reads (reference options/eld/{base,train}_options.py), with defaults."""
+    o = dict(name='eld_b200', gpu_ids=[0], model='eld_model', checkpoints_dir='./checkpoints', resume=False,
+             resume_epoch=None, seed=2018, chop=False, no_log=True, no_verbose=True, netG='unet', channels=4,
+             stage_in='raw', stage_out='raw', model_path=None, include=4, crf=False, batchSize=1, lr=1e-4,
+             beta1=0.9, wd=0.0, loss='l1', noise='g', isTrain=True, save_epoch_freq=100, noise_on_gpu=False,
+             defer_loss_sync=False)
+    o.update(kw)
+    return SimpleNamespace(**o)
+
+
+class BaseModel:
+    """models/base_model.py:6-74"""
+
+    def name(self):
+        return self.__class__.__name__.lower()
+
+    def initialize(self, opt):
+        self.opt = opt
+        self.gpu_ids = opt.gpu_ids
+        self.isTrain = opt.isTrain
+        self.save_dir = os.path.join(opt.checkpoints_dir, opt.name)
+        self._count = 0
+
+    def update_learning_rate(self):
+        for scheduler in self.schedulers:
+            scheduler.step()
+        lr = self.optimizers[0].param_groups[0]['lr']
+        print('learning rate = %.7f' % lr)
+
+    def print_optimizer_param(self):
+        print(self.optimizers[-1])
+
+    def save(self, label=None):
+        epoch, iterations = self.epoch, self.iterations
+        if label is None:
+            model_name = os.path.join(self.save_dir, 'model' + '_%03d_%08d.pt' % (epoch, iterations))
+        else:
+            model_name = os.path.join(self.save_dir, 'model' + '_' + label + '.pt')
+        os.makedirs(self.save_dir, exist_ok=True)
+        torch.save(self.state_dict(), model_name)
+
+    def _init_optimizer(self, optimizers):
+        self.optimizers = optimizers
+        self.schedulers = []
+        for optimizer in self.optimizers:
+            for group in optimizer.param_groups:             # util.set_opt_param
+                group['initial_lr'] = self.opt.lr
+                group['weight_decay'] = self.opt.wd
+
+
+class ELDModel(BaseModel):
+    def __init__(self):
+        self.epoch = 0
+        self.iterations = 0
+        self.device = torch.device('cuda', torch.cuda.current_device()) if torch.cuda.is_available() else None
+        self.noise_maker = None
+        self.loss_pixel = None
+        self._frame_counter = 0
+
+    def _eval(self):
+        self.netG.eval()
+
+    def _train(self):
+        self.netG.train()
+
+    def initialize(self, opt, noise_maker=None):
+        BaseModel.initialize(self, opt)
+        if self.device is None:
+            raise RuntimeError('ELDModel (eld_b200) needs a CUDA device: no CPU fallback')
+        if opt.stage_in != 'raw' or opt.stage_out != 'raw':
+            raise NotImplementedError('only the raw->raw path is in scope (SURVEY 8f.4 lists the sRGB branch as next)')
+        if len(opt.gpu_ids) > 0:
+            self.device = torch.device('cuda', opt.gpu_ids[0])
+        self.netG = arch.__dict__[opt.netG](opt.channels, opt.channels).to(self.device)     # ELD_model.py:391
+        self.noise_maker = noise_maker
+        if self.isTrain:
+            if opt.loss != 'l1':
+                raise NotImplementedError("the fused head implements the default L1 pixel loss (losses.py:31-32)")
+            self.optimizer_G = arch.FusedAdam(self.netG, lr=opt.lr, betas=(opt.beta1, 0.999), weight_decay=opt.wd)
+            self._init_optimizer([self.optimizer_G])
+        if opt.resume:
+            self.load(self, opt.resume_epoch)
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.rank = dist.get_rank() if self.world > 1 else 0
+
+    # ---- ELDModelBase.set_input (ELD_model.py:173-200) -------------------------------------------------
+    def set_input(self, data, mode='train'):
+        mode = mode.lower()
+        target, data_name = None, None
+        if mode == 'train':
+            input, target = data.get('input'), data['target']
+        elif mode == 'eval':
+            input, target, data_name = data['input'], data['target'], data['fn']
+        elif mode == 'test':
+            input, data_name = data['input'], data['fn']
+        else:
+            raise NotImplementedError('Mode [%s] is not implemented' % mode)
+        if target is not None:
+            target = target.to(device=self.device, dtype=torch.float32, non_blocking=True)
+        synth = mode == 'train' and (input is None or getattr(self.opt, 'noise_on_gpu', False))
+        if synth:
+            # on-the-fly synthesis on the training stream (SynDataset semantics, sid_dataset.py:259-280,
+            # incl. the [0,1] clip): global frame ids keep the stream invariant to the number of GPUs.
+            assert self.noise_maker is not None, 'noise_on_gpu needs a noise_maker (eld_b200.noise.NoiseModel)'
+            n = target.shape[0]
+            fid0 = (self._frame_counter * self.world + self.rank) * n
+            self._frame_counter += 1
+            input = self.noise_maker.batch_gpu(target, frame_id0=fid0, clip=True)
+        else:
+            input = input.to(device=self.device, dtype=torch.float32, non_blocking=True)
+        self.input, self.target, self.data_name = input, target, data_name
+        self.rawpath = data['rawpath'][0] if 'rawpath' in data else None
+        self.cfa = data['cfa'][0] if 'cfa' in data else 'bayer'
+        self.aligned = False if 'unaligned' in data else True
+
+    # ---- forward / optimise (ELD_model.py:411-475) -------------------------------------------------------
+    def forward(self):
+        if self.opt.chop:
+            output = self.forward_chop(self.input)
+        else:
+            output = self.netG(self.input)
+        self.output = output
+        return output
+
+    def forward_chop(self, x, base=16):
+        """ELD_model.py:434-467: 4 overlapping quadrants; each quadrant is padded up to the tile grid the
+        engine needs (H%128, W%256) by replication and cropped back."""
+        b, c, h, w = x.size()
+        h_half, w_half = h // 2, w // 2
+        shave_h = np.ceil(h_half / base) * base - h_half
+        shave_w = np.ceil(w_half / base) * base - w_half
+        shave_h = shave_h if shave_h >= 10 else shave_h + base
+        shave_w = shave_w if shave_w >= 10 else shave_w + base
+        h_size, w_size = int(h_half + shave_h), int(w_half + shave_w)
+        inputs = [x[:, :, 0:h_size, 0:w_size], x[:, :, 0:h_size, (w - w_size):w],
+                  x[:, :, (h - h_size):h, 0:w_size], x[:, :, (h - h_size):h, (w - w_size):w]]
+        outputs = [self._padded_forward(i) for i in inputs]
+        output = x.new_empty(b, outputs[0].shape[1], h, w)
+        output[:, :, 0:h_half, 0:w_half] = outputs[0][:, :, 0:h_half, 0:w_half]
+        output[:, :, 0:h_half, w_half:w] = outputs[1][:, :, 0:h_half, (w_size - w + w_half):w_size]
+        output[:, :, h_half:h, 0:w_half] = outputs[2][:, :, (h_size - h + h_half):h_size, 0:w_half]
+        output[:, :, h_half:h, w_half:w] = outputs[3][:, :, (h_size - h + h_half):h_size, (w_size - w + w_half):w_size]
+        return output
+
+    def _padded_forward(self, x):
+        h, w = x.shape[2:]
+        H, W = -(-h // 128) * 128, -(-w // 256) * 256
+        if (H, W) != (h, w):
+            x = torch.nn.functional.pad(x, (0, W - w, 0, H - h), mode='replicate')
+        return self.netG(x.contiguous())[:, :, :h, :w]
+
+    def optimize_parameters(self):
+        """forward, zero_grad, L1 backward, (all-reduce), Adam - ELD_model.py:469-475."""
+        self._train()
+        self.output, self.loss_pixel = self.netG.train_step(self.input, self.target)
+        if self.world > 1:
+            dist.all_reduce(self.netG.flat_grads)
+        self.optimizer_G.step(grad_scale=1.0 / self.world)
+
+    def backward_G(self):
+        raise RuntimeError('backward is fused into optimize_parameters() (one C-ABI call)')
+
+    def get_current_errors(self):
+        ret_errors = OrderedDict()
+        if self.loss_pixel is not None:
+            ret_errors['Pixel'] = self.loss_pixel if getattr(self.opt, 'defer_loss_sync', False) else self.loss_pixel.item()
+        return ret_errors
+
+    def eval(self, data, savedir=None, **kwargs):
+        """Minimal GPU eval: forward + PSNR (util/index.py:79 restated); the rawpy/skimage based
+        visualisation of ELD_model.py:203-307 is out of scope."""
+        self._eval()
+        self.set_input(data, 'eval')
+        with torch.no_grad():
+            out = self._padded_forward(self.input) if not self.opt.chop else self.forward_chop(self.input)
+        a = (out.clamp(0, 1) * 255.0).double()
+        b = (self.target.clamp(0, 1) * 255.0).double()
+        mse = ((a - b) ** 2).mean().item()
+        return {'PSNR': 10.0 * np.log10(255.0 ** 2 / max(mse, 1e-30))}
+
+    def test(self, data, savedir=None, **kwargs):
+        self._eval()
+        self.set_input(data, 'test')
+        with torch.no_grad():
+            return self._padded_forward(self.input)
+
+    # ---- checkpoints (ELD_model.py:492-523) -----------------------------------------------------------------
+    @staticmethod
+    def load(model, resume_epoch=None):
+        model_path = model.opt.model_path
+        if model_path is None:
+            name = 'model_latest.pt' if resume_epoch is None else None
+            if name is None:
+                cands = [f for f in os.listdir(model.save_dir) if f.startswith('model_%03d_' % resume_epoch)]
+                name = cands[0]
+            model_path = os.path.join(model.save_dir, name)
+        state_dict = torch.load(model_path, map_location='cpu', weights_only=False)
+        model.epoch = state_dict['epoch']
+        model.iterations = state_dict['iterations']
+        model.netG.load_state_dict(state_dict['netG'])
+        if model.isTrain and 'opt_g' in state_dict:
+            model.optimizer_G.load_state_dict(state_dict['opt_g'])
+        print('Resume from epoch %d, iteration %d' % (model.epoch, model.iterations))
+        return state_dict
+
+    def state_dict(self):
+        return {'netG': {k: v.detach().cpu().clone() for k, v in self.netG.state_dict().items()},
+                'opt_g': self.optimizer_G.state_dict(), 'epoch': self.epoch, 'iterations': self.iterations}
+
+
+def eld_model():
+    """models/__init__.py:3-4"""
+    return ELDModel()

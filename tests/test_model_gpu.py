@@ -1,0 +1,92 @@
+"""GPU tests of the drop-in ELDModel / Engine seams (reference models/ELD_model.py, engine.py)."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def torch():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip('no GPU')
+    return torch
+
+
+def _batch(torch, n, seed, h=128, w=256):
+    g = torch.Generator().manual_seed(seed)
+    return {'target': torch.rand(n, 4, h, w, generator=g)}
+
+
+def test_engine_train_loop_matches_reference_step(torch, tmp_path):
+    """Engine.train over 3 batches with GPU noise == oracle loop fed the SAME noisy inputs:
+    losses within 1e-2 relative, parameters after 3 Adam steps within 2e-3 of the fp32 oracle's."""
+    from eld_b200 import models
+    from eld_b200.engine import Engine
+    from eld_b200.noise import NoiseModel
+    from oracle.unet_ref import UNetSeeInDarkRef, l1_train_step
+    torch.manual_seed(2018)
+    np.random.seed(2018)
+    opt = models.default_opt(name='t', checkpoints_dir=str(tmp_path), noise='p+g', noise_on_gpu=True, lr=1e-3)
+    nm = NoiseModel('p+g', include=4, verbose=False, seed=7)
+    eng = Engine(opt, noise_maker=nm)
+    torch.manual_seed(2018)
+    ref = UNetSeeInDarkRef(4, 4)
+    ropt = torch.optim.Adam(ref.parameters(), lr=1e-3, betas=(0.9, 0.999), weight_decay=0)
+    eng.set_learning_rate(1e-3)
+    assert eng.model.optimizers[0].param_groups[0]['lr'] == 1e-3
+    batches = [_batch(torch, 2, s) for s in range(3)]
+    for b in batches:
+        eng.model.set_input(b, 'train')
+        x = eng.model.input.cpu()
+        assert x.min() >= 0 and x.max() <= 1 and not torch.equal(x, b['target'])       # noisy, clipped
+        eng.model.optimize_parameters()
+        err = eng.model.get_current_errors()
+        _, loss_ref = l1_train_step(ref, ropt, x, b['target'])
+        assert abs(err['Pixel'] - loss_ref.item()) <= 1e-2 * loss_ref.item()
+    for (k, p), (_, q) in zip(ref.named_parameters(), eng.model.netG.named_parameters()):
+        d = (p.detach() - q.detach().cpu()).abs().max().item()
+        assert d <= 2e-3 + 0.2 * 3e-3, (k, d)        # 3 Adam steps of lr 1e-3 move a weight by <= 3e-3
+    avg = eng.train(batches)
+    assert eng.epoch == 1 and eng.iterations == 3 and avg['Pixel'] > 0
+
+
+def test_checkpoint_roundtrip_reference_format(torch, tmp_path):
+    from eld_b200 import models
+    from oracle.unet_ref import UNetSeeInDarkRef
+    opt = models.default_opt(name='ck', checkpoints_dir=str(tmp_path))
+    m = models.eld_model()
+    m.initialize(opt)
+    m.set_input({'input': torch.rand(1, 4, 128, 256), 'target': torch.rand(1, 4, 128, 256)}, 'train')
+    m.optimize_parameters()
+    m.epoch, m.iterations = 3, 17
+    m.save(label='latest')
+    sd = torch.load(os.path.join(str(tmp_path), 'ck', 'model_latest.pt'), weights_only=False)
+    assert set(sd) == {'netG', 'opt_g', 'epoch', 'iterations'}                 # ELD_model.py:516-523
+    UNetSeeInDarkRef(4, 4).load_state_dict(sd['netG'])                          # loads into the reference-shaped module
+    ref_adam = torch.optim.Adam(UNetSeeInDarkRef(4, 4).parameters())
+    ref_adam.load_state_dict(sd['opt_g'])                                       # torch.optim.Adam accepts 'opt_g'
+    m2 = models.eld_model()
+    opt2 = models.default_opt(name='ck', checkpoints_dir=str(tmp_path), resume=True)
+    m2.initialize(opt2)
+    assert m2.epoch == 3 and m2.iterations == 17
+    assert torch.equal(m2.netG.flat_params, m.netG.flat_params)
+    assert torch.equal(m2.optimizer_G.m, m.optimizer_G.m) and m2.optimizer_G.t == 1
+
+
+def test_eval_and_chop(torch, tmp_path):
+    from eld_b200 import models
+    opt = models.default_opt(name='ev', checkpoints_dir=str(tmp_path))
+    m = models.eld_model()
+    m.initialize(opt)
+    d = {'input': torch.rand(1, 4, 160, 272), 'target': torch.rand(1, 4, 160, 272), 'fn': ['x']}
+    r = m.eval(d)
+    assert np.isfinite(r['PSNR'])
+    m.set_input(d, 'eval')
+    full = m._padded_forward(m.input)
+    chop = m.forward_chop(m.input)
+    assert chop.shape == full.shape == (1, 4, 160, 272)
+    # the quadrant interiors agree with the full-frame forward away from the replicate-padded borders
+    assert (chop[:, :, 16:64, 16:120] - full[:, :, 16:64, 16:120]).abs().max().item() < 5e-2
