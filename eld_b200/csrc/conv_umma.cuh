@@ -7,6 +7,10 @@
 //           box at shifted coordinates - TMA zero-fills out-of-image pixels, which IS the padding.
 // K       = taps x cin, walked in chunks of kc = 32 or 64 channels (one 64 B / 128 B swizzled row per
 //           pixel), each chunk = kc/16 tcgen05.mma.kind::f16 instructions (M=128, N=n_tile, K=16).
+// halo    = for conv3x3 with a small weight operand the three vertical taps of one filter column share ONE
+//           TMA box {kc, 16, 10}: tap kh is the same smem tile read 16 pixel rows (a multiple of the swizzle
+//           period) further down - 2.4x fewer L2->SM requests; weights can stay RESIDENT in smem for the
+//           whole persistent CTA (b_res) so thin full-resolution layers stream activations only.
 // roles   = warp 0: TMA producer | warp 1: MMA issuer (one elected lane) | warps 2-5: epilogue
 //           (tcgen05.ld -> bias / LeakyReLU / mask -> bf16 -> global).  Two TMEM accumulators so the
 //           epilogue of tile i overlaps the MMAs of tile i+1.
@@ -35,6 +39,8 @@ struct ConvGemmParams {
     int cout;             // EPI_SHUFFLE: channels per sub-pixel
     int stages;
     int tmem_cols;
+    int halo;             // conv3x3: one {kc,16,10} box per filter column, kh taps = row-shifted views
+    int b_res;            // weights resident in smem (loaded once per CTA); requires n_total == n_tile
 };
 
 constexpr int kConvThreads = 192;
@@ -47,27 +53,33 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t raw = ptx::smem_u32(smem_raw);
     uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
 
-    const int a_bytes = 128 * p.kc * 2;
-    const int b_bytes = p.n_tile * p.kc * 2;
-    const int stage_bytes = a_bytes + b_bytes;
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+    const int row_bytes = p.kc * 2;
+    const int a_bytes = (p.halo ? 160 : 128) * row_bytes;
+    const int b_bytes = p.n_tile * row_bytes;                       // one tap, one channel chunk
+    const int kchunks = p.cin / p.kc;
+    const int b_per_stage = p.b_res ? 0 : (p.halo ? 3 : 1);
+    const int stage_bytes = a_bytes + b_per_stage * b_bytes;
+    const int bres_bytes = p.b_res ? p.taps * kchunks * b_bytes : 0;
+    uint8_t* stage0 = smem + bres_bytes;
+    uint64_t* full = reinterpret_cast<uint64_t*>(stage0 + (size_t)p.stages * stage_bytes);
     uint64_t* empty = full + p.stages;
     uint64_t* tmem_full = empty + p.stages;
     uint64_t* tmem_empty = tmem_full + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    uint64_t* bres_full = tmem_empty + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bres_full + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_tiles = p.n_total / p.n_tile;
     const int m_tiles = p.n_img * p.tiles_y * p.tiles_x;
     const int total_tiles = m_tiles * n_tiles;
-    const int kchunks = p.cin / p.kc;
-    const int ksteps = p.taps * kchunks;
+    const int ksteps = (p.halo ? 3 : p.taps) * kchunks;
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&tmA);
         ptx::prefetch_tmap(&tmB);
         for (int s = 0; s < p.stages; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
         for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tmem_full[a], 1); ptx::mbar_init(&tmem_empty[a], 4); }
+        ptx::mbar_init(bres_full, 1);
         ptx::fence_barrier_init();
     }
     if (warp == 2) ptx::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
@@ -79,9 +91,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
+            if (p.b_res) {
+                ptx::mbar_arrive_expect_tx(bres_full, (uint32_t)bres_bytes);
+                for (int j = 0; j < p.taps * kchunks; ++j)         // j = tap*kchunks + chunk  <=>  K offset j*kc
+                    ptx::tma_load_2d(smem + (size_t)j * b_bytes, &tmB, bres_full, j * p.kc, 0);
+            }
             int s = 0;
             uint32_t ph = 0;
-            uint8_t* sa = smem;
+            uint8_t* sa = stage0;
             const int tiles_xy = p.tiles_x * p.tiles_y;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int m_tile = tile / n_tiles, n_t = tile - m_tile * n_tiles;
@@ -90,6 +107,25 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
                 const int x0 = tx * 16, y0 = ty * 8;
                 const int n0 = n_t * p.n_tile;
+                if (p.halo) {
+                    for (int kw = 0; kw < 3; ++kw) {
+                        int c = p.a_c0;
+                        for (int kcI = 0; kcI < kchunks; ++kcI) {
+                            ptx::mbar_wait(&empty[s], ph ^ 1u);
+                            ptx::mbar_arrive_expect_tx(&full[s], (uint32_t)stage_bytes);
+                            ptx::tma_load_5d(sa, &tmA, &full[s], c, x0 + kw - 1, y0 - 1, img, 0);
+                            if (!p.b_res) {
+                                for (int kh = 0; kh < 3; ++kh)
+                                    ptx::tma_load_2d(sa + a_bytes + kh * b_bytes, &tmB, &full[s],
+                                                     (kh * 3 + kw) * p.cin + kcI * p.kc, n0);
+                            }
+                            c += p.kc;
+                            sa += stage_bytes;
+                            if (++s == p.stages) { s = 0; ph ^= 1u; sa = stage0; }
+                        }
+                    }
+                    continue;
+                }
                 const int gy = img * p.H + y0;
                 int kb = 0;                                   // K coordinate in the weight matrix
                 for (int tap = 0; tap < p.taps; ++tap) {
@@ -107,10 +143,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         ptx::mbar_wait(&empty[s], ph ^ 1u);
                         ptx::mbar_arrive_expect_tx(&full[s], (uint32_t)stage_bytes);
                         ptx::tma_load_5d(sa, &tmA, &full[s], c, c1, c2, c3, c4);
-                        ptx::tma_load_2d(sa + a_bytes, &tmB, &full[s], kb, n0);
+                        if (!p.b_res) ptx::tma_load_2d(sa + a_bytes, &tmB, &full[s], kb, n0);
                         c += p.kc; kb += p.kc;
                         sa += stage_bytes;
-                        if (++s == p.stages) { s = 0; ph ^= 1u; sa = smem; }
+                        if (++s == p.stages) { s = 0; ph ^= 1u; sa = stage0; }
                     }
                 }
             }
@@ -121,11 +157,16 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const uint32_t layout = (p.kc == 64) ? ptx::LAYOUT_SW128 : ptx::LAYOUT_SW64;
         const uint32_t sbo = (p.kc == 64) ? 1024u : 512u;
         const uint64_t desc_hi = ptx::make_smem_desc(0, 16, sbo, layout);   // everything but the address
-        const uint32_t smem_base = ptx::smem_u32(smem);
+        const uint32_t stage_base = ptx::smem_u32(stage0);
+        const uint32_t bres_base = ptx::smem_u32(smem);
         const int ksub = p.kc / 16;
+        const int nsub = p.halo ? 3 : 1;                                    // taps served by one stage
+        const uint32_t a_tap_step = (uint32_t)(16 * row_bytes) >> 4;        // one image row of the patch, in 16 B units
+        const uint32_t b_step = (uint32_t)b_bytes >> 4;
         int s = 0;
         uint32_t ph = 0, tile_it = 0;
-        uint32_t a_addr = smem_base;
+        uint32_t a_addr = stage_base;
+        if (p.b_res) { ptx::mbar_wait(bres_full, 0); ptx::tc_fence_after(); }
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_it) {
             const uint32_t acc = tile_it & 1u;
             const uint32_t acc_ph = (tile_it >> 1) & 1u;
@@ -136,18 +177,33 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 ptx::mbar_wait(&full[s], ph);
                 ptx::tc_fence_after();
                 if (lane == 0) {
-                    uint64_t ad = desc_hi | (uint64_t)((a_addr & 0x3FFFFu) >> 4);
-                    uint64_t bd = desc_hi | (uint64_t)(((a_addr + (uint32_t)a_bytes) & 0x3FFFFu) >> 4);
-                    for (int k = 0; k < ksub; ++k) {
-                        ptx::umma_bf16(d_tmem, ad, bd, idesc, (ks | k) != 0 ? 1u : 0u);
-                        ad += 2; bd += 2;                       // +32 bytes along K inside the swizzle atom
+                    uint64_t ad0 = desc_hi | (uint64_t)((a_addr & 0x3FFFFu) >> 4);
+                    uint64_t bd0;
+                    uint32_t b_sub_step;                       // descriptor units between the B tiles of taps kh, kh+1
+                    if (p.b_res) {
+                        // halo: ks = kw*kchunks + chunk, tap = kh*3 + kw -> tile index (kh*3+kw)*kchunks + chunk
+                        int j;
+                        if (p.halo) { const int kw = ks / kchunks; j = kw * kchunks + (ks - kw * kchunks); b_sub_step = 3u * kchunks * b_step; }
+                        else { j = ks; b_sub_step = 0; }
+                        bd0 = desc_hi | (uint64_t)(((bres_base + (uint32_t)j * (uint32_t)b_bytes) & 0x3FFFFu) >> 4);
+                    } else {
+                        bd0 = desc_hi | (uint64_t)(((a_addr + (uint32_t)a_bytes) & 0x3FFFFu) >> 4);
+                        b_sub_step = b_step;
+                    }
+                    for (int sub = 0; sub < nsub; ++sub) {
+                        uint64_t ad = ad0, bd = bd0;
+                        for (int k = 0; k < ksub; ++k) {
+                            ptx::umma_bf16(d_tmem, ad, bd, idesc, (ks | sub | k) != 0 ? 1u : 0u);
+                            ad += 2; bd += 2;                   // +32 bytes along K inside the swizzle atom
+                        }
+                        ad0 += a_tap_step; bd0 += b_sub_step;
                     }
                     ptx::umma_commit(&empty[s]);
                     if (ks == ksteps - 1) ptx::umma_commit(&tmem_full[acc]);
                 }
                 __syncwarp();
                 a_addr += (uint32_t)stage_bytes;
-                if (++s == p.stages) { s = 0; ph ^= 1u; a_addr = smem_base; }
+                if (++s == p.stages) { s = 0; ph ^= 1u; a_addr = stage_base; }
             }
         }
     } else {

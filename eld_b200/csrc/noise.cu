@@ -130,8 +130,9 @@ __device__ __forceinline__ void row_normals(const Stream& s, uint32_t i, float& 
 }
 
 // ---- packed in, aligned: w % 4 == 0 and 16-byte aligned planes ---------------------------------
+// Gaussian-only masks are issue/latency bound on MUFU chains: cap registers at 32 so 8 blocks (64 warps) fit.
 template <uint32_t MASK>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, (MASK != kRuntimeMask && !(MASK & (ELD_NOISE_P | ELD_NOISE_G))) ? 8 : 1)
 noise_packed_vec_kernel(const float* __restrict__ clean, float* __restrict__ noisy,
                         const __grid_constant__ NoiseLaunch L)
 {

@@ -50,19 +50,37 @@ __device__ __forceinline__ float u24(uint32_t x) { return __fmul_rn(__uint2float
 __device__ __forceinline__ float fast_sqrt(float x)
 {
     float r;
-    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
 __device__ __forceinline__ float fast_ex2(float x)
 {
     float r;
-    asm("ex2.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
 __device__ __forceinline__ float fast_rcp(float x)
 {
     float r;
-    asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float fast_lg2(float x)
+{
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float fast_sin(float x)
+{
+    float r;
+    asm("sin.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float fast_cos(float x)
+{
+    float r;
+    asm("cos.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
 
@@ -71,9 +89,9 @@ __device__ __forceinline__ void box_muller(uint32_t xa, uint32_t xb, float& n_co
 {
     const float u = u01(xa);
     const float th = __fmaf_rn(u01(xb), 6.2831853071795865f, -3.1415926535897932f);
-    const float r = fast_sqrt(-2.0f * __logf(u));
-    n_cos = r * __cosf(th);
-    n_sin = r * __sinf(th);
+    const float r = fast_sqrt(-1.3862943611198906f * fast_lg2(u));   // sqrt(-2 ln u); u >= 2^-33: no denormals
+    n_cos = r * fast_cos(th);
+    n_sin = r * fast_sin(th);
 }
 
 // four normals for the four pixels of a quad from one Philox call

@@ -1,6 +1,7 @@
 // unet_prims.cu - host side of the tcgen05 conv/deconv tiles: TMA tensor-map construction, launch
 // geometry, weight packing, and the C-ABI primitives (include/eld_b200_unet.h).
 #include "common.cuh"
+#include <cstdlib>
 #include "conv_umma.cuh"
 #include "wgrad_umma.cuh"
 #include "unet_prims.h"
@@ -45,8 +46,15 @@ int launch_conv_gemm(eld_ctx* ctx, const GemmOp& op, cudaStream_t st)
     p.bias = op.bias;
     p.aux = static_cast<const __nv_bfloat16*>(op.aux); p.aux_pitch = op.aux_pitch; p.aux_c0 = op.aux_c0;
     p.cout = op.cout;
-    const int stage_bytes = (128 + p.n_tile) * p.kc * 2;
-    int stages = (200 * 1024) / stage_bytes;
+    const int rb = p.kc * 2;
+    const int b_tile = p.n_tile * rb;
+    const int b_total = op.taps * (op.cin / p.kc) * b_tile;
+    const int budget = 200 * 1024;
+    p.b_res = (op.a_mode == A_CONV && op.taps == 9 && p.n_total == p.n_tile && b_total <= 80 * 1024) ? 1 : 0;
+    p.halo = (op.a_mode == A_CONV && op.taps == 9 && (p.b_res || (160 * rb + 3 * b_tile) <= 64 * 1024)) ? 1 : 0;
+    if (getenv("ELD_CONV_V1")) { p.b_res = 0; p.halo = 0; }       // debugging aid: the plain 9-box path
+    const int stage_bytes = (p.halo ? 160 : 128) * rb + (p.b_res ? 0 : (p.halo ? 3 : 1) * b_tile);
+    int stages = (budget - (p.b_res ? b_total : 0)) / stage_bytes;
     if (stages > 8) stages = 8;
     if (stages < 2) stages = 2;
     p.stages = stages;
@@ -61,7 +69,7 @@ int launch_conv_gemm(eld_ctx* ctx, const GemmOp& op, cudaStream_t st)
         cuuint64_t str[4] = { op.a_pitch * eb, (cuuint64_t)op.W * op.a_pitch * eb,
                               (cuuint64_t)op.H * op.W * op.a_pitch * eb,
                               (cuuint64_t)op.n_img * op.H * op.W * op.a_pitch * eb };
-        cuuint32_t box[5] = { (cuuint32_t)p.kc, 16, 8, 1, 1 };
+        cuuint32_t box[5] = { (cuuint32_t)p.kc, 16, (cuuint32_t)(p.halo ? 10 : 8), 1, 1 };
         int rc = encode(ctx, &tmA, op.a, 5, dims, str, box, p.kc * 2);
         if (rc) return rc;
     } else {
@@ -81,7 +89,7 @@ int launch_conv_gemm(eld_ctx* ctx, const GemmOp& op, cudaStream_t st)
         int rc = encode(ctx, &tmB, op.b, 2, dims, str, box, p.kc * 2);
         if (rc) return rc;
     }
-    const size_t smem = (size_t)stages * stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    const size_t smem = (size_t)stages * stage_bytes + (p.b_res ? b_total : 0) + 1024 /*align slack*/ + 256 /*barriers*/;
     const int total_tiles = op.n_img * p.tiles_x * p.tiles_y * (p.n_total / p.n_tile);
     const int grid = total_tiles < ctx->num_sms ? total_tiles : ctx->num_sms;
     conv_umma_kernel<<<grid, kConvThreads, smem, st>>>(tmA, tmB, p);
