@@ -41,6 +41,8 @@ struct ConvGemmParams {
     int tmem_cols;
     int halo;             // conv3x3: one {kc,16,10} box per filter column, kh taps = row-shifted views
     int b_res;            // weights resident in smem (loaded once per CTA); requires n_total == n_tile
+    int tile_w;           // 16 (8x16 patch) or 8 (16x8 patch, full-halo mode)
+    int bo_mode;          // full-halo mode: 1 = put (start>>7)&7 into the descriptor's base_offset field
 };
 
 constexpr int kConvThreads = 192;
@@ -54,7 +56,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
 
     const int row_bytes = p.kc * 2;
-    const int a_bytes = (p.halo ? 160 : 128) * row_bytes;
+    // halo == 2 ("full halo"): ONE box {kc, 10, 18} per channel chunk; all nine taps are views of it
+    // (start shifted by (kh*10 + kw) pixel rows, 8-row groups 10 rows apart) - needs b_res.
+    const int a_bytes = p.halo == 2 ? ((180 * row_bytes + 1023) & ~1023) : (p.halo ? 160 : 128) * row_bytes;
     const int b_bytes = p.n_tile * row_bytes;                       // one tap, one channel chunk
     const int kchunks = p.cin / p.kc;
     const int b_per_stage = p.b_res ? 0 : (p.halo ? 3 : 1);
@@ -72,7 +76,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int n_tiles = p.n_total / p.n_tile;
     const int m_tiles = p.n_img * p.tiles_y * p.tiles_x;
     const int total_tiles = m_tiles * n_tiles;
-    const int ksteps = (p.halo ? 3 : p.taps) * kchunks;
+    const int ksteps = (p.halo == 2 ? 1 : (p.halo ? 3 : p.taps)) * kchunks;
+    const int tile_h = 128 / p.tile_w;
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&tmA);
@@ -105,8 +110,20 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const int img = m_tile / tiles_xy;
                 const int rem = m_tile - img * tiles_xy;
                 const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
-                const int x0 = tx * 16, y0 = ty * 8;
+                const int x0 = tx * p.tile_w, y0 = ty * tile_h;
                 const int n0 = n_t * p.n_tile;
+                if (p.halo == 2) {
+                    int c = p.a_c0;
+                    for (int kcI = 0; kcI < kchunks; ++kcI) {
+                        ptx::mbar_wait(&empty[s], ph ^ 1u);
+                        ptx::mbar_arrive_expect_tx(&full[s], (uint32_t)(180 * row_bytes));
+                        ptx::tma_load_5d(sa, &tmA, &full[s], c, x0 - 1, y0 - 1, img, 0);
+                        c += p.kc;
+                        sa += stage_bytes;
+                        if (++s == p.stages) { s = 0; ph ^= 1u; sa = stage0; }
+                    }
+                    continue;
+                }
                 if (p.halo) {
                     for (int kw = 0; kw < 3; ++kw) {
                         int c = p.a_c0;
@@ -176,7 +193,23 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int ks = 0; ks < ksteps; ++ks) {
                 ptx::mbar_wait(&full[s], ph);
                 ptx::tc_fence_after();
-                if (lane == 0) {
+                if (lane == 0 && p.halo == 2) {
+                    // ks = channel chunk; 9 taps, each a shifted view of the same halo tile
+                    const uint64_t a_hi = ptx::make_smem_desc(0, 16, 10u * row_bytes, layout);
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const int kh = tap / 3, kw = tap - 3 * kh;
+                        const uint32_t astart = a_addr + (uint32_t)((kh * 10 + kw) * row_bytes);
+                        uint64_t ad = a_hi | (uint64_t)((astart & 0x3FFFFu) >> 4);
+                        if (p.bo_mode) ad |= (uint64_t)((astart >> 7) & 7u) << 49;
+                        uint64_t bd = desc_hi | (uint64_t)(((bres_base + (uint32_t)(tap * kchunks + ks) * (uint32_t)b_bytes) & 0x3FFFFu) >> 4);
+                        for (int k = 0; k < ksub; ++k) {
+                            ptx::umma_bf16(d_tmem, ad, bd, idesc, (ks | tap | k) != 0 ? 1u : 0u);
+                            ad += 2; bd += 2;
+                        }
+                    }
+                    ptx::umma_commit(&empty[s]);
+                    if (ks == ksteps - 1) ptx::umma_commit(&tmem_full[acc]);
+                } else if (lane == 0) {
                     uint64_t ad0 = desc_hi | (uint64_t)((a_addr & 0x3FFFFu) >> 4);
                     uint64_t bd0;
                     uint32_t b_sub_step;                       // descriptor units between the B tiles of taps kh, kh+1
@@ -210,14 +243,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // ===================== epilogue (warps 2..5) =====================
         const int q = warp & 3;                // TMEM lane quarter this warp may read
         const int m = q * 32 + lane;           // pixel inside the 8x16 patch
-        const int py = m >> 4, px = m & 15;
+        const int py = m / p.tile_w, px = m % p.tile_w;
         uint32_t tile_it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_it) {
             const int m_tile = tile / n_tiles, n_t = tile - m_tile * n_tiles;
             const int img = m_tile / (p.tiles_x * p.tiles_y);
             const int rem = m_tile - img * (p.tiles_x * p.tiles_y);
             const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
-            const int x = tx * 16 + px, y = ty * 8 + py;
+            const int x = tx * p.tile_w + px, y = ty * (128 / p.tile_w) + py;
             const uint32_t acc = tile_it & 1u;
             const uint32_t acc_ph = (tile_it >> 1) & 1u;
             ptx::mbar_wait(&tmem_full[acc], acc_ph);

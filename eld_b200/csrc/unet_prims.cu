@@ -53,7 +53,19 @@ int launch_conv_gemm(eld_ctx* ctx, const GemmOp& op, cudaStream_t st)
     p.b_res = (op.a_mode == A_CONV && op.taps == 9 && p.n_total == p.n_tile && b_total <= 80 * 1024) ? 1 : 0;
     p.halo = (op.a_mode == A_CONV && op.taps == 9 && (p.b_res || (160 * rb + 3 * b_tile) <= 64 * 1024)) ? 1 : 0;
     if (getenv("ELD_CONV_V1")) { p.b_res = 0; p.halo = 0; }       // debugging aid: the plain 9-box path
-    const int stage_bytes = (p.halo ? 160 : 128) * rb + (p.b_res ? 0 : (p.halo ? 3 : 1) * b_tile);
+    p.tile_w = 16;
+    p.bo_mode = 0;
+    // Full halo: measured on B200 - the UMMA descriptor's swizzle is a function of the ABSOLUTE smem address
+    // bits, so a K-major operand may start at any 16-byte-aligned pixel row of a TMA-written tile and its
+    // 8-row groups may be any stride apart (base_offset left 0; setting it to (start>>7)&7 gives wrong
+    // results).  One {kc,10,18} box then serves all nine taps.
+    if (p.b_res && !getenv("ELD_CONV_NOHALO2") && op.H % 16 == 0 && op.W % 8 == 0) {
+        p.halo = 2; p.tile_w = 8;
+        p.bo_mode = getenv("ELD_CONV_BO") ? atoi(getenv("ELD_CONV_BO")) : 0;
+    }
+    p.tiles_x = op.W / p.tile_w; p.tiles_y = op.H / (128 / p.tile_w);
+    const int stage_bytes = p.halo == 2 ? ((180 * rb + 1023) & ~1023)
+                                        : (p.halo ? 160 : 128) * rb + (p.b_res ? 0 : (p.halo ? 3 : 1) * b_tile);
     int stages = (budget - (p.b_res ? b_total : 0)) / stage_bytes;
     if (stages > 8) stages = 8;
     if (stages < 2) stages = 2;
@@ -69,7 +81,8 @@ int launch_conv_gemm(eld_ctx* ctx, const GemmOp& op, cudaStream_t st)
         cuuint64_t str[4] = { op.a_pitch * eb, (cuuint64_t)op.W * op.a_pitch * eb,
                               (cuuint64_t)op.H * op.W * op.a_pitch * eb,
                               (cuuint64_t)op.n_img * op.H * op.W * op.a_pitch * eb };
-        cuuint32_t box[5] = { (cuuint32_t)p.kc, 16, (cuuint32_t)(p.halo ? 10 : 8), 1, 1 };
+        cuuint32_t box[5] = { (cuuint32_t)p.kc, (cuuint32_t)(p.halo == 2 ? 10 : 16),
+                              (cuuint32_t)(p.halo == 2 ? 18 : (p.halo ? 10 : 8)), 1, 1 };
         int rc = encode(ctx, &tmA, op.a, 5, dims, str, box, p.kc * 2);
         if (rc) return rc;
     } else {
