@@ -47,6 +47,23 @@ struct ConvGemmParams {
 
 constexpr int kConvThreads = 192;
 
+// Full-halo issue: 9 taps x KSUB tcgen05.mma, fully unrolled so that every operand offset is an immediate
+// (the MMA issuer is ONE thread: for N = 32 tiles its instruction count per MMA is what bounds the layer).
+template <int KSUB>
+__device__ __forceinline__ void issue_halo2(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                            uint32_t b_tap_step, uint32_t idesc, bool first_chunk)
+{
+    constexpr uint32_t kRow = (uint32_t)(32 * KSUB) >> 4;          // one pixel row of kc = 16*KSUB channels, in 16 B units
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+        const uint32_t a_tap = a_lo + (uint32_t)((tap / 3) * 10 + (tap % 3)) * kRow;
+#pragma unroll
+        for (int k = 0; k < KSUB; ++k)
+            ptx::umma_bf16_lohi(d_tmem, a_tap + 2u * k, a_hi, b_lo + 2u * k, b_hi, idesc, !(first_chunk && tap == 0 && k == 0));
+        b_lo += b_tap_step;
+    }
+}
+
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const ConvGemmParams p)
@@ -195,18 +212,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 ptx::tc_fence_after();
                 if (lane == 0 && p.halo == 2) {
                     // ks = channel chunk; 9 taps, each a shifted view of the same halo tile
-                    const uint64_t a_hi = ptx::make_smem_desc(0, 16, 10u * row_bytes, layout);
-                    for (int tap = 0; tap < 9; ++tap) {
-                        const int kh = tap / 3, kw = tap - 3 * kh;
-                        const uint32_t astart = a_addr + (uint32_t)((kh * 10 + kw) * row_bytes);
-                        uint64_t ad = a_hi | (uint64_t)((astart & 0x3FFFFu) >> 4);
-                        if (p.bo_mode) ad |= (uint64_t)((astart >> 7) & 7u) << 49;
-                        uint64_t bd = desc_hi | (uint64_t)(((bres_base + (uint32_t)(tap * kchunks + ks) * (uint32_t)b_bytes) & 0x3FFFFu) >> 4);
-                        for (int k = 0; k < ksub; ++k) {
-                            ptx::umma_bf16(d_tmem, ad, bd, idesc, (ks | tap | k) != 0 ? 1u : 0u);
-                            ad += 2; bd += 2;
-                        }
-                    }
+                    const uint64_t a_hi64 = ptx::make_smem_desc(0, 16, 10u * row_bytes, layout);
+                    const uint32_t a_lo = (uint32_t)a_hi64 | ((a_addr & 0x3FFFFu) >> 4);
+                    const uint32_t b_lo = (uint32_t)desc_hi | (((bres_base + (uint32_t)ks * (uint32_t)b_bytes) & 0x3FFFFu) >> 4);
+                    const uint32_t b_tap_step = (uint32_t)kchunks * b_step;
+                    if (ksub == 2) issue_halo2<2>(d_tmem, a_lo, (uint32_t)(a_hi64 >> 32), b_lo, (uint32_t)(desc_hi >> 32), b_tap_step, idesc, ks == 0);
+                    else           issue_halo2<4>(d_tmem, a_lo, (uint32_t)(a_hi64 >> 32), b_lo, (uint32_t)(desc_hi >> 32), b_tap_step, idesc, ks == 0);
                     ptx::umma_commit(&empty[s]);
                     if (ks == ksteps - 1) ptx::umma_commit(&tmem_full[acc]);
                 } else if (lane == 0) {

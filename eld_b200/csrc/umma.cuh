@@ -89,6 +89,26 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// same, descriptors given as (lo, hi) 32-bit halves; `accumulate` is a compile-time-friendly flag
+__device__ __forceinline__ void umma_bf16_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                               uint32_t idesc, bool accumulate)
+{
+    if (accumulate) {
+        asm volatile(
+            "{\n\t.reg .b64 da, db;\n\t.reg .pred p;\n\t"
+            "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+            "setp.eq.b32 p, 0, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+            ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc) : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .b64 da, db;\n\t.reg .pred p;\n\t"
+            "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+            "setp.ne.b32 p, 0, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+            ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc) : "memory");
+    }
+}
 // arrive on an mbarrier when all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar)
 {
