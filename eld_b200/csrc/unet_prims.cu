@@ -4,6 +4,7 @@
 #include <cstdlib>
 #include "conv_umma.cuh"
 #include "wgrad_umma.cuh"
+#include "wgrad_conv.cuh"
 #include "unet_prims.h"
 
 namespace eld {
@@ -116,11 +117,74 @@ int init_gemm_kernels(eld_ctx* ctx)
     ELD_CHECK_CUDA(cudaSetDevice(ctx->device));
     ELD_CHECK_CUDA(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     ELD_CHECK_CUDA(cudaFuncSetAttribute(wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    ELD_CHECK_CUDA(cudaFuncSetAttribute(wgrad_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    return ELD_OK;
+}
+
+// conv3x3 weight gradient, full-halo generation (wgrad_conv.cuh)
+static int launch_wgrad_conv(eld_ctx* ctx, const WgradOp& op, cudaStream_t st)
+{
+    Wgrad2Params p{};
+    p.n_img = op.n_img; p.H = op.H; p.W = op.W;
+    p.chunks_x = op.W / 8; p.chunks_y = op.H / 8;
+    p.cin = op.p_ch; p.cout = op.q_ch; p.p_c0 = op.p_c0; p.q_c0 = op.q_c0;
+    if (op.p_ch == 32) { p.kind = 0; p.box_ch = 32; p.m_tiles = 3; p.cps = 1; p.p_boxes = 1; }
+    else if (op.p_ch == 64) { p.kind = 1; p.box_ch = 64; p.m_tiles = 5; p.cps = 1; p.p_boxes = 1; }
+    else { p.kind = 2; p.box_ch = 64; p.m_tiles = 9; p.cps = op.p_ch / 128; p.p_boxes = 2; }
+    p.q_box_ch = (op.q_ch % 64 == 0) ? 64 : 32;
+    p.n_tile = op.q_ch <= 256 ? op.q_ch : 256;
+    p.n_tiles = op.q_ch / p.n_tile;
+    p.q_boxes = p.n_tile / p.q_box_ch;
+    int gmax = 512 / p.n_tile;
+    if (gmax > kWg2MaxG) gmax = kWg2MaxG;
+    p.groups = (p.m_tiles + gmax - 1) / gmax;
+    p.G = (p.m_tiles + p.groups - 1) / p.groups;
+    const int rb_p = p.box_ch * 2, rb_q = p.q_box_ch * 2;
+    const int stage_bytes = p.p_boxes * ((100 * rb_p + 1023) & ~1023) + p.q_boxes * 64 * rb_q;
+    int stages = (200 * 1024) / stage_bytes;
+    if (stages > 8) stages = 8;
+    if (stages < 2) stages = 2;
+    p.stages = stages;
+    int cols = 32;
+    while (cols < p.G * p.n_tile) cols *= 2;
+    p.tmem_cols = cols;
+    const int items = p.cps * p.groups * p.n_tiles;
+    const int total_chunks = op.n_img * p.chunks_x * p.chunks_y;
+    int ksplit = (2 * ctx->num_sms) / items;
+    if (ksplit < 1) ksplit = 1;
+    if (ksplit > total_chunks) ksplit = total_chunks;
+    p.ksplit = ksplit;
+    p.dw = op.dw;
+    CUtensorMap tmP, tmQ;
+    const cuuint64_t eb = 2;
+    {
+        cuuint64_t dims[5] = { (cuuint64_t)op.p_pitch, (cuuint64_t)op.W, (cuuint64_t)op.H, (cuuint64_t)op.n_img, 1 };
+        cuuint64_t str[4] = { op.p_pitch * eb, (cuuint64_t)op.W * op.p_pitch * eb, (cuuint64_t)op.H * op.W * op.p_pitch * eb,
+                              (cuuint64_t)op.n_img * op.H * op.W * op.p_pitch * eb };
+        cuuint32_t box[5] = { (cuuint32_t)p.box_ch, 10, 10, 1, 1 };
+        int rc = encode(ctx, &tmP, op.p, 5, dims, str, box, p.box_ch * 2);
+        if (rc) return rc;
+    }
+    {
+        cuuint64_t dims[5] = { (cuuint64_t)op.q_pitch, (cuuint64_t)op.W, (cuuint64_t)op.H, (cuuint64_t)op.n_img, 1 };
+        cuuint64_t str[4] = { op.q_pitch * eb, (cuuint64_t)op.W * op.q_pitch * eb, (cuuint64_t)op.H * op.W * op.q_pitch * eb,
+                              (cuuint64_t)op.n_img * op.H * op.W * op.q_pitch * eb };
+        cuuint32_t box[5] = { (cuuint32_t)p.q_box_ch, 8, 8, 1, 1 };
+        int rc = encode(ctx, &tmQ, op.q, 5, dims, str, box, p.q_box_ch * 2);
+        if (rc) return rc;
+    }
+    const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
+    wgrad_conv_kernel<<<items * p.ksplit, kWg2Threads, smem, st>>>(tmP, tmQ, p);
+    ELD_CHECK_CUDA(cudaGetLastError());
+    count_launch(ctx);
     return ELD_OK;
 }
 
 int launch_wgrad(eld_ctx* ctx, const WgradOp& op, cudaStream_t st)
 {
+    if (op.mode == WG_CONV && op.H % 8 == 0 && op.W % 8 == 0 && (op.p_ch == 32 || op.p_ch == 64 || op.p_ch % 128 == 0) &&
+        op.q_ch % 32 == 0 && !getenv("ELD_WGRAD_V1"))
+        return launch_wgrad_conv(ctx, op, st);
     ELD_REQUIRE(op.H % 4 == 0 && op.W % 16 == 0, "wgrad tile: H=%d must be a multiple of 4 and W=%d of 16", op.H, op.W);
     ELD_REQUIRE(op.p_ch % 32 == 0 && op.q_ch % 32 == 0, "wgrad tile: channel counts must be multiples of 32");
     WgradParams p{};
