@@ -61,6 +61,30 @@ pack_all_kernel(const float* __restrict__ params, __nv_bfloat16* __restrict__ pa
     }
 }
 
+// staging [tap][ci][co] -> PyTorch OIHW [co][ci][tap]; one block per (32 co x 32 ci) tile of one layer
+__global__ void __launch_bounds__(256)
+wgrad_permute_kernel(const float* __restrict__ gtmp, float* __restrict__ grads, const __grid_constant__ PackTable T)
+{
+    __shared__ float tile[9][32][33];
+    const PackEntry& e = T.e[blockIdx.y];
+    if (e.type != L_CONV3) return;
+    const int ct = e.cout / 32, it = e.cin / 32;
+    for (int t = blockIdx.x; t < ct * it; t += gridDim.x) {
+        const int co0 = (t % ct) * 32, ci0 = (t / ct) * 32;
+        __syncthreads();
+        for (int i = threadIdx.x; i < 9 * 32 * 32; i += 256) {
+            const int co = i & 31, ci = (i >> 5) & 31, tap = i >> 10;
+            tile[tap][ci][co] = gtmp[e.src + ((size_t)tap * e.cin + ci0 + ci) * e.cout + co0 + co];
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < 32 * 288; i += 256) {
+            const int co = i / 288, r = i - co * 288;          // r = ci*9 + tap, contiguous in OIHW
+            const int ci = r / 9, tap = r - ci * 9;
+            grads[e.src + ((size_t)(co0 + co) * e.cin + ci0 + ci) * 9 + tap] = tile[tap][ci][co];
+        }
+    }
+}
+
 }  // namespace eld
 
 using namespace eld;
@@ -78,6 +102,7 @@ struct eld_unet {
     __nv_bfloat16 *dz9_2, *dz9_1, *dcat9, *dz8_2, *dz8_1, *dcat8, *dz7_2, *dz7_1, *dcat7, *dz6_2, *dz6_1, *dcat6,
         *dz5_2, *dz5_1, *dp4, *dz4_2, *dz4_1, *dp3, *dz3_2, *dz3_1, *dp2, *dz2_2, *dz2_1, *dp1, *dz1_2, *dz1_1;
     __nv_bfloat16* packed;
+    float* gtmp = nullptr;
     PackTable table;
     // optional per-launch profile (CUDA events on the launch stream)
     bool profile = false;
@@ -125,6 +150,10 @@ static size_t layout(eld_unet* u, char* base, bool train)
     }
     u->packed = reinterpret_cast<__nv_bfloat16*>(base + off);
     off += (pk * 2 + 1023) & ~(size_t)1023;
+    if (train) {   // [tap][ci][co] staging of the conv3x3 weight gradients (same offsets as the fp32 parameters)
+        u->gtmp = reinterpret_cast<float*>(base + off);
+        off += (u->n_params * 4 + 1023) & ~(size_t)1023;
+    }
     return off;
 }
 
@@ -297,7 +326,8 @@ struct Runner {
         WgradOp op{};
         op.mode = WG_CONV; op.p = x; op.p_pitch = xp; op.p_c0 = xc0; op.p_ch = l.cin;
         op.q = dz; op.q_pitch = l.cout; op.q_c0 = 0; op.q_ch = l.cout;
-        op.n_img = u->n; op.H = u->H >> lvl; op.W = u->W >> lvl; op.dw = grads + l.w_off;
+        op.n_img = u->n; op.H = u->H >> lvl; op.W = u->W >> lvl;
+        op.dw = u->gtmp + l.w_off; op.out_tco = 1;
         const double px = (double)u->n * op.H * op.W;
         {
             Scope sc(u, st, l.name, "wgrad", 2.0 * px * l.cout * 9 * l.cin, px * 2 * (l.cin + l.cout) + 36.0 * l.cin * l.cout);
@@ -425,8 +455,17 @@ struct Runner {
         TRY(conv_wgrad(I_C12, U->a1_1, 32, 0, U->dz1_2, g, 0));
         TRY(conv_dgrad(I_C12, U->dz1_2, U->dz1_1, 32, 0, U->a1_1, 32, 0, 0));
         const double px = (double)U->n * U->H * U->W;
-        Scope sc(u, st, "conv1_1", "wgrad", 2.0 * px * 32 * 36, px * (16 + 64));
-        TRY(launch_first_conv_wgrad(ctx(), x, U->dz1_1, g + U->L[I_C11].w_off, g + U->L[I_C11].b_off, U->n, U->H, U->W, st));
+        {
+            Scope sc(u, st, "conv1_1", "wgrad", 2.0 * px * 32 * 36, px * (16 + 64));
+            TRY(launch_first_conv_wgrad(ctx(), x, U->dz1_1, g + U->L[I_C11].w_off, g + U->L[I_C11].b_off, U->n, U->H, U->W, st));
+        }
+        {
+            Scope sc(u, st, "weights", "gperm", 0.0, (double)U->n_params * 8);
+            dim3 grid(32, U->table.n);
+            wgrad_permute_kernel<<<grid, 256, 0, st>>>(U->gtmp, g, U->table);
+            ELD_CHECK_CUDA(cudaGetLastError());
+            count_launch(ctx());
+        }
         return ELD_OK;
     }
 };
@@ -453,6 +492,7 @@ extern "C" int eld_unet_train_step(eld_unet* u, const float* params, const float
     ELD_CHECK_CUDA(cudaSetDevice(u->ctx->device));
     Runner r{ u, params, static_cast<cudaStream_t>(stream) };
     ELD_CHECK_CUDA(cudaMemsetAsync(grads, 0, u->n_params * sizeof(float), r.st));
+    ELD_CHECK_CUDA(cudaMemsetAsync(u->gtmp, 0, u->n_params * sizeof(float), r.st));
     ELD_CHECK_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), r.st));
     TRY(r.forward(x));
     {

@@ -150,11 +150,14 @@ static int launch_wgrad_conv(eld_ctx* ctx, const WgradOp& op, cudaStream_t st)
     p.tmem_cols = cols;
     const int items = p.cps * p.groups * p.n_tiles;
     const int total_chunks = op.n_img * p.chunks_x * p.chunks_y;
-    int ksplit = (2 * ctx->num_sms) / items;
+    // split-K: every split adds its whole [9*cin x cout] tile with red.add, so big outputs get one wave only
+    const size_t outputs = (size_t)9 * op.p_ch * op.q_ch;
+    int ksplit = ((outputs > (1u << 18) ? 1 : 2) * ctx->num_sms) / items;
     if (ksplit < 1) ksplit = 1;
     if (ksplit > total_chunks) ksplit = total_chunks;
     p.ksplit = ksplit;
     p.dw = op.dw;
+    p.out_tco = op.out_tco;
     CUtensorMap tmP, tmQ;
     const cuuint64_t eb = 2;
     {

@@ -34,6 +34,7 @@ struct WgradOp {
     int q_pitch, q_c0, q_ch;
     int n_img, H, W;     // pixel grid of the reduction (deconv: coarse)
     float* dw;           // f32, PyTorch layout, accumulated into (zero it first)
+    int out_tco;         // conv only: 1 = dw is the [tap][ci][co] staging layout (vector red.add), see wgrad_conv.cuh
 };
 int init_gemm_kernels(eld_ctx* ctx);   // opt in to large dynamic smem (call once, outside graph capture)
 int launch_wgrad(eld_ctx* ctx, const WgradOp& op, cudaStream_t st);

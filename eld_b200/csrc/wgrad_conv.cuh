@@ -30,6 +30,7 @@ struct Wgrad2Params {
     int p_boxes, q_boxes;
     int ksplit, stages, tmem_cols;
     float* dw;
+    int out_tco;                // 0: dw is OIHW [co][ci][3][3], scalar red.add; 1: dw is [tap][ci][co], 16-byte vector red.add
 };
 
 constexpr int kWg2Threads = 192;
@@ -183,10 +184,19 @@ wgrad_conv_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant
                 ptx::tmem_ld32(t_addr + c32 * 32, v);
                 ptx::tmem_ld_wait();
                 if (tap <= 8) {
+                    if (p.out_tco) {
+                        float* dst = p.dw + ((size_t)tap * p.cin + ci) * p.cout + nt * p.n_tile + c32 * 32;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int co = nt * p.n_tile + c32 * 32 + j;
-                        atomicAdd(p.dw + ((size_t)co * p.cin + ci) * 9 + tap, __uint_as_float(v[j]));
+                        for (int j = 0; j < 32; j += 4)
+                            asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};"
+                                         :: "l"(dst + j), "f"(__uint_as_float(v[j])), "f"(__uint_as_float(v[j + 1])),
+                                            "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3])) : "memory");
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int co = nt * p.n_tile + c32 * 32 + j;
+                            atomicAdd(p.dw + ((size_t)co * p.cin + ci) * 9 + tap, __uint_as_float(v[j]));
+                        }
                     }
                 }
             }
