@@ -34,7 +34,7 @@ enum { I_C11 = 0, I_C12, I_C21, I_C22, I_C31, I_C32, I_C41, I_C42, I_C51, I_C52,
        I_C71, I_C72, I_UP8, I_C81, I_C82, I_UP9, I_C91, I_C92, I_C10 };
 
 struct PackEntry { unsigned long long src, dst_f, dst_d; int cout, cin, type; int pad; };
-struct PackTable { PackEntry e[kNumLayers]; int n; };
+struct PackTable { PackEntry e[kNumLayers]; int n; unsigned long long first_stage, first_dst; };
 
 // one launch packs every layer's fp32 master weights into both bf16 GEMM operands (fprop + dgrad)
 __global__ void __launch_bounds__(256)
@@ -66,6 +66,14 @@ __global__ void __launch_bounds__(256)
 wgrad_permute_kernel(const float* __restrict__ gtmp, float* __restrict__ grads, const __grid_constant__ PackTable T)
 {
     __shared__ float tile[9][32][33];
+    if ((int)blockIdx.y == T.n) {   // conv1_1: staging is [9][32 (4 real)][32] behind the regular area; dst [32][4][9] at offset 0
+        const float* src = gtmp + T.first_stage;
+        for (int i = blockIdx.x * 256 + threadIdx.x; i < 32 * 36; i += gridDim.x * 256) {
+            const int co = i / 36, r = i - co * 36, ci = r / 9, tap = r - ci * 9;
+            grads[T.first_dst + i] = src[(tap * 32 + ci) * 32 + co];
+        }
+        return;
+    }
     const PackEntry& e = T.e[blockIdx.y];
     if (e.type != L_CONV3) return;
     const int ct = e.cout / 32, it = e.cin / 32;
@@ -98,7 +106,7 @@ struct eld_unet {
     size_t ws_bytes;
     // activations / gradients (bf16), offsets in bytes into ws
     __nv_bfloat16 *a1_1, *cat9, *p1, *a2_1, *cat8, *p2, *a3_1, *cat7, *p3, *a4_1, *cat6, *p4, *a5_1, *a5_2,
-        *a6_1, *a6_2, *a7_1, *a7_2, *a8_1, *a8_2, *a9_1, *a9_2;
+        *a6_1, *a6_2, *a7_1, *a7_2, *a8_1, *a8_2, *a9_1, *a9_2, *x32 = nullptr;
     __nv_bfloat16 *dz9_2, *dz9_1, *dcat9, *dz8_2, *dz8_1, *dcat8, *dz7_2, *dz7_1, *dcat7, *dz6_2, *dz6_1, *dcat6,
         *dz5_2, *dz5_1, *dp4, *dz4_2, *dz4_1, *dp3, *dz3_2, *dz3_1, *dp2, *dz2_2, *dz2_1, *dp1, *dz1_2, *dz1_1;
     __nv_bfloat16* packed;
@@ -129,6 +137,7 @@ static size_t layout(eld_unet* u, char* base, bool train)
     take(&u->a6_1, 3, 256); take(&u->a6_2, 3, 256); take(&u->a7_1, 2, 128); take(&u->a7_2, 2, 128);
     take(&u->a8_1, 1, 64); take(&u->a8_2, 1, 64); take(&u->a9_1, 0, 32); take(&u->a9_2, 0, 32);
     if (train) {
+        take(&u->x32, 0, 32);
         take(&u->dz9_2, 0, 32); take(&u->dz9_1, 0, 32); take(&u->dcat9, 0, 64);
         take(&u->dz8_2, 1, 64); take(&u->dz8_1, 1, 64); take(&u->dcat8, 1, 128);
         take(&u->dz7_2, 2, 128); take(&u->dz7_1, 2, 128); take(&u->dcat7, 2, 256);
@@ -152,7 +161,7 @@ static size_t layout(eld_unet* u, char* base, bool train)
     off += (pk * 2 + 1023) & ~(size_t)1023;
     if (train) {   // [tap][ci][co] staging of the conv3x3 weight gradients (same offsets as the fp32 parameters)
         u->gtmp = reinterpret_cast<float*>(base + off);
-        off += (u->n_params * 4 + 1023) & ~(size_t)1023;
+        off += ((u->n_params + 9216) * 4 + 1023) & ~(size_t)1023;     // + [9][32][32] staging of conv1_1 (input padded to 32 ch)
     }
     return off;
 }
@@ -229,6 +238,8 @@ extern "C" int eld_unet_create(eld_ctx* ctx, int n, int h, int w, int train, voi
         u->table.e[k++] = PackEntry{ l.w_off, l.wf_off, l.wd_off, l.cout, l.cin, l.type, 0 };
     }
     u->table.n = k;
+    u->table.first_stage = u->n_params;
+    u->table.first_dst = u->L[I_C11].w_off;
     // opt in to large dynamic shared memory once (not inside a captured region)
     { int rc = init_gemm_kernels(ctx); if (rc != ELD_OK) { delete u; return rc; } }
     *out = u;
@@ -381,7 +392,7 @@ struct Runner {
         {
             const double px = (double)U->n * U->H * U->W;
             Scope sc(u, st, "conv1_1", "fprop", 2.0 * px * 32 * 36, px * (16 + 64));
-            TRY(launch_first_conv(ctx(), x, params + U->L[I_C11].w_off, bias(I_C11), U->a1_1, U->n, U->H, U->W, st));
+            TRY(launch_first_conv(ctx(), x, params + U->L[I_C11].w_off, bias(I_C11), U->a1_1, U->x32, U->n, U->H, U->W, st));
         }
         TRY(conv(I_C12, U->a1_1, 32, 0, U->cat9, 64, 32, 0));  TRY(pool(U->cat9, 64, 32, U->p1, 32, 1));
         TRY(conv(I_C21, U->p1, 32, 0, U->a2_1, 64, 0, 1));
@@ -456,12 +467,21 @@ struct Runner {
         TRY(conv_dgrad(I_C12, U->dz1_2, U->dz1_1, 32, 0, U->a1_1, 32, 0, 0));
         const double px = (double)U->n * U->H * U->W;
         {
-            Scope sc(u, st, "conv1_1", "wgrad", 2.0 * px * 32 * 36, px * (16 + 64));
-            TRY(launch_first_conv_wgrad(ctx(), x, U->dz1_1, g + U->L[I_C11].w_off, g + U->L[I_C11].b_off, U->n, U->H, U->W, st));
+            // conv1_1: the tcgen05 wgrad tile on the 32-channel padded copy of the input (4 real channels)
+            Scope sc(u, st, "conv1_1", "wgrad", 2.0 * px * 32 * 36, px * (64 + 64));
+            WgradOp op{};
+            op.mode = WG_CONV; op.p = U->x32; op.p_pitch = 32; op.p_c0 = 0; op.p_ch = 32;
+            op.q = U->dz1_1; op.q_pitch = 32; op.q_c0 = 0; op.q_ch = 32;
+            op.n_img = U->n; op.H = U->H; op.W = U->W; op.dw = U->gtmp + U->n_params; op.out_tco = 1;
+            TRY(launch_wgrad(ctx(), op, st));
+        }
+        {
+            Scope sc(u, st, "conv1_1", "bgrad", 0.0, px * 64);
+            TRY(launch_colsum(ctx(), U->dz1_1, 32, 0, 32, (size_t)px, g + U->L[I_C11].b_off, st));
         }
         {
             Scope sc(u, st, "weights", "gperm", 0.0, (double)U->n_params * 8);
-            dim3 grid(32, U->table.n);
+            dim3 grid(32, U->table.n + 1);
             wgrad_permute_kernel<<<grid, 256, 0, st>>>(U->gtmp, g, U->table);
             ELD_CHECK_CUDA(cudaGetLastError());
             count_launch(ctx());
@@ -492,7 +512,7 @@ extern "C" int eld_unet_train_step(eld_unet* u, const float* params, const float
     ELD_CHECK_CUDA(cudaSetDevice(u->ctx->device));
     Runner r{ u, params, static_cast<cudaStream_t>(stream) };
     ELD_CHECK_CUDA(cudaMemsetAsync(grads, 0, u->n_params * sizeof(float), r.st));
-    ELD_CHECK_CUDA(cudaMemsetAsync(u->gtmp, 0, u->n_params * sizeof(float), r.st));
+    ELD_CHECK_CUDA(cudaMemsetAsync(u->gtmp, 0, (u->n_params + 9216) * sizeof(float), r.st));
     ELD_CHECK_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), r.st));
     TRY(r.forward(x));
     {

@@ -22,7 +22,7 @@ __device__ __forceinline__ uint32_t pack_bf2(float a, float b)
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 first_conv_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
-                  __nv_bfloat16* __restrict__ y, int H, int W)
+                  __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ x32, int H, int W)
 {
     __shared__ float xs[4][18][18];
     __shared__ __align__(16) float ws[36][32];
@@ -62,6 +62,14 @@ first_conv_kernel(const float* __restrict__ x, const float* __restrict__ w, cons
                 acc[4 * j + 3] = fmaf(v, w4.w, acc[4 * j + 3]);
             }
         }
+    }
+    if (x32) {   // the input as a 32-channel NHWC bf16 tensor (channels 4..31 zero): operand of the tcgen05 wgrad
+        uint4* d32 = reinterpret_cast<uint4*>(x32 + (((size_t)n * H + (y0 + py)) * W + (x0 + px)) * 32);
+        d32[0] = make_uint4(pack_bf2(xs[0][py + 1][px + 1], xs[1][py + 1][px + 1]),
+                            pack_bf2(xs[2][py + 1][px + 1], xs[3][py + 1][px + 1]), 0u, 0u);
+        d32[1] = make_uint4(0u, 0u, 0u, 0u);
+        d32[2] = make_uint4(0u, 0u, 0u, 0u);
+        d32[3] = make_uint4(0u, 0u, 0u, 0u);
     }
     uint4* dst = reinterpret_cast<uint4*>(y + (((size_t)n * H + (y0 + py)) * W + (x0 + px)) * 32);
 #pragma unroll
@@ -389,10 +397,10 @@ static inline int grid_for(size_t work, int per_block, int cap)
     return (int)b;
 }
 
-int launch_first_conv(eld_ctx* ctx, const float* x, const float* w, const float* b, void* y, int n, int H, int W, cudaStream_t st)
+int launch_first_conv(eld_ctx* ctx, const float* x, const float* w, const float* b, void* y, void* x32, int n, int H, int W, cudaStream_t st)
 {
     dim3 grid((W + 15) / 16, (H + 15) / 16, n);
-    first_conv_kernel<<<grid, 256, 0, st>>>(x, w, b, static_cast<__nv_bfloat16*>(y), H, W);
+    first_conv_kernel<<<grid, 256, 0, st>>>(x, w, b, static_cast<__nv_bfloat16*>(y), static_cast<__nv_bfloat16*>(x32), H, W);
     ELD_CHECK_CUDA(cudaGetLastError());
     count_launch(ctx);
     return ELD_OK;
