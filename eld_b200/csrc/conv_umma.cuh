@@ -43,9 +43,11 @@ struct ConvGemmParams {
     int b_res;            // weights resident in smem (loaded once per CTA); requires n_total == n_tile
     int tile_w;           // 16 (8x16 patch) or 8 (16x8 patch, full-halo mode)
     int bo_mode;          // full-halo mode: 1 = put (start>>7)&7 into the descriptor's base_offset field
+    int acc_stages;       // TMEM accumulator ring depth (2..8): acc_stages * n_tile <= 512 columns
 };
 
-constexpr int kConvThreads = 192;
+constexpr int kConvThreads = 320;   // warp 0 TMA, warp 1 MMA, warps 2-5 and 6-9: two epilogue groups (alternate tiles)
+constexpr int kMaxAccStages = 8;
 
 // Full-halo issue: 9 taps x KSUB tcgen05.mma, fully unrolled so that every operand offset is an immediate
 // (the MMA issuer is ONE thread: for N = 32 tiles its instruction count per MMA is what bounds the layer).
@@ -85,8 +87,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint64_t* full = reinterpret_cast<uint64_t*>(stage0 + (size_t)p.stages * stage_bytes);
     uint64_t* empty = full + p.stages;
     uint64_t* tmem_full = empty + p.stages;
-    uint64_t* tmem_empty = tmem_full + 2;
-    uint64_t* bres_full = tmem_empty + 2;
+    uint64_t* tmem_empty = tmem_full + kMaxAccStages;
+    uint64_t* bres_full = tmem_empty + kMaxAccStages;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bres_full + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -100,7 +102,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         ptx::prefetch_tmap(&tmA);
         ptx::prefetch_tmap(&tmB);
         for (int s = 0; s < p.stages; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
-        for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tmem_full[a], 1); ptx::mbar_init(&tmem_empty[a], 4); }
+        for (int a = 0; a < p.acc_stages; ++a) { ptx::mbar_init(&tmem_full[a], 1); ptx::mbar_init(&tmem_empty[a], 4); }
         ptx::mbar_init(bres_full, 1);
         ptx::fence_barrier_init();
     }
@@ -201,12 +203,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         uint32_t ph = 0, tile_it = 0;
         uint32_t a_addr = stage_base;
         if (p.b_res) { ptx::mbar_wait(bres_full, 0); ptx::tc_fence_after(); }
+        uint32_t acc = 0, acc_ph = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_it) {
-            const uint32_t acc = tile_it & 1u;
-            const uint32_t acc_ph = (tile_it >> 1) & 1u;
             ptx::mbar_wait(&tmem_empty[acc], acc_ph ^ 1u);
             ptx::tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.n_tile;
+            const uint32_t acc_cur = acc;
+            if (++acc == (uint32_t)p.acc_stages) { acc = 0; acc_ph ^= 1u; }
             for (int ks = 0; ks < ksteps; ++ks) {
                 ptx::mbar_wait(&full[s], ph);
                 ptx::tc_fence_after();
@@ -219,7 +222,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     if (ksub == 2) issue_halo2<2>(d_tmem, a_lo, (uint32_t)(a_hi64 >> 32), b_lo, (uint32_t)(desc_hi >> 32), b_tap_step, idesc, ks == 0);
                     else           issue_halo2<4>(d_tmem, a_lo, (uint32_t)(a_hi64 >> 32), b_lo, (uint32_t)(desc_hi >> 32), b_tap_step, idesc, ks == 0);
                     ptx::umma_commit(&empty[s]);
-                    if (ks == ksteps - 1) ptx::umma_commit(&tmem_full[acc]);
+                    if (ks == ksteps - 1) ptx::umma_commit(&tmem_full[acc_cur]);
                 } else if (lane == 0) {
                     uint64_t ad0 = desc_hi | (uint64_t)((a_addr & 0x3FFFFu) >> 4);
                     uint64_t bd0;
@@ -243,7 +246,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         ad0 += a_tap_step; bd0 += b_sub_step;
                     }
                     ptx::umma_commit(&empty[s]);
-                    if (ks == ksteps - 1) ptx::umma_commit(&tmem_full[acc]);
+                    if (ks == ksteps - 1) ptx::umma_commit(&tmem_full[acc_cur]);
                 }
                 __syncwarp();
                 a_addr += (uint32_t)stage_bytes;
@@ -251,22 +254,24 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
         }
     } else {
-        // ===================== epilogue (warps 2..5) =====================
+        // ===================== epilogue: group 0 = warps 2..5 (even tiles), group 1 = warps 6..9 (odd tiles) =====
+        const uint32_t egroup = (uint32_t)(warp - 2) >> 2;
         const int q = warp & 3;                // TMEM lane quarter this warp may read
         const int m = q * 32 + lane;           // pixel inside the 8x16 patch
         const int py = m / p.tile_w, px = m % p.tile_w;
-        uint32_t tile_it = 0;
+        uint32_t tile_it = 0, acc = 0, acc_ph = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_it) {
+            const uint32_t acc_cur = acc, acc_ph_cur = acc_ph;
+            if (++acc == (uint32_t)p.acc_stages) { acc = 0; acc_ph ^= 1u; }
+            if ((tile_it & 1u) != egroup) continue;
             const int m_tile = tile / n_tiles, n_t = tile - m_tile * n_tiles;
             const int img = m_tile / (p.tiles_x * p.tiles_y);
             const int rem = m_tile - img * (p.tiles_x * p.tiles_y);
             const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
             const int x = tx * p.tile_w + px, y = ty * (128 / p.tile_w) + py;
-            const uint32_t acc = tile_it & 1u;
-            const uint32_t acc_ph = (tile_it >> 1) & 1u;
-            ptx::mbar_wait(&tmem_full[acc], acc_ph);
+            ptx::mbar_wait(&tmem_full[acc_cur], acc_ph_cur);
             ptx::tc_fence_after();
-            const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)p.n_tile;
+            const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc_cur * (uint32_t)p.n_tile;
             for (int c32 = 0; c32 < p.n_tile / 32; ++c32) {
                 uint32_t r[32];
                 ptx::tmem_ld32(t_addr + c32 * 32, r);
@@ -324,7 +329,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
             ptx::tc_fence_before();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+            if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc_cur]);
         }
     }
     ptx::tc_fence_before();

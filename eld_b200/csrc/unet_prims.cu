@@ -71,8 +71,10 @@ int launch_conv_gemm(eld_ctx* ctx, const GemmOp& op, cudaStream_t st)
     if (stages > 8) stages = 8;
     if (stages < 2) stages = 2;
     p.stages = stages;
+    p.acc_stages = 512 / p.n_tile;
+    if (p.acc_stages > kMaxAccStages) p.acc_stages = kMaxAccStages;
     int cols = 32;
-    while (cols < 2 * p.n_tile) cols *= 2;
+    while (cols < p.acc_stages * p.n_tile) cols *= 2;
     p.tmem_cols = cols;
 
     CUtensorMap tmA, tmB;
@@ -103,7 +105,7 @@ int launch_conv_gemm(eld_ctx* ctx, const GemmOp& op, cudaStream_t st)
         int rc = encode(ctx, &tmB, op.b, 2, dims, str, box, p.kc * 2);
         if (rc) return rc;
     }
-    const size_t smem = (size_t)stages * stage_bytes + (p.b_res ? b_total : 0) + 1024 /*align slack*/ + 256 /*barriers*/;
+    const size_t smem = (size_t)stages * stage_bytes + (p.b_res ? b_total : 0) + 1024 /*align slack*/ + 512 /*barriers*/;
     const int total_tiles = op.n_img * p.tiles_x * p.tiles_y * (p.n_total / p.n_tile);
     const int grid = total_tiles < ctx->num_sms ? total_tiles : ctx->num_sms;
     conv_umma_kernel<<<grid, kConvThreads, smem, st>>>(tmA, tmB, p);
