@@ -43,6 +43,7 @@ struct ConvGemmParams {
     int b_res;            // weights resident in smem (loaded once per CTA); requires n_total == n_tile
     int tile_w;           // 16 (8x16 patch) or 8 (16x8 patch, full-halo mode)
     int bo_mode;          // full-halo mode: 1 = put (start>>7)&7 into the descriptor's base_offset field
+    int l2_prefetch;      // full-halo mode: prefetch the A box this many tiles ahead into L2 (0 = off)
     int acc_stages;       // TMEM accumulator ring depth (2..8): acc_stages * n_tile <= 512 columns
 };
 
@@ -132,6 +133,18 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const int x0 = tx * p.tile_w, y0 = ty * tile_h;
                 const int n0 = n_t * p.n_tile;
                 if (p.halo == 2) {
+                    if (p.l2_prefetch > 0) {
+                        // pull the box of the tile `l2_prefetch` iterations ahead into L2 (DRAM-sourced TMA rows are
+                        // ~2x slower than L2 hits; the stream is perfectly predictable)
+                        const int ft = tile + p.l2_prefetch * (int)gridDim.x;
+                        if (ft < total_tiles) {
+                            const int fm = ft / n_tiles;
+                            const int fimg = fm / tiles_xy, frem = fm - fimg * tiles_xy;
+                            const int fty = frem / p.tiles_x, ftx = frem - fty * p.tiles_x;
+                            for (int kcI = 0; kcI < kchunks; ++kcI)
+                                ptx::tma_prefetch_5d(&tmA, p.a_c0 + kcI * p.kc, ftx * p.tile_w - 1, fty * tile_h - 1, fimg, 0);
+                        }
+                    }
                     int c = p.a_c0;
                     for (int kcI = 0; kcI < kchunks; ++kcI) {
                         ptx::mbar_wait(&empty[s], ph ^ 1u);

@@ -48,28 +48,13 @@ static FrameConsts make_consts(const eld_noise_params& p)
     return c;
 }
 
-// Noise for the 4 pixels of one quad of plane c.  l0 = linear index of the first pixel in the plane
-// (multiple of 4 on the aligned path), rown[k] = row-noise normal of pixel k's sensor row.
+// everything after the shot noise: read (g / Tukey-lambda), colour bias, row, quantisation, unscale, clip
 template <uint32_t MASK>
-__device__ __forceinline__ void form_quad(const FrameConsts& fc, const Stream& s, uint32_t rt_mask,
-                                          uint32_t c, uint32_t l0, const float rown[4], int clip01,
-                                          float y[4])
+__device__ __forceinline__ void post_shot(const FrameConsts& fc, const Stream& s, uint32_t rt_mask, uint32_t c,
+                                          uint32_t l0, const float rown[4], int clip01, float z[4])
 {
     const uint32_t mask = (MASK == kRuntimeMask) ? rt_mask : MASK;
     const uint32_t quad = l0 >> 2;
-    float z[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) z[k] = y[k] * fc.scale_in;
-
-    if (mask & ELD_NOISE_P) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) z[k] = poisson_px(s, l0 + k, c, z[k] * fc.invK) * fc.K;
-    } else if (mask & ELD_NOISE_p) {
-        float n[4];
-        quad_normals(s, quad, c, D_SHOT, n);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) z[k] = __fmaf_rn(n[k], fast_sqrt(fmaxf(fc.K * z[k], 1e-10f)), z[k]);
-    }
     if (mask & ELD_NOISE_g) {
         float n[4];
         quad_normals(s, quad, c, D_READ, n);
@@ -100,8 +85,35 @@ __device__ __forceinline__ void form_quad(const FrameConsts& fc, const Stream& s
     for (int k = 0; k < 4; ++k) {
         float o = z[k] * fc.scale_out;
         if (clip01) o = fminf(fmaxf(o, 0.0f), 1.0f);
-        y[k] = o;
+        z[k] = o;
     }
+}
+
+// Noise for the 4 pixels of one quad of plane c.  l0 = linear index of the first pixel in the plane
+// (multiple of 4 on the aligned path), rown[k] = row-noise normal of pixel k's sensor row.
+template <uint32_t MASK>
+__device__ __forceinline__ void form_quad(const FrameConsts& fc, const Stream& s, uint32_t rt_mask,
+                                          uint32_t c, uint32_t l0, const float rown[4], int clip01,
+                                          float y[4])
+{
+    const uint32_t mask = (MASK == kRuntimeMask) ? rt_mask : MASK;
+    const uint32_t quad = l0 >> 2;
+    float z[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) z[k] = y[k] * fc.scale_in;
+
+    if (mask & ELD_NOISE_P) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) z[k] = poisson_px(s, l0 + k, c, z[k] * fc.invK) * fc.K;
+    } else if (mask & ELD_NOISE_p) {
+        float n[4];
+        quad_normals(s, quad, c, D_SHOT, n);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) z[k] = __fmaf_rn(n[k], fast_sqrt(fmaxf(fc.K * z[k], 1e-10f)), z[k]);
+    }
+    post_shot<MASK>(fc, s, rt_mask, c, l0, rown, clip01, z);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) y[k] = z[k];
 }
 
 __device__ __forceinline__ float4 ldg_stream(const float4* p)
@@ -160,6 +172,126 @@ noise_packed_vec_kernel(const float* __restrict__ clean, float* __restrict__ noi
         const float rown[4] = { rr, rr, rr, rr };
         form_quad<MASK>(fc, s, L.mask, (uint32_t)c, t * 4u, rown, L.clip01, y);
         stg_stream(reinterpret_cast<float4*>(noisy + base + (size_t)c * plane), make_float4(y[0], y[1], y[2], y[3]));
+    }
+}
+
+// ---- packed in, aligned, Poisson shot noise: lane-persistent sampler ---------------------------------
+// A rejection sampler run "one pixel after the other" makes every lane wait for the slowest pixel of each
+// of its 16 positions.  Here each lane walks its OWN 16 pixels: an iteration performs one unit of work for
+// the lane's current pixel (one PTRS attempt, or up to four inversion search steps) and advances on
+// acceptance, so a warp iterates ~1.2 x 16 times instead of 16 x max-over-lanes.  The per-pixel arithmetic
+// and draw order are exactly poisson_px's (same values; oracle: eld_oracle_poisson_px).  The lane's 16 rates
+// and counts live in a private shared-memory column (dynamic indexing without local memory).
+template <uint32_t MASK>
+__global__ void __launch_bounds__(256)
+noise_packed_poisson_kernel(const float* __restrict__ clean, float* __restrict__ noisy,
+                            const __grid_constant__ NoiseLaunch L)
+{
+    __shared__ float s_buf[16][256];
+    const int f = blockIdx.y;
+    const uint32_t plane = (uint32_t)L.h * (uint32_t)L.w;
+    const uint32_t quads = plane >> 2;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= quads) return;
+    const uint32_t mask = (MASK == kRuntimeMask) ? L.mask : MASK;
+    const FrameConsts& fc = L.fr[f];
+    const Stream s = make_stream(L, f);
+    const size_t base = (size_t)f * 4 * plane + (size_t)t * 4;
+    const int tid = threadIdx.x;
+
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const float4 v = ldg_stream(reinterpret_cast<const float4*>(clean + base + (size_t)c * plane));
+        s_buf[c * 4 + 0][tid] = (v.x * fc.scale_in) * fc.invK;
+        s_buf[c * 4 + 1][tid] = (v.y * fc.scale_in) * fc.invK;
+        s_buf[c * 4 + 2][tid] = (v.z * fc.scale_in) * fc.invK;
+        s_buf[c * 4 + 3][tid] = (v.w * fc.scale_in) * fc.invK;
+    }
+
+    // ---- lane-persistent Poisson ----
+    int cur = 0;
+    bool fresh = true;
+    int mode = 0;                 // 1 = inversion, 2 = PTRS
+    float lam = 0.f, u = 0.f, pp = 0.f, F = 0.f, k = 0.f, pb = 0.f, pa = 0.f, invalpha = 0.f, vr = 0.f;
+    uint32_t att = 0, l = 0, c = 0;
+    uint4 x = make_uint4(0, 0, 0, 0);
+    while (cur < 16) {
+        bool done = false;
+        float result = 0.f;
+        if (fresh) {
+            fresh = false;
+            lam = s_buf[cur][tid];
+            l = t * 4u + (uint32_t)(cur & 3);
+            c = (uint32_t)cur >> 2;
+            if (!(lam > 0.0f)) { done = true; result = 0.f; mode = 0; }
+            else if (lam < 10.0f) {
+                x = draw(s, l, DOM_PIX, c, 0);
+                u = u24(x.x);
+                pp = __expf(-lam); F = pp; k = 0.f; mode = 1;
+            } else {
+                const float slam = fast_sqrt(lam);
+                pb = __fmaf_rn(2.53f, slam, 0.931f);
+                pa = __fmaf_rn(0.02483f, pb, -0.059f);
+                invalpha = 1.1239f + __fdividef(1.1328f, pb - 3.4f);
+                vr = 0.9277f - __fdividef(3.6224f, pb - 2.0f);
+                att = 0; mode = 2;
+            }
+        }
+        if (mode == 1) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (!done) {
+                    if (u > F) {
+                        k += 1.0f;
+                        pp = __fmul_rn(pp, __fdividef(lam, k));
+                        F = __fadd_rn(F, pp);
+                        if (pp < 1e-9f && k > lam) done = true;
+                    } else done = true;
+                }
+            }
+            result = k;
+        } else if (mode == 2) {
+            if ((att & 1u) == 0) x = draw(s, l, DOM_PIX, c, att >> 1);
+            const uint32_t xa = (att & 1u) ? x.z : x.x, xb = (att & 1u) ? x.w : x.y;
+            const float U = __fadd_rn(u_open(xa), -0.5f);
+            const float V = u01(xb);
+            const float us = __fadd_rn(0.5f, -fabsf(U));
+            const float kf = floorf(__fmaf_rn(__fadd_rn(__fdividef(2.0f * pa, us), pb), U, __fadd_rn(lam, 0.43f)));
+            result = kf;
+            if (us >= 0.07f && V <= vr) done = true;
+            else if (!(kf < 0.0f || (us < 0.013f && V > us))) {
+                const float lhs = __logf(__fdividef(V * invalpha, __fdividef(pa, us * us) + pb));
+                float rhs;
+                if (kf < 10.0f) {
+                    rhs = __fmaf_rn(kf, __logf(lam), -lam) - c_logfact[(int)kf];
+                } else {
+                    const float rk = fast_rcp(kf);
+                    rhs = __fmaf_rn(kf, log1pf((lam - kf) * rk), kf - lam)
+                          - 0.5f * __logf(6.2831853071795865f * kf)
+                          - rk * (1.0f / 12.0f) + rk * rk * rk * (1.0f / 360.0f);
+                }
+                if (lhs <= rhs) done = true;
+            }
+            ++att;
+            if (!done && att == 16u) { done = true; result = floorf(lam + 0.5f); }
+        }
+        if (done) {
+            s_buf[cur][tid] = result * fc.K;
+            ++cur;
+            fresh = true;
+        }
+    }
+
+    // ---- read noise / row / quant / unscale / clip / store ----
+    float r_even = 0.f, r_odd = 0.f;
+    if (mask & ELD_NOISE_R) row_normals(s, (t * 4u) / (uint32_t)L.w, r_even, r_odd);
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+        float z[4] = { s_buf[cc * 4 + 0][tid], s_buf[cc * 4 + 1][tid], s_buf[cc * 4 + 2][tid], s_buf[cc * 4 + 3][tid] };
+        const float rr = (cc < 2) ? r_even : r_odd;
+        const float rown[4] = { rr, rr, rr, rr };
+        post_shot<MASK>(fc, s, L.mask, (uint32_t)cc, t * 4u, rown, L.clip01, z);
+        stg_stream(reinterpret_cast<float4*>(noisy + base + (size_t)cc * plane), make_float4(z[0], z[1], z[2], z[3]));
     }
 }
 
@@ -322,7 +454,12 @@ noise_mosaic_generic_kernel(const void* __restrict__ mosaic, float* __restrict__
 template <uint32_t MASK>
 static void launch_packed_vec(dim3 grid, cudaStream_t st, const float* clean, float* noisy, const NoiseLaunch& L)
 {
-    noise_packed_vec_kernel<MASK><<<grid, 256, 0, st>>>(clean, noisy, L);
+    if (MASK != kRuntimeMask && (MASK & ELD_NOISE_P))
+        noise_packed_poisson_kernel<MASK><<<grid, 256, 0, st>>>(clean, noisy, L);
+    else if (MASK == kRuntimeMask && (L.mask & ELD_NOISE_P))
+        noise_packed_poisson_kernel<kRuntimeMask><<<grid, 256, 0, st>>>(clean, noisy, L);
+    else
+        noise_packed_vec_kernel<MASK><<<grid, 256, 0, st>>>(clean, noisy, L);
 }
 
 template <uint32_t MASK, int DT>
@@ -336,6 +473,7 @@ static void launch_mosaic_vec(dim3 grid, cudaStream_t st, const void* m, float* 
 #define ELD_FOR_EACH_MASK(X)                                                        \
     X(ELD_NOISE_g)                                                                  \
     X(ELD_NOISE_p | ELD_NOISE_g)                                                    \
+    X(ELD_NOISE_P)                                                                  \
     X(ELD_NOISE_P | ELD_NOISE_g)                                                    \
     X(ELD_NOISE_P | ELD_NOISE_G | ELD_NOISE_R | ELD_NOISE_U)                        \
     X(ELD_NOISE_P | ELD_NOISE_G | ELD_NOISE_B | ELD_NOISE_R | ELD_NOISE_U)

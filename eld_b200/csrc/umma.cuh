@@ -65,6 +65,13 @@ __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* m, uin
         ::"r"(smem_u32(dst)), "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
 }
 
+// L2 prefetch of a tensor box (no smem destination, no barrier)
+__device__ __forceinline__ void tma_prefetch_5d(const CUtensorMap* m, int c0, int c1, int c2, int c3, int c4)
+{
+    asm volatile("cp.async.bulk.prefetch.tensor.5d.L2.global [%0, {%1, %2, %3, %4, %5}];"
+                 ::"l"(m), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+
 // ---- TMEM -----------------------------------------------------------------------------------------
 // one full warp; writes the allocated base address (lane 0, column base) to *dst_smem
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols)

@@ -36,27 +36,54 @@ enum { I_C11 = 0, I_C12, I_C21, I_C22, I_C31, I_C32, I_C41, I_C42, I_C51, I_C52,
 struct PackEntry { unsigned long long src, dst_f, dst_d; int cout, cin, type; int pad; };
 struct PackTable { PackEntry e[kNumLayers]; int n; unsigned long long first_stage, first_dst; };
 
-// one launch packs every layer's fp32 master weights into both bf16 GEMM operands (fprop + dgrad)
+// one launch packs every layer's fp32 master weights into both bf16 GEMM operands (fprop + dgrad).
+// A block moves a (32 x 32 x taps) tile through shared memory so that reads are 1 KB runs and writes are
+// 64-byte runs in both destination layouts.
 __global__ void __launch_bounds__(256)
 pack_all_kernel(const float* __restrict__ params, __nv_bfloat16* __restrict__ packed, const __grid_constant__ PackTable T)
 {
+    __shared__ float tile[32][32 * 9 + 1];
     const PackEntry& e = T.e[blockIdx.y];
     const float* w = params + e.src;
-    const int ksz = e.type == L_CONV3 ? 9 : 4;
-    const size_t total = (size_t)e.cout * e.cin * ksz;
     __nv_bfloat16* of = packed + e.dst_f;
     __nv_bfloat16* od = packed + e.dst_d;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const float v = w[i];
-        const __nv_bfloat16 h = __float2bfloat16_rn(v);
-        if (e.type == L_CONV3) {          // w[co][ci][t]
-            const int t = i % 9, ci = (i / 9) % e.cin, co = i / ((size_t)9 * e.cin);
-            of[((size_t)co * 9 + t) * e.cin + ci] = h;
-            od[((size_t)ci * 9 + (8 - t)) * e.cout + co] = h;
-        } else {                          // wt[ci][co][s]
-            const int s = i % 4, co = (i / 4) % e.cout, ci = i / ((size_t)4 * e.cout);
-            of[((size_t)s * e.cout + co) * e.cin + ci] = h;
-            od[((size_t)ci * 4 + s) * e.cout + co] = h;
+    if (e.type == L_CONV3) {              // w[co][ci][t]
+        const int ct = e.cout / 32, it = e.cin / 32;
+        for (int tl = blockIdx.x; tl < ct * it; tl += gridDim.x) {
+            const int co0 = (tl / it) * 32, ci0 = (tl % it) * 32;
+            __syncthreads();
+            for (int i = threadIdx.x; i < 32 * 288; i += 256) {
+                const int co = i / 288, r = i - co * 288;              // r = ci*9 + t
+                tile[co][r] = w[((size_t)(co0 + co) * e.cin + ci0) * 9 + r];
+            }
+            __syncthreads();
+            for (int i = threadIdx.x; i < 32 * 288; i += 256) {       // fprop: [co][t][ci]
+                const int ci = i & 31, t = (i >> 5) % 9, co = i / 288;
+                of[((size_t)(co0 + co) * 9 + t) * e.cin + ci0 + ci] = __float2bfloat16_rn(tile[co][ci * 9 + t]);
+            }
+            for (int i = threadIdx.x; i < 32 * 288; i += 256) {       // dgrad: [ci][8-t][co]
+                const int co = i & 31, t = (i >> 5) % 9, ci = i / 288;
+                od[((size_t)(ci0 + ci) * 9 + (8 - t)) * e.cout + co0 + co] = __float2bfloat16_rn(tile[co][ci * 9 + t]);
+            }
+        }
+    } else {                              // deconv wt[ci][co][s]
+        const int ct = e.cout / 32, it = e.cin / 32;
+        for (int tl = blockIdx.x; tl < ct * it; tl += gridDim.x) {
+            const int ci0 = (tl / ct) * 32, co0 = (tl % ct) * 32;
+            __syncthreads();
+            for (int i = threadIdx.x; i < 32 * 128; i += 256) {
+                const int ci = i / 128, r = i - ci * 128;              // r = co*4 + s
+                tile[ci][r] = w[((size_t)(ci0 + ci) * e.cout + co0) * 4 + r];
+            }
+            __syncthreads();
+            for (int i = threadIdx.x; i < 32 * 128; i += 256) {       // fprop: [(s*cout + co)][ci]
+                const int ci = i & 31, co = (i >> 5) & 31, sp = i >> 10;
+                of[((size_t)sp * e.cout + co0 + co) * e.cin + ci0 + ci] = __float2bfloat16_rn(tile[ci][co * 4 + sp]);
+            }
+            for (int i = threadIdx.x; i < 32 * 128; i += 256) {       // dgrad: [ci][s][co]
+                const int co = i & 31, sp = (i >> 5) & 3, ci = i >> 7;
+                od[((size_t)(ci0 + ci) * 4 + sp) * e.cout + co0 + co] = __float2bfloat16_rn(tile[ci][co * 4 + sp]);
+            }
         }
     }
 }
@@ -339,13 +366,10 @@ struct Runner {
         op.q = dz; op.q_pitch = l.cout; op.q_c0 = 0; op.q_ch = l.cout;
         op.n_img = u->n; op.H = u->H >> lvl; op.W = u->W >> lvl;
         op.dw = u->gtmp + l.w_off; op.out_tco = 1;
+        op.db = grads + l.b_off;                     // bias gradient fused into the same launch
         const double px = (double)u->n * op.H * op.W;
-        {
-            Scope sc(u, st, l.name, "wgrad", 2.0 * px * l.cout * 9 * l.cin, px * 2 * (l.cin + l.cout) + 36.0 * l.cin * l.cout);
-            TRY(launch_wgrad(ctx(), op, st));
-        }
-        Scope sc(u, st, l.name, "bgrad", 0.0, px * 2 * l.cout);
-        return launch_colsum(ctx(), dz, l.cout, 0, l.cout, (size_t)u->n * op.H * op.W, grads + l.b_off, st);
+        Scope sc(u, st, l.name, "wgrad", 2.0 * px * l.cout * 9 * l.cin, px * 2 * (l.cin + l.cout) + 36.0 * l.cin * l.cout);
+        return launch_wgrad(ctx(), op, st);
     }
     int deconv_wgrad(int li, const void* x, const void* dy, int dyp, float* grads, int lvl_in) const
     {
@@ -473,11 +497,8 @@ struct Runner {
             op.mode = WG_CONV; op.p = U->x32; op.p_pitch = 32; op.p_c0 = 0; op.p_ch = 32;
             op.q = U->dz1_1; op.q_pitch = 32; op.q_c0 = 0; op.q_ch = 32;
             op.n_img = U->n; op.H = U->H; op.W = U->W; op.dw = U->gtmp + U->n_params; op.out_tco = 1;
+            op.db = g + U->L[I_C11].b_off;
             TRY(launch_wgrad(ctx(), op, st));
-        }
-        {
-            Scope sc(u, st, "conv1_1", "bgrad", 0.0, px * 64);
-            TRY(launch_colsum(ctx(), U->dz1_1, 32, 0, 32, (size_t)px, g + U->L[I_C11].b_off, st));
         }
         {
             Scope sc(u, st, "weights", "gperm", 0.0, (double)U->n_params * 8);

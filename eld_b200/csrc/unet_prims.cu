@@ -71,6 +71,7 @@ int launch_conv_gemm(eld_ctx* ctx, const GemmOp& op, cudaStream_t st)
     if (stages > 8) stages = 8;
     if (stages < 2) stages = 2;
     p.stages = stages;
+    p.l2_prefetch = getenv("ELD_CONV_PREFETCH") ? atoi(getenv("ELD_CONV_PREFETCH")) : 0;
     p.acc_stages = 512 / p.n_tile;
     if (p.acc_stages > kMaxAccStages) p.acc_stages = kMaxAccStages;
     int cols = 32;
@@ -160,6 +161,7 @@ static int launch_wgrad_conv(eld_ctx* ctx, const WgradOp& op, cudaStream_t st)
     p.ksplit = ksplit;
     p.dw = op.dw;
     p.out_tco = op.out_tco;
+    p.db = op.db;
     CUtensorMap tmP, tmQ;
     const cuuint64_t eb = 2;
     {
@@ -190,6 +192,7 @@ int launch_wgrad(eld_ctx* ctx, const WgradOp& op, cudaStream_t st)
     if (op.mode == WG_CONV && op.H % 8 == 0 && op.W % 8 == 0 && (op.p_ch == 32 || op.p_ch == 64 || op.p_ch % 128 == 0) &&
         op.q_ch % 32 == 0 && !getenv("ELD_WGRAD_V1"))
         return launch_wgrad_conv(ctx, op, st);
+    ELD_REQUIRE(op.db == nullptr, "wgrad tile: fused bias gradient needs the full-halo conv generation");
     ELD_REQUIRE(op.H % 4 == 0 && op.W % 16 == 0, "wgrad tile: H=%d must be a multiple of 4 and W=%d of 16", op.H, op.W);
     ELD_REQUIRE(op.p_ch % 32 == 0 && op.q_ch % 32 == 0, "wgrad tile: channel counts must be multiples of 32");
     WgradParams p{};

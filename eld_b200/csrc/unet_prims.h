@@ -35,6 +35,7 @@ struct WgradOp {
     int n_img, H, W;     // pixel grid of the reduction (deconv: coarse)
     float* dw;           // f32, PyTorch layout, accumulated into (zero it first)
     int out_tco;         // conv only: 1 = dw is the [tap][ci][co] staging layout (vector red.add), see wgrad_conv.cuh
+    float* db;           // conv (full-halo generation) only: optional fused bias gradient, db[co] += sum_pixels dz
 };
 int init_gemm_kernels(eld_ctx* ctx);   // opt in to large dynamic smem (call once, outside graph capture)
 int launch_wgrad(eld_ctx* ctx, const WgradOp& op, cudaStream_t st);

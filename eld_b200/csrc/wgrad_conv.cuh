@@ -31,6 +31,8 @@ struct Wgrad2Params {
     int ksplit, stages, tmem_cols;
     float* dw;
     int out_tco;                // 0: dw is OIHW [co][ci][3][3], scalar red.add; 1: dw is [tap][ci][co], 16-byte vector red.add
+    float* db;                  // optional bias gradient: db[co] += sum over pixels of dZ (column sums of the Q tiles,
+                                // computed by the otherwise idle epilogue warps of the cp == 0, grp == 0 CTAs)
 };
 
 constexpr int kWg2Threads = 192;
@@ -71,10 +73,11 @@ wgrad_conv_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant
     const int ch_begin = ks * per;
     const int nchunks = max(0, min(total_chunks, ch_begin + per) - ch_begin);
 
+    const bool do_bias = p.db != nullptr && cp == 0 && grp == 0;
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&tmP);
         ptx::prefetch_tmap(&tmQ);
-        for (int s = 0; s < p.stages; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
+        for (int s = 0; s < p.stages; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], do_bias ? 5 : 1); }
         ptx::mbar_init(acc_full, 1);
         ptx::fence_barrier_init();
     }
@@ -167,9 +170,40 @@ wgrad_conv_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant
             if (++s == p.stages) { s = 0; ph ^= 1u; st_addr = smem_base; }
         }
     } else if (nchunks > 0) {
-        // ===================== epilogue: TMEM -> red.add into dW (OIHW) =====================
         const int q = warp & 3;
         const int r = q * 32 + lane;                      // accumulator row
+        if (do_bias) {
+            // ---- bias gradient while the MMAs run: column sums of the dZ (Q) tile of every chunk ----
+            const int et = (warp - 2) * 32 + lane;        // 0..127
+            const int words = p.n_tile >> 1;              // 32-bit words (channel pairs) per pixel row: 16..128
+            const int rgroups = 128 / words;              // threads sharing a word split the 64 pixel rows
+            const int wd = et % words, rg = et / words;
+            const int wpb = p.q_box_ch >> 1;              // words per row of one box
+            const int bx = wd / wpb, wb = wd - bx * wpb;
+            const uint32_t col_byte = (uint32_t)(wb & 3) * 4u;
+            const uint32_t chunk16 = (uint32_t)wb >> 2;
+            float s0 = 0.f, s1 = 0.f;
+            int s = 0;
+            uint32_t ph = 0;
+            const uint8_t* qb = smem + p_bytes + (size_t)bx * q_box;
+            for (int i = 0; i < nchunks; ++i) {
+                ptx::mbar_wait(&full[s], ph);
+                const uint8_t* base = qb + (size_t)s * stage_bytes;
+                for (int row = rg; row < 64; row += rgroups) {
+                    const uint32_t swz = (rb_q == 128) ? (uint32_t)(row & 7) : (uint32_t)((row >> 1) & 3);
+                    const uint32_t v = *reinterpret_cast<const uint32_t*>(base + row * rb_q + ((chunk16 ^ swz) << 4) + col_byte);
+                    s0 += __uint_as_float(v << 16);
+                    s1 += __uint_as_float(v & 0xFFFF0000u);
+                }
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&empty[s]);
+                if (++s == p.stages) { s = 0; ph ^= 1u; }
+            }
+            const int co = nt * p.n_tile + 2 * wd;
+            atomicAdd(p.db + co, s0);
+            atomicAdd(p.db + co + 1, s1);
+        }
+        // ===================== epilogue: TMEM -> red.add into dW =====================
         ptx::mbar_wait(acc_full, 0);
         ptx::tc_fence_after();
         for (int g = 0; g < g_cnt; ++g) {
