@@ -47,6 +47,25 @@ struct ConvGemmParams {
     int acc_stages;       // TMEM accumulator ring depth (2..8): acc_stages * n_tile <= 512 columns
 };
 
+// Two tiles at once: consecutive MMAs alternate between two accumulators, so an N = 32 tile's chain of
+// 18 dependent accumulates no longer runs at MMA latency (measured: ~100 cycles per dependent N=32 MMA).
+template <int KSUB>
+__device__ __forceinline__ void issue_halo2_pair(uint32_t d0, uint32_t d1, uint32_t a0_lo, uint32_t a1_lo, uint32_t a_hi,
+                                                 uint32_t b_lo, uint32_t b_hi, uint32_t b_tap_step, uint32_t idesc)
+{
+    constexpr uint32_t kRow = (uint32_t)(32 * KSUB) >> 4;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+        const uint32_t off = (uint32_t)((tap / 3) * 10 + (tap % 3)) * kRow;
+#pragma unroll
+        for (int k = 0; k < KSUB; ++k) {
+            ptx::umma_bf16_lohi(d0, a0_lo + off + 2u * k, a_hi, b_lo + 2u * k, b_hi, idesc, !(tap == 0 && k == 0));
+            ptx::umma_bf16_lohi(d1, a1_lo + off + 2u * k, a_hi, b_lo + 2u * k, b_hi, idesc, !(tap == 0 && k == 0));
+        }
+        b_lo += b_tap_step;
+    }
+}
+
 constexpr int kConvThreads = 320;   // warp 0 TMA, warp 1 MMA, warps 2-5 and 6-9: two epilogue groups (alternate tiles)
 constexpr int kMaxAccStages = 8;
 
@@ -217,7 +236,42 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         uint32_t a_addr = stage_base;
         if (p.b_res) { ptx::mbar_wait(bres_full, 0); ptx::tc_fence_after(); }
         uint32_t acc = 0, acc_ph = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_it) {
+        int tile = blockIdx.x;
+        if (p.halo == 2 && kchunks == 1) {
+            // pairs of tiles (one stage each), interleaved issue
+            const uint64_t a_hi64 = ptx::make_smem_desc(0, 16, 10u * row_bytes, layout);
+            const uint32_t a_hi = (uint32_t)(a_hi64 >> 32);
+            const uint32_t b_lo = (uint32_t)desc_hi | ((bres_base & 0x3FFFFu) >> 4);
+            for (; tile + (int)gridDim.x < total_tiles; tile += 2 * gridDim.x, tile_it += 2) {
+                const uint32_t acc0 = acc, ph0 = acc_ph;
+                if (++acc == (uint32_t)p.acc_stages) { acc = 0; acc_ph ^= 1u; }
+                const uint32_t acc1 = acc, ph1 = acc_ph;
+                if (++acc == (uint32_t)p.acc_stages) { acc = 0; acc_ph ^= 1u; }
+                ptx::mbar_wait(&tmem_empty[acc0], ph0 ^ 1u);
+                ptx::mbar_wait(&tmem_empty[acc1], ph1 ^ 1u);
+                const int s0 = s; const uint32_t sph0 = ph; const uint32_t a0 = a_addr;
+                a_addr += (uint32_t)stage_bytes;
+                if (++s == p.stages) { s = 0; ph ^= 1u; a_addr = stage_base; }
+                const int s1 = s; const uint32_t sph1 = ph; const uint32_t a1 = a_addr;
+                a_addr += (uint32_t)stage_bytes;
+                if (++s == p.stages) { s = 0; ph ^= 1u; a_addr = stage_base; }
+                ptx::mbar_wait(&full[s0], sph0);
+                ptx::mbar_wait(&full[s1], sph1);
+                ptx::tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t d0 = tmem_base + acc0 * (uint32_t)p.n_tile, d1 = tmem_base + acc1 * (uint32_t)p.n_tile;
+                    const uint32_t a0_lo = (uint32_t)a_hi64 | ((a0 & 0x3FFFFu) >> 4), a1_lo = (uint32_t)a_hi64 | ((a1 & 0x3FFFFu) >> 4);
+                    if (ksub == 2) issue_halo2_pair<2>(d0, d1, a0_lo, a1_lo, a_hi, b_lo, (uint32_t)(desc_hi >> 32), b_step, idesc);
+                    else           issue_halo2_pair<4>(d0, d1, a0_lo, a1_lo, a_hi, b_lo, (uint32_t)(desc_hi >> 32), b_step, idesc);
+                    ptx::umma_commit(&empty[s0]);
+                    ptx::umma_commit(&empty[s1]);
+                    ptx::umma_commit(&tmem_full[acc0]);
+                    ptx::umma_commit(&tmem_full[acc1]);
+                }
+                __syncwarp();
+            }
+        }
+        for (; tile < total_tiles; tile += gridDim.x, ++tile_it) {
             ptx::mbar_wait(&tmem_empty[acc], acc_ph ^ 1u);
             ptx::tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.n_tile;
