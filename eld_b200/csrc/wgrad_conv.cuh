@@ -147,19 +147,17 @@ wgrad_conv_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant
             if (lane == 0) {
                 const uint32_t a_st = (st_addr & 0x3FFFFu) >> 4;
                 const uint32_t b_lo0 = b_lo_c + (((st_addr + (uint32_t)p_bytes) & 0x3FFFFu) >> 4);
-                // k outermost: consecutive MMAs target DIFFERENT accumulators, so the tensor pipe never waits for
-                // the previous (dependent) accumulate of the same TMEM tile
+                // g outermost (4 consecutive K steps per accumulator): measured faster than k-outermost on B200
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
+                for (int g = 0; g < kWg2MaxG; ++g) {
+                    if (g < g_cnt) {
+                        const uint32_t d_tmem = tmem_base + (uint32_t)(g * p.n_tile);
+                        const uint32_t a_lo0 = a_lo_c[g] + a_st;
+                        if (i == 0) ptx::umma_bf16_lohi(d_tmem, a_lo0, a_hi, b_lo0, b_hi, idesc, false);
+                        else        ptx::umma_bf16_lohi(d_tmem, a_lo0, a_hi, b_lo0, b_hi, idesc, true);
 #pragma unroll
-                    for (int g = 0; g < kWg2MaxG; ++g) {
-                        if (g < g_cnt) {
-                            const uint32_t d_tmem = tmem_base + (uint32_t)(g * p.n_tile);
-                            const uint32_t a_lo = a_lo_c[g] + a_st + k * a_kstep;
-                            const uint32_t b_lo = b_lo0 + k * b_kstep;
-                            if (k == 0 && i == 0) ptx::umma_bf16_lohi(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, false);
-                            else                  ptx::umma_bf16_lohi(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, true);
-                        }
+                        for (int k = 1; k < 4; ++k)
+                            ptx::umma_bf16_lohi(d_tmem, a_lo0 + k * a_kstep, a_hi, b_lo0 + k * b_kstep, b_hi, idesc, true);
                     }
                 }
                 ptx::umma_commit(&empty[s]);
