@@ -20,7 +20,8 @@ constexpr uint32_t kRuntimeMask = 0xFFFFFFFFu;
 struct FrameConsts {
     float K, invK, g, Gs, Gl, Rs, q, scale_in, scale_out;
     float bias[4];
-    float pad[3];
+    float Kbm, gbm;     // K * 2 ln 2 and g * sqrt(2 ln 2): Box-Muller's constant folded into the sigmas
+    float pad[1];
 };  // 64 bytes
 
 struct NoiseLaunch {
@@ -38,6 +39,8 @@ static FrameConsts make_consts(const eld_noise_params& p)
     c.K = p.K;
     c.invK = 1.0f / p.K;
     c.g = fmaxf(p.g_scale, 1e-10f);
+    c.Kbm = p.K * 1.3862943611198906f;
+    c.gbm = c.g * 1.1774100225154747f;
     c.Gs = p.G_scale;
     c.Gl = p.G_lambda;
     c.Rs = p.R_scale;
@@ -49,7 +52,7 @@ static FrameConsts make_consts(const eld_noise_params& p)
 }
 
 // everything after the shot noise: read (g / Tukey-lambda), colour bias, row, quantisation, unscale, clip
-template <uint32_t MASK>
+template <uint32_t MASK, int CLIP = -1>
 __device__ __forceinline__ void post_shot(const FrameConsts& fc, const Stream& s, uint32_t rt_mask, uint32_t c,
                                           uint32_t l0, const float rown[4], int clip01, float z[4])
 {
@@ -57,9 +60,9 @@ __device__ __forceinline__ void post_shot(const FrameConsts& fc, const Stream& s
     const uint32_t quad = l0 >> 2;
     if (mask & ELD_NOISE_g) {
         float n[4];
-        quad_normals(s, quad, c, D_READ, n);
+        quad_normals_unscaled(s, quad, c, D_READ, n);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) z[k] = __fmaf_rn(n[k], fc.g, z[k]);
+        for (int k = 0; k < 4; ++k) z[k] = __fmaf_rn(n[k], fc.gbm, z[k]);
     }
     if (mask & ELD_NOISE_G) {
         const uint4 x = draw(s, quad, DOM_QUAD, c, D_TL);
@@ -81,17 +84,22 @@ __device__ __forceinline__ void post_shot(const FrameConsts& fc, const Stream& s
 #pragma unroll
         for (int k = 0; k < 4; ++k) z[k] = __fmaf_rn(u_open(xs[k]) - 0.5f, fc.q, z[k]);
     }
+    if (CLIP == 1 || (CLIP < 0 && clip01)) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        float o = z[k] * fc.scale_out;
-        if (clip01) o = fminf(fmaxf(o, 0.0f), 1.0f);
-        z[k] = o;
+        for (int k = 0; k < 4; ++k) {   // unscale and clip to [0,1] in one instruction (FMUL.SAT)
+            float o;
+            asm("mul.sat.f32 %0, %1, %2;" : "=f"(o) : "f"(z[k]), "f"(fc.scale_out));
+            z[k] = o;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) z[k] = z[k] * fc.scale_out;
     }
 }
 
 // Noise for the 4 pixels of one quad of plane c.  l0 = linear index of the first pixel in the plane
 // (multiple of 4 on the aligned path), rown[k] = row-noise normal of pixel k's sensor row.
-template <uint32_t MASK>
+template <uint32_t MASK, int CLIP = -1>
 __device__ __forceinline__ void form_quad(const FrameConsts& fc, const Stream& s, uint32_t rt_mask,
                                           uint32_t c, uint32_t l0, const float rown[4], int clip01,
                                           float y[4])
@@ -107,11 +115,11 @@ __device__ __forceinline__ void form_quad(const FrameConsts& fc, const Stream& s
         for (int k = 0; k < 4; ++k) z[k] = poisson_px(s, l0 + k, c, z[k] * fc.invK) * fc.K;
     } else if (mask & ELD_NOISE_p) {
         float n[4];
-        quad_normals(s, quad, c, D_SHOT, n);
+        quad_normals_unscaled(s, quad, c, D_SHOT, n);     // n * sqrt(2 ln 2) is N(0,1): the factor lives in Kbm
 #pragma unroll
-        for (int k = 0; k < 4; ++k) z[k] = __fmaf_rn(n[k], fast_sqrt(fmaxf(fc.K * z[k], 1e-10f)), z[k]);
+        for (int k = 0; k < 4; ++k) z[k] = __fmaf_rn(n[k], fast_sqrt(fmaxf(fc.Kbm * z[k], 1.3862944e-10f)), z[k]);
     }
-    post_shot<MASK>(fc, s, rt_mask, c, l0, rown, clip01, z);
+    post_shot<MASK, CLIP>(fc, s, rt_mask, c, l0, rown, clip01, z);
 #pragma unroll
     for (int k = 0; k < 4; ++k) y[k] = z[k];
 }
@@ -143,7 +151,7 @@ __device__ __forceinline__ void row_normals(const Stream& s, uint32_t i, float& 
 
 // ---- packed in, aligned: w % 4 == 0 and 16-byte aligned planes ---------------------------------
 // Gaussian-only masks are issue/latency bound on MUFU chains: cap registers at 32 so 8 blocks (64 warps) fit.
-template <uint32_t MASK>
+template <uint32_t MASK, int CLIP>
 __global__ void __launch_bounds__(256, (MASK != kRuntimeMask && !(MASK & (ELD_NOISE_P | ELD_NOISE_G))) ? 8 : 1)
 noise_packed_vec_kernel(const float* __restrict__ clean, float* __restrict__ noisy,
                         const __grid_constant__ NoiseLaunch L)
@@ -170,7 +178,7 @@ noise_packed_vec_kernel(const float* __restrict__ clean, float* __restrict__ noi
         float y[4] = { v[c].x, v[c].y, v[c].z, v[c].w };
         const float rr = (c < 2) ? r_even : r_odd;
         const float rown[4] = { rr, rr, rr, rr };
-        form_quad<MASK>(fc, s, L.mask, (uint32_t)c, t * 4u, rown, L.clip01, y);
+        form_quad<MASK, CLIP>(fc, s, L.mask, (uint32_t)c, t * 4u, rown, L.clip01, y);
         stg_stream(reinterpret_cast<float4*>(noisy + base + (size_t)c * plane), make_float4(y[0], y[1], y[2], y[3]));
     }
 }
@@ -458,8 +466,10 @@ static void launch_packed_vec(dim3 grid, cudaStream_t st, const float* clean, fl
         noise_packed_poisson_kernel<MASK><<<grid, 256, 0, st>>>(clean, noisy, L);
     else if (MASK == kRuntimeMask && (L.mask & ELD_NOISE_P))
         noise_packed_poisson_kernel<kRuntimeMask><<<grid, 256, 0, st>>>(clean, noisy, L);
+    else if (L.clip01)
+        noise_packed_vec_kernel<MASK, 1><<<grid, 256, 0, st>>>(clean, noisy, L);
     else
-        noise_packed_vec_kernel<MASK><<<grid, 256, 0, st>>>(clean, noisy, L);
+        noise_packed_vec_kernel<MASK, 0><<<grid, 256, 0, st>>>(clean, noisy, L);
 }
 
 template <uint32_t MASK, int DT>

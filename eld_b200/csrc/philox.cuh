@@ -88,10 +88,29 @@ __device__ __forceinline__ float fast_cos(float x)
 __device__ __forceinline__ void box_muller(uint32_t xa, uint32_t xb, float& n_cos, float& n_sin)
 {
     const float u = u01(xa);
-    const float th = __fmaf_rn(u01(xb), 6.2831853071795865f, -3.1415926535897932f);
+    // theta = 2*pi*u01(xb) - pi folded into ONE fma on the raw word: (xb + 0.5) * 2*pi*2^-32 - pi
+    const float th = __fmaf_rn(__uint2float_rn(xb), 1.4629180792671596e-09f, -3.1415926521267655f);
     const float r = fast_sqrt(-1.3862943611198906f * fast_lg2(u));   // sqrt(-2 ln u); u >= 2^-33: no denormals
     n_cos = r * fast_cos(th);
     n_sin = r * fast_sin(th);
+}
+
+// Box-Muller WITHOUT the sqrt(2 ln 2) factor: returns n / 1.1774100 (the caller folds the constant into
+// the sigma it multiplies with - one FMUL less per pair).  sqrt(-lg2 u), u in (0,1].
+constexpr float kBmScale = 1.1774100225154747f;      // sqrt(2 ln 2)
+__device__ __forceinline__ void box_muller_unscaled(uint32_t xa, uint32_t xb, float& n_cos, float& n_sin)
+{
+    const float u = u01(xa);
+    const float th = __fmaf_rn(__uint2float_rn(xb), 1.4629180792671596e-09f, -3.1415926521267655f);
+    const float r = fast_sqrt(-fast_lg2(u));
+    n_cos = r * fast_cos(th);
+    n_sin = r * fast_sin(th);
+}
+__device__ __forceinline__ void quad_normals_unscaled(const Stream& s, uint32_t quad, uint32_t c, uint32_t d, float n[4])
+{
+    const uint4 x = draw(s, quad, DOM_QUAD, c, d);
+    box_muller_unscaled(x.x, x.y, n[0], n[1]);
+    box_muller_unscaled(x.z, x.w, n[2], n[3]);
 }
 
 // four normals for the four pixels of a quad from one Philox call

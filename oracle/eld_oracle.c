@@ -88,7 +88,8 @@ static float u24(uint32_t x) { return (float)(x >> 8) * 0x1p-24f; }
 static void box_muller(uint32_t xa, uint32_t xb, float* n_cos, float* n_sin)
 {
     float u = u01(xa);
-    float th = fmaf(u01(xb), 6.2831853071795865f, -3.1415926535897932f);
+    /* theta = 2*pi*(xb + 0.5)*2^-32 - pi as one fma on the raw word (same constants as the kernel) */
+    float th = fmaf((float)xb, 1.4629180792671596e-09f, -3.1415926521267655f);
     float r = sqrtf(-2.0f * logf(u));
     *n_cos = r * cosf(th);
     *n_sin = r * sinf(th);
