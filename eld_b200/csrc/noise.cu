@@ -114,10 +114,16 @@ __device__ __forceinline__ void form_quad(const FrameConsts& fc, const Stream& s
 #pragma unroll
         for (int k = 0; k < 4; ++k) z[k] = poisson_px(s, l0 + k, c, z[k] * fc.invK) * fc.K;
     } else if (mask & ELD_NOISE_p) {
-        float n[4];
-        quad_normals_unscaled(s, quad, c, D_SHOT, n);     // n * sqrt(2 ln 2) is N(0,1): the factor lives in Kbm
-#pragma unroll
-        for (int k = 0; k < 4; ++k) z[k] = __fmaf_rn(n[k], fast_sqrt(fmaxf(fc.Kbm * z[k], 1.3862944e-10f)), z[k]);
+        // z += N(0,1) * sqrt(max(K z, 1e-10)) with N = sqrt(-2 ln u) * trig: both square roots merged into one
+        // MUFU per pixel: trig * sqrt( (-lg2 u) * max(2 ln2 * K z, 2 ln2 * 1e-10) )
+        const uint4 x = draw(s, quad, DOM_QUAD, c, D_SHOT);
+        float l01, c01, s01, l23, c23, s23;
+        box_muller_parts(x.x, x.y, l01, c01, s01);
+        box_muller_parts(x.z, x.w, l23, c23, s23);
+        z[0] = __fmaf_rn(c01, fast_sqrt(l01 * fmaxf(fc.Kbm * z[0], 1.3862944e-10f)), z[0]);
+        z[1] = __fmaf_rn(s01, fast_sqrt(l01 * fmaxf(fc.Kbm * z[1], 1.3862944e-10f)), z[1]);
+        z[2] = __fmaf_rn(c23, fast_sqrt(l23 * fmaxf(fc.Kbm * z[2], 1.3862944e-10f)), z[2]);
+        z[3] = __fmaf_rn(s23, fast_sqrt(l23 * fmaxf(fc.Kbm * z[3], 1.3862944e-10f)), z[3]);
     }
     post_shot<MASK, CLIP>(fc, s, rt_mask, c, l0, rown, clip01, z);
 #pragma unroll

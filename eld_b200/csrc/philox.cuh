@@ -84,12 +84,21 @@ __device__ __forceinline__ float fast_cos(float x)
     return r;
 }
 
-// Box-Muller: (xa, xb) -> two N(0,1).  theta in (-pi, pi] keeps MUFU.SIN/COS in its accurate range.
+// Box-Muller inputs without an int->float conversion (those issue on the XU pipe next to MUFU, which is the
+// busiest pipe of this kernel): the top 23 bits become the mantissa of a float in [1,2).
+//   bm_u(x)     = f - (1 - 2^-24)      in [2^-24, 1)   exact
+//   bm_theta(x) = 2*pi*f - 3*pi        in [-pi, pi)    keeps MUFU.SIN/COS in their accurate range
+__device__ __forceinline__ float bm_u(uint32_t x) { return __fadd_rn(__uint_as_float(0x3F800000u | (x >> 9)), -0.99999994f); }
+__device__ __forceinline__ float bm_theta(uint32_t x)
+{
+    return __fmaf_rn(__uint_as_float(0x3F800000u | (x >> 9)), 6.2831853071795865f, -9.4247779607693797f);
+}
+
+// Box-Muller: (xa, xb) -> two N(0,1).
 __device__ __forceinline__ void box_muller(uint32_t xa, uint32_t xb, float& n_cos, float& n_sin)
 {
-    const float u = u01(xa);
-    // theta = 2*pi*u01(xb) - pi folded into ONE fma on the raw word: (xb + 0.5) * 2*pi*2^-32 - pi
-    const float th = __fmaf_rn(__uint2float_rn(xb), 1.4629180792671596e-09f, -3.1415926521267655f);
+    const float u = bm_u(xa);
+    const float th = bm_theta(xb);
     const float r = fast_sqrt(-1.3862943611198906f * fast_lg2(u));   // sqrt(-2 ln u); u >= 2^-33: no denormals
     n_cos = r * fast_cos(th);
     n_sin = r * fast_sin(th);
@@ -100,11 +109,19 @@ __device__ __forceinline__ void box_muller(uint32_t xa, uint32_t xb, float& n_co
 constexpr float kBmScale = 1.1774100225154747f;      // sqrt(2 ln 2)
 __device__ __forceinline__ void box_muller_unscaled(uint32_t xa, uint32_t xb, float& n_cos, float& n_sin)
 {
-    const float u = u01(xa);
-    const float th = __fmaf_rn(__uint2float_rn(xb), 1.4629180792671596e-09f, -3.1415926521267655f);
+    const float u = bm_u(xa);
+    const float th = bm_theta(xb);
     const float r = fast_sqrt(-fast_lg2(u));
     n_cos = r * fast_cos(th);
     n_sin = r * fast_sin(th);
+}
+// the pair's radius^2 / (2 ln 2) and its two directions, for callers that fold sigma^2 under the sqrt
+__device__ __forceinline__ void box_muller_parts(uint32_t xa, uint32_t xb, float& neg_lg2u, float& c, float& sn)
+{
+    neg_lg2u = -fast_lg2(bm_u(xa));
+    const float th = bm_theta(xb);
+    c = fast_cos(th);
+    sn = fast_sin(th);
 }
 __device__ __forceinline__ void quad_normals_unscaled(const Stream& s, uint32_t quad, uint32_t c, uint32_t d, float n[4])
 {

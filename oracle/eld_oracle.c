@@ -87,9 +87,12 @@ static float u24(uint32_t x) { return (float)(x >> 8) * 0x1p-24f; }
 /* Box-Muller on one (xa, xb) pair -> two independent N(0,1) */
 static void box_muller(uint32_t xa, uint32_t xb, float* n_cos, float* n_sin)
 {
-    float u = u01(xa);
-    /* theta = 2*pi*(xb + 0.5)*2^-32 - pi as one fma on the raw word (same constants as the kernel) */
-    float th = fmaf((float)xb, 1.4629180792671596e-09f, -3.1415926521267655f);
+    /* top 23 bits -> mantissa of f in [1,2):  u = f - (1 - 2^-24) in [2^-24, 1),  theta = 2*pi*f - 3*pi in [-pi, pi) */
+    union { uint32_t i; float f; } a, b;
+    a.i = 0x3F800000u | (xa >> 9);
+    b.i = 0x3F800000u | (xb >> 9);
+    float u = a.f - 0.99999994f;
+    float th = fmaf(b.f, 6.2831853071795865f, -9.4247779607693797f);
     float r = sqrtf(-2.0f * logf(u));
     *n_cos = r * cosf(th);
     *n_sin = r * sinf(th);
