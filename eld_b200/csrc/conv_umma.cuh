@@ -43,6 +43,7 @@ struct ConvGemmParams {
     int b_res;            // weights resident in smem (loaded once per CTA); requires n_total == n_tile
     int tile_w;           // 16 (8x16 patch) or 8 (16x8 patch, full-halo mode)
     int bo_mode;          // full-halo mode: 1 = put (start>>7)&7 into the descriptor's base_offset field
+    int b_stages;         // halo == 3: depth of the separate weight ring
     int l2_prefetch;      // full-halo mode: prefetch the A box this many tiles ahead into L2 (0 = off)
     int acc_stages;       // TMEM accumulator ring depth (2..8): acc_stages * n_tile <= 512 columns
 };
@@ -97,25 +98,32 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int row_bytes = p.kc * 2;
     // halo == 2 ("full halo"): ONE box {kc, 10, 18} per channel chunk; all nine taps are views of it
     // (start shifted by (kh*10 + kw) pixel rows, 8-row groups 10 rows apart) - needs b_res.
-    const int a_bytes = p.halo == 2 ? ((180 * row_bytes + 1023) & ~1023) : (p.halo ? 160 : 128) * row_bytes;
+    const int a_bytes = p.halo >= 2 ? ((180 * row_bytes + 1023) & ~1023) : (p.halo ? 160 : 128) * row_bytes;
     const int b_bytes = p.n_tile * row_bytes;                       // one tap, one channel chunk
     const int kchunks = p.cin / p.kc;
-    const int b_per_stage = p.b_res ? 0 : (p.halo ? 3 : 1);
+    // halo == 3: full-halo activations (one {kc,10,18} box per channel chunk, ring of `stages`) and weights
+    // STREAMED through their own ring of `b_stages` one-tap tiles - 180 + 9*n_tile TMA rows per chunk instead
+    // of 9*(128 + n_tile).
+    const int b_per_stage = (p.b_res || p.halo == 3) ? 0 : (p.halo ? 3 : 1);
     const int stage_bytes = a_bytes + b_per_stage * b_bytes;
     const int bres_bytes = p.b_res ? p.taps * kchunks * b_bytes : 0;
     uint8_t* stage0 = smem + bres_bytes;
-    uint64_t* full = reinterpret_cast<uint64_t*>(stage0 + (size_t)p.stages * stage_bytes);
+    uint8_t* bring0 = stage0 + (size_t)p.stages * stage_bytes;
+    const int bring_bytes = p.halo == 3 ? p.b_stages * b_bytes : 0;
+    uint64_t* full = reinterpret_cast<uint64_t*>(bring0 + bring_bytes);
     uint64_t* empty = full + p.stages;
     uint64_t* tmem_full = empty + p.stages;
     uint64_t* tmem_empty = tmem_full + kMaxAccStages;
     uint64_t* bres_full = tmem_empty + kMaxAccStages;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bres_full + 1);
+    uint64_t* bfull = bres_full + 1;               // halo == 3 weight ring (<= 8 stages)
+    uint64_t* bempty = bfull + 8;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bempty + 8);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_tiles = p.n_total / p.n_tile;
     const int m_tiles = p.n_img * p.tiles_y * p.tiles_x;
     const int total_tiles = m_tiles * n_tiles;
-    const int ksteps = (p.halo == 2 ? 1 : (p.halo ? 3 : p.taps)) * kchunks;
+    const int ksteps = (p.halo >= 2 ? 1 : (p.halo ? 3 : p.taps)) * kchunks;
     const int tile_h = 128 / p.tile_w;
 
     if (warp == 0 && lane == 0) {
@@ -124,6 +132,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int s = 0; s < p.stages; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
         for (int a = 0; a < p.acc_stages; ++a) { ptx::mbar_init(&tmem_full[a], 1); ptx::mbar_init(&tmem_empty[a], 4); }
         ptx::mbar_init(bres_full, 1);
+        for (int b = 0; b < 8; ++b) { ptx::mbar_init(&bfull[b], 1); ptx::mbar_init(&bempty[b], 1); }
         ptx::fence_barrier_init();
     }
     if (warp == 2) ptx::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
@@ -140,8 +149,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 for (int j = 0; j < p.taps * kchunks; ++j)         // j = tap*kchunks + chunk  <=>  K offset j*kc
                     ptx::tma_load_2d(smem + (size_t)j * b_bytes, &tmB, bres_full, j * p.kc, 0);
             }
-            int s = 0;
-            uint32_t ph = 0;
+            int s = 0, sb = 0;
+            uint32_t ph = 0, bph = 0;
             uint8_t* sa = stage0;
             const int tiles_xy = p.tiles_x * p.tiles_y;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -151,6 +160,24 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
                 const int x0 = tx * p.tile_w, y0 = ty * tile_h;
                 const int n0 = n_t * p.n_tile;
+                if (p.halo == 3) {
+                    int c = p.a_c0;
+                    for (int kcI = 0; kcI < kchunks; ++kcI) {
+                        ptx::mbar_wait(&empty[s], ph ^ 1u);
+                        ptx::mbar_arrive_expect_tx(&full[s], (uint32_t)(180 * row_bytes));
+                        ptx::tma_load_5d(sa, &tmA, &full[s], c, x0 - 1, y0 - 1, img, 0);
+                        for (int tap = 0; tap < 9; ++tap) {
+                            ptx::mbar_wait(&bempty[sb], bph ^ 1u);
+                            ptx::mbar_arrive_expect_tx(&bfull[sb], (uint32_t)b_bytes);
+                            ptx::tma_load_2d(bring0 + (size_t)sb * b_bytes, &tmB, &bfull[sb], tap * p.cin + kcI * p.kc, n0);
+                            if (++sb == p.b_stages) { sb = 0; bph ^= 1u; }
+                        }
+                        c += p.kc;
+                        sa += stage_bytes;
+                        if (++s == p.stages) { s = 0; ph ^= 1u; sa = stage0; }
+                    }
+                    continue;
+                }
                 if (p.halo == 2) {
                     if (p.l2_prefetch > 0) {
                         // pull the box of the tile `l2_prefetch` iterations ahead into L2 (DRAM-sourced TMA rows are
@@ -271,12 +298,47 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 __syncwarp();
             }
         }
+        int sb = 0;
+        uint32_t bph = 0;
+        const uint32_t bring_base = ptx::smem_u32(bring0);
         for (; tile < total_tiles; tile += gridDim.x, ++tile_it) {
             ptx::mbar_wait(&tmem_empty[acc], acc_ph ^ 1u);
             ptx::tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.n_tile;
             const uint32_t acc_cur = acc;
             if (++acc == (uint32_t)p.acc_stages) { acc = 0; acc_ph ^= 1u; }
+            if (p.halo == 3) {
+                const uint64_t a_hi64 = ptx::make_smem_desc(0, 16, 10u * row_bytes, layout);
+                const uint32_t a_hi32 = (uint32_t)(a_hi64 >> 32), b_hi32 = (uint32_t)(desc_hi >> 32);
+                const uint32_t krow = (uint32_t)row_bytes >> 4;
+                for (int ks = 0; ks < ksteps; ++ks) {                 // ks = channel chunk
+                    ptx::mbar_wait(&full[s], ph);
+                    const uint32_t a_lo = (uint32_t)a_hi64 | ((a_addr & 0x3FFFFu) >> 4);
+                    for (int tap = 0; tap < 9; ++tap) {
+                        ptx::mbar_wait(&bfull[sb], bph);
+                        ptx::tc_fence_after();
+                        if (lane == 0) {
+                            const int kh = tap / 3, kw = tap - 3 * kh;
+                            const uint32_t at = a_lo + (uint32_t)(kh * 10 + kw) * krow;
+                            const uint32_t bt = (uint32_t)desc_hi | (((bring_base + (uint32_t)sb * (uint32_t)b_bytes) & 0x3FFFFu) >> 4);
+                            if (ks == 0 && tap == 0) ptx::umma_bf16_lohi(d_tmem, at, a_hi32, bt, b_hi32, idesc, false);
+                            else                     ptx::umma_bf16_lohi(d_tmem, at, a_hi32, bt, b_hi32, idesc, true);
+                            for (int k = 1; k < ksub; ++k)
+                                ptx::umma_bf16_lohi(d_tmem, at + 2u * k, a_hi32, bt + 2u * k, b_hi32, idesc, true);
+                            ptx::umma_commit(&bempty[sb]);
+                            if (tap == 8) {
+                                ptx::umma_commit(&empty[s]);
+                                if (ks == ksteps - 1) ptx::umma_commit(&tmem_full[acc_cur]);
+                            }
+                        }
+                        __syncwarp();
+                        if (++sb == p.b_stages) { sb = 0; bph ^= 1u; }
+                    }
+                    a_addr += (uint32_t)stage_bytes;
+                    if (++s == p.stages) { s = 0; ph ^= 1u; a_addr = stage_base; }
+                }
+                continue;
+            }
             for (int ks = 0; ks < ksteps; ++ks) {
                 ptx::mbar_wait(&full[s], ph);
                 ptx::tc_fence_after();

@@ -59,10 +59,16 @@ __device__ __forceinline__ void post_shot(const FrameConsts& fc, const Stream& s
     const uint32_t mask = (MASK == kRuntimeMask) ? rt_mask : MASK;
     const uint32_t quad = l0 >> 2;
     if (mask & ELD_NOISE_g) {
-        float n[4];
-        quad_normals_unscaled(s, quad, c, D_READ, n);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) z[k] = __fmaf_rn(n[k], fc.gbm, z[k]);
+        // z += g * sqrt(-2 ln u) * trig, with r*g formed once per Box-Muller pair
+        const uint4 x = draw(s, quad, DOM_QUAD, c, D_READ);
+        float l01, c01, s01, l23, c23, s23;
+        box_muller_parts(x.x, x.y, l01, c01, s01);
+        box_muller_parts(x.z, x.w, l23, c23, s23);
+        const float rg01 = fast_sqrt(l01) * fc.gbm, rg23 = fast_sqrt(l23) * fc.gbm;
+        z[0] = __fmaf_rn(c01, rg01, z[0]);
+        z[1] = __fmaf_rn(s01, rg01, z[1]);
+        z[2] = __fmaf_rn(c23, rg23, z[2]);
+        z[3] = __fmaf_rn(s23, rg23, z[3]);
     }
     if (mask & ELD_NOISE_G) {
         const uint4 x = draw(s, quad, DOM_QUAD, c, D_TL);

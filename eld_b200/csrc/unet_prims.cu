@@ -64,10 +64,21 @@ int launch_conv_gemm(eld_ctx* ctx, const GemmOp& op, cudaStream_t st)
         p.halo = 2; p.tile_w = 8;
         p.bo_mode = getenv("ELD_CONV_BO") ? atoi(getenv("ELD_CONV_BO")) : 0;
     }
+    // streamed weights + full-halo activations for every other conv3x3 (two rings)
+    p.b_stages = 0;
+    if (!p.b_res && op.a_mode == A_CONV && op.taps == 9 && !getenv("ELD_CONV_NOHALO3") && op.H % 16 == 0 && op.W % 8 == 0) {
+        p.halo = 3; p.tile_w = 8;
+    }
     p.tiles_x = op.W / p.tile_w; p.tiles_y = op.H / (128 / p.tile_w);
-    const int stage_bytes = p.halo == 2 ? ((180 * rb + 1023) & ~1023)
+    const int stage_bytes = p.halo >= 2 ? ((180 * rb + 1023) & ~1023)
                                         : (p.halo ? 160 : 128) * rb + (p.b_res ? 0 : (p.halo ? 3 : 1) * b_tile);
     int stages = (budget - (p.b_res ? b_total : 0)) / stage_bytes;
+    if (p.halo == 3) {
+        stages = 3;                                              // activations: 3 x 23 KB (kc = 64)
+        int bs = (216 * 1024 - stages * stage_bytes) / b_tile;   // weights: the rest, one tap per stage
+        if (bs > 8) bs = 8;
+        p.b_stages = bs;
+    }
     if (stages > 8) stages = 8;
     if (stages < 2) stages = 2;
     p.stages = stages;
@@ -85,8 +96,8 @@ int launch_conv_gemm(eld_ctx* ctx, const GemmOp& op, cudaStream_t st)
         cuuint64_t str[4] = { op.a_pitch * eb, (cuuint64_t)op.W * op.a_pitch * eb,
                               (cuuint64_t)op.H * op.W * op.a_pitch * eb,
                               (cuuint64_t)op.n_img * op.H * op.W * op.a_pitch * eb };
-        cuuint32_t box[5] = { (cuuint32_t)p.kc, (cuuint32_t)(p.halo == 2 ? 10 : 16),
-                              (cuuint32_t)(p.halo == 2 ? 18 : (p.halo ? 10 : 8)), 1, 1 };
+        cuuint32_t box[5] = { (cuuint32_t)p.kc, (cuuint32_t)(p.halo >= 2 ? 10 : 16),
+                              (cuuint32_t)(p.halo >= 2 ? 18 : (p.halo ? 10 : 8)), 1, 1 };
         int rc = encode(ctx, &tmA, op.a, 5, dims, str, box, p.kc * 2);
         if (rc) return rc;
     } else {
@@ -106,7 +117,8 @@ int launch_conv_gemm(eld_ctx* ctx, const GemmOp& op, cudaStream_t st)
         int rc = encode(ctx, &tmB, op.b, 2, dims, str, box, p.kc * 2);
         if (rc) return rc;
     }
-    const size_t smem = (size_t)stages * stage_bytes + (p.b_res ? b_total : 0) + 1024 /*align slack*/ + 512 /*barriers*/;
+    const size_t smem = (size_t)stages * stage_bytes + (p.b_res ? b_total : 0) + (size_t)p.b_stages * b_tile +
+                        1024 /*align slack*/ + 768 /*barriers*/;
     const int total_tiles = op.n_img * p.tiles_x * p.tiles_y * (p.n_total / p.n_tile);
     const int grid = total_tiles < ctx->num_sms ? total_tiles : ctx->num_sms;
     conv_umma_kernel<<<grid, kConvThreads, smem, st>>>(tmA, tmB, p);
