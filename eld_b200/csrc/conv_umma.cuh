@@ -43,6 +43,7 @@ struct ConvGemmParams {
     int b_res;            // weights resident in smem (loaded once per CTA); requires n_total == n_tile
     int tile_w;           // 16 (8x16 patch) or 8 (16x8 patch, full-halo mode)
     int bo_mode;          // full-halo mode: 1 = put (start>>7)&7 into the descriptor's base_offset field
+    const uint8_t* b_ptr; // packed weights: blocks [n_tile][tap][chunk] in smem-image order (unet_prims.h packed_index)
     int b_stages;         // halo == 3: depth of the separate weight ring
     int l2_prefetch;      // full-halo mode: prefetch the A box this many tiles ahead into L2 (0 = off)
     int acc_stages;       // TMEM accumulator ring depth (2..8): acc_stages * n_tile <= 512 columns
@@ -88,8 +89,7 @@ __device__ __forceinline__ void issue_halo2(uint32_t d_tmem, uint32_t a_lo, uint
 }
 
 __global__ void __launch_bounds__(kConvThreads, 1)
-conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const ConvGemmParams p)
+conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const ConvGemmParams p)
 {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = ptx::smem_u32(smem_raw);
@@ -128,7 +128,6 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&tmA);
-        ptx::prefetch_tmap(&tmB);
         for (int s = 0; s < p.stages; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
         for (int a = 0; a < p.acc_stages; ++a) { ptx::mbar_init(&tmem_full[a], 1); ptx::mbar_init(&tmem_empty[a], 4); }
         ptx::mbar_init(bres_full, 1);
@@ -146,8 +145,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (lane == 0) {
             if (p.b_res) {
                 ptx::mbar_arrive_expect_tx(bres_full, (uint32_t)bres_bytes);
-                for (int j = 0; j < p.taps * kchunks; ++j)         // j = tap*kchunks + chunk  <=>  K offset j*kc
-                    ptx::tma_load_2d(smem + (size_t)j * b_bytes, &tmB, bres_full, j * p.kc, 0);
+                for (int j = 0; j < p.taps; ++j)                    // the whole operand is one contiguous smem image
+                    ptx::bulk_load(smem + (size_t)j * kchunks * b_bytes, p.b_ptr + (size_t)j * kchunks * b_bytes,
+                                   (uint32_t)(kchunks * b_bytes), bres_full);
             }
             int s = 0, sb = 0;
             uint32_t ph = 0, bph = 0;
@@ -169,7 +169,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         for (int tap = 0; tap < 9; ++tap) {
                             ptx::mbar_wait(&bempty[sb], bph ^ 1u);
                             ptx::mbar_arrive_expect_tx(&bfull[sb], (uint32_t)b_bytes);
-                            ptx::tma_load_2d(bring0 + (size_t)sb * b_bytes, &tmB, &bfull[sb], tap * p.cin + kcI * p.kc, n0);
+                            ptx::bulk_load(bring0 + (size_t)sb * b_bytes,
+                                           p.b_ptr + ((size_t)(n_t * 9 + tap) * kchunks + kcI) * b_bytes, (uint32_t)b_bytes, &bfull[sb]);
                             if (++sb == p.b_stages) { sb = 0; bph ^= 1u; }
                         }
                         c += p.kc;
@@ -211,8 +212,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             ptx::tma_load_5d(sa, &tmA, &full[s], c, x0 + kw - 1, y0 - 1, img, 0);
                             if (!p.b_res) {
                                 for (int kh = 0; kh < 3; ++kh)
-                                    ptx::tma_load_2d(sa + a_bytes + kh * b_bytes, &tmB, &full[s],
-                                                     (kh * 3 + kw) * p.cin + kcI * p.kc, n0);
+                                    ptx::bulk_load(sa + a_bytes + kh * b_bytes,
+                                                   p.b_ptr + ((size_t)(n_t * 9 + kh * 3 + kw) * kchunks + kcI) * b_bytes,
+                                                   (uint32_t)b_bytes, &full[s]);
                             }
                             c += p.kc;
                             sa += stage_bytes;
@@ -238,7 +240,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         ptx::mbar_wait(&empty[s], ph ^ 1u);
                         ptx::mbar_arrive_expect_tx(&full[s], (uint32_t)stage_bytes);
                         ptx::tma_load_5d(sa, &tmA, &full[s], c, c1, c2, c3, c4);
-                        if (!p.b_res) ptx::tma_load_2d(sa + a_bytes, &tmB, &full[s], kb, n0);
+                        if (!p.b_res) ptx::bulk_load(sa + a_bytes, p.b_ptr + ((size_t)(n_t * p.taps + tap) * kchunks + kcI) * b_bytes,
+                                                     (uint32_t)b_bytes, &full[s]);
                         c += p.kc; kb += p.kc;
                         sa += stage_bytes;
                         if (++s == p.stages) { s = 0; ph ^= 1u; sa = stage0; }

@@ -59,11 +59,11 @@ pack_all_kernel(const float* __restrict__ params, __nv_bfloat16* __restrict__ pa
             __syncthreads();
             for (int i = threadIdx.x; i < 32 * 288; i += 256) {       // fprop: [co][t][ci]
                 const int ci = i & 31, t = (i >> 5) % 9, co = i / 288;
-                of[((size_t)(co0 + co) * 9 + t) * e.cin + ci0 + ci] = __float2bfloat16_rn(tile[co][ci * 9 + t]);
+                of[packed_index(e.cout, e.cin, 9, co0 + co, t, ci0 + ci)] = __float2bfloat16_rn(tile[co][ci * 9 + t]);
             }
             for (int i = threadIdx.x; i < 32 * 288; i += 256) {       // dgrad: [ci][8-t][co]
                 const int co = i & 31, t = (i >> 5) % 9, ci = i / 288;
-                od[((size_t)(ci0 + ci) * 9 + (8 - t)) * e.cout + co0 + co] = __float2bfloat16_rn(tile[co][ci * 9 + t]);
+                od[packed_index(e.cin, e.cout, 9, ci0 + ci, 8 - t, co0 + co)] = __float2bfloat16_rn(tile[co][ci * 9 + t]);
             }
         }
     } else {                              // deconv wt[ci][co][s]
@@ -78,11 +78,11 @@ pack_all_kernel(const float* __restrict__ params, __nv_bfloat16* __restrict__ pa
             __syncthreads();
             for (int i = threadIdx.x; i < 32 * 128; i += 256) {       // fprop: [(s*cout + co)][ci]
                 const int ci = i & 31, co = (i >> 5) & 31, sp = i >> 10;
-                of[((size_t)sp * e.cout + co0 + co) * e.cin + ci0 + ci] = __float2bfloat16_rn(tile[ci][co * 4 + sp]);
+                of[packed_index(4 * e.cout, e.cin, 1, sp * e.cout + co0 + co, 0, ci0 + ci)] = __float2bfloat16_rn(tile[ci][co * 4 + sp]);
             }
             for (int i = threadIdx.x; i < 32 * 128; i += 256) {       // dgrad: [ci][s][co]
                 const int co = i & 31, sp = (i >> 5) & 3, ci = i >> 7;
-                od[((size_t)(ci0 + ci) * 4 + sp) * e.cout + co0 + co] = __float2bfloat16_rn(tile[ci][co * 4 + sp]);
+                od[packed_index(e.cin, e.cout, 4, ci0 + ci, sp, co0 + co)] = __float2bfloat16_rn(tile[ci][co * 4 + sp]);
             }
         }
     }

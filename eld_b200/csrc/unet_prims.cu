@@ -89,7 +89,7 @@ int launch_conv_gemm(eld_ctx* ctx, const GemmOp& op, cudaStream_t st)
     while (cols < p.acc_stages * p.n_tile) cols *= 2;
     p.tmem_cols = cols;
 
-    CUtensorMap tmA, tmB;
+    CUtensorMap tmA;
     const cuuint64_t eb = 2;  // bf16
     if (op.a_mode == A_CONV) {
         cuuint64_t dims[5] = { (cuuint64_t)op.a_pitch, (cuuint64_t)op.W, (cuuint64_t)op.H, (cuuint64_t)op.n_img, 1 };
@@ -109,19 +109,12 @@ int launch_conv_gemm(eld_ctx* ctx, const GemmOp& op, cudaStream_t st)
         int rc = encode(ctx, &tmA, op.a, 5, dims, str, box, p.kc * 2);
         if (rc) return rc;
     }
-    {
-        const cuuint64_t ktot = (cuuint64_t)op.taps * op.cin;
-        cuuint64_t dims[2] = { ktot, (cuuint64_t)op.n_total };
-        cuuint64_t str[1] = { ktot * eb };
-        cuuint32_t box[2] = { (cuuint32_t)p.kc, (cuuint32_t)p.n_tile };
-        int rc = encode(ctx, &tmB, op.b, 2, dims, str, box, p.kc * 2);
-        if (rc) return rc;
-    }
+    p.b_ptr = static_cast<const uint8_t*>(op.b);
     const size_t smem = (size_t)stages * stage_bytes + (p.b_res ? b_total : 0) + (size_t)p.b_stages * b_tile +
                         1024 /*align slack*/ + 768 /*barriers*/;
     const int total_tiles = op.n_img * p.tiles_x * p.tiles_y * (p.n_total / p.n_tile);
     const int grid = total_tiles < ctx->num_sms ? total_tiles : ctx->num_sms;
-    conv_umma_kernel<<<grid, kConvThreads, smem, st>>>(tmA, tmB, p);
+    conv_umma_kernel<<<grid, kConvThreads, smem, st>>>(tmA, p);
     ELD_CHECK_CUDA(cudaGetLastError());
     count_launch(ctx);
     return ELD_OK;
@@ -277,20 +270,25 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* 
     const size_t total = (size_t)cout * cin * ksz;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         float v;
-        if (kind == PACK_CONV_FPROP) {            // out[co][t*cin + ci] = W[co][ci][kh][kw], t = kh*3+kw
+        size_t dst;
+        if (kind == PACK_CONV_FPROP) {            // B[co][t][ci] = W[co][ci][kh][kw], t = kh*3+kw
             const int ci = i % cin, t = (i / cin) % 9, co = i / ((size_t)cin * 9);
             v = w[((size_t)co * cin + ci) * 9 + t];
-        } else if (kind == PACK_CONV_DGRAD) {     // out[ci][t'*cout + co] = W[co][ci][2-kh'][2-kw'] = W[..][8-t']
+            dst = packed_index(cout, cin, 9, co, t, ci);
+        } else if (kind == PACK_CONV_DGRAD) {     // B[ci][t'][co] = W[co][ci][2-kh'][2-kw'] = W[..][8-t']
             const int co = i % cout, t = (i / cout) % 9, ci = i / ((size_t)cout * 9);
             v = w[((size_t)co * cin + ci) * 9 + (8 - t)];
-        } else if (kind == PACK_DECONV_FPROP) {   // out[(s*cout + co)][ci] = Wt[ci][co][kh][kw], s = kh*2+kw
+            dst = packed_index(cin, cout, 9, ci, t, co);
+        } else if (kind == PACK_DECONV_FPROP) {   // B[(s*cout + co)][ci] = Wt[ci][co][kh][kw], s = kh*2+kw
             const int ci = i % cin, co = (i / cin) % cout, s = i / ((size_t)cin * cout);
             v = w[((size_t)ci * cout + co) * 4 + s];
-        } else {                                  // PACK_DECONV_DGRAD: out[ci][s*cout + co] = Wt[ci][co][s]
+            dst = packed_index(4 * cout, cin, 1, s * cout + co, 0, ci);
+        } else {                                  // PACK_DECONV_DGRAD: B[ci][s][co] = Wt[ci][co][s]
             const int co = i % cout, s = (i / cout) % 4, ci = i / ((size_t)cout * 4);
             v = w[((size_t)ci * cout + co) * 4 + s];
+            dst = packed_index(cin, cout, 4, ci, s, co);
         }
-        out[i] = __float2bfloat16_rn(v);
+        out[dst] = __float2bfloat16_rn(v);
     }
 }
 

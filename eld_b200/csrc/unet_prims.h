@@ -11,6 +11,24 @@ enum { ACT_NONE = 0, ACT_LRELU = 1, ACT_MASK = 2 };
 enum { WG_CONV = 0, WG_DECONV = 1 };
 enum { PACK_CONV_FPROP = 0, PACK_CONV_DGRAD = 1, PACK_DECONV_FPROP = 2, PACK_DECONV_DGRAD = 3 };
 
+// Element index of logical B[n][tap][c] (n < rows, c < ck) inside the packed weight operand.
+// The operand is stored as the exact shared-memory IMAGE the conv tile consumes: contiguous blocks
+// [n_tile_idx][tap][channel chunk], each block = n_tile rows of kc channels (64 B / 128 B per row) with the
+// UMMA/TMA 64B / 128B swizzle already applied - so a whole block (or, for resident weights, a whole n-tile) is
+// ONE linear cp.async.bulk instead of n_tile TMA tensor rows.
+__host__ __device__ inline size_t packed_index(int rows, int ck, int taps, int n, int tap, int c)
+{
+    const int n_tile = rows <= 256 ? rows : 256;
+    const int kc = (ck % 64 == 0) ? 64 : 32;
+    const int kchunks = ck / kc, rb = kc * 2;
+    const int nt = n / n_tile, r = n - nt * n_tile;
+    const int chunk = c / kc, cc = c - chunk * kc;
+    const size_t block = ((size_t)nt * taps + tap) * kchunks + chunk;
+    const int swz = rb == 128 ? (r & 7) : ((r >> 1) & 3);
+    const int byte = r * rb + ((((cc * 2) >> 4) ^ swz) << 4) + ((cc * 2) & 15);
+    return block * ((size_t)n_tile * kc) + (size_t)(byte >> 1);
+}
+
 struct GemmOp {
     const void* a;      // bf16 NHWC activation (or gradient) tensor
     int a_pitch, a_c0;  // channels per pixel in memory, first channel used

@@ -9,7 +9,10 @@
 #ifndef ELD_B200_UNET_H
 #define ELD_B200_UNET_H
 
-/* kinds for eld_pack_weights: source layout is PyTorch's (Conv2d OIHW, ConvTranspose2d IOHW) */
+/* kinds for eld_pack_weights: source layout is PyTorch's (Conv2d OIHW, ConvTranspose2d IOHW).  The packed
+ * operand is OPAQUE: the logical K-major matrix listed below, stored as the shared-memory image the tiles
+ * consume (blocks [n_tile][tap][64-channel chunk], 64B/128B swizzle applied) so that a block is one linear
+ * bulk copy.  Same element count as the source. */
 #define ELD_PACK_CONV_FPROP    0  /* [cout][ (kh*3+kw)*cin + ci ]            <- W[co][ci][kh][kw]      */
 #define ELD_PACK_CONV_DGRAD    1  /* [cin ][ (kh*3+kw)*cout + co ]           <- W[co][ci][2-kh][2-kw]  */
 #define ELD_PACK_DECONV_FPROP  2  /* [(kh*2+kw)*cout + co][ci]               <- Wt[ci][co][kh][kw]     */
