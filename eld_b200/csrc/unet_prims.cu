@@ -66,7 +66,9 @@ int launch_conv_gemm(eld_ctx* ctx, const GemmOp& op, cudaStream_t st)
     }
     // streamed weights + full-halo activations for every other conv3x3 (two rings)
     p.b_stages = 0;
-    if (!p.b_res && op.a_mode == A_CONV && op.taps == 9 && !getenv("ELD_CONV_NOHALO3") && op.H % 16 == 0 && op.W % 8 == 0) {
+    // (measured: for n_tile == 64 the per-tap barrier round trip costs more than the rows it saves - keep halo == 1)
+    if (!p.b_res && op.a_mode == A_CONV && op.taps == 9 && p.n_tile >= 128 && !getenv("ELD_CONV_NOHALO3") &&
+        op.H % 16 == 0 && op.W % 8 == 0) {
         p.halo = 3; p.tile_w = 8;
     }
     p.tiles_x = op.W / p.tile_w; p.tiles_y = op.H / (128 / p.tile_w);
