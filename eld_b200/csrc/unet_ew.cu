@@ -269,14 +269,16 @@ colsum_kernel(const __nv_bfloat16* __restrict__ g, int pitch, int c0, int C, siz
 //   dw[co][ci] += dout[co] a[p][ci] ; db[co] += dout[co]
 // One pixel per thread per iteration, persistent blocks; per-thread partial dW in registers.
 // ---------------------------------------------------------------------------------------------------
+// Four threads per pixel (thread = one output channel co): 32 dW accumulators per thread instead of 128,
+// so two 256-thread blocks fit per SM and the loads of many pixels are in flight.
 template <bool TRAIN>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 head_kernel(const __nv_bfloat16* __restrict__ a, const float* __restrict__ w, const float* __restrict__ b,
             float* __restrict__ out, const float* __restrict__ target, __nv_bfloat16* __restrict__ dz,
             float* __restrict__ dw, float* __restrict__ db, float* __restrict__ loss,
             int n_img, size_t plane, float inv_numel)
 {
-    __shared__ float ws[4][32];
+    __shared__ float ws[4][33];
     __shared__ float bs[4];
     __shared__ float red[4 * 32 + 4 + 1];
     const int tid = threadIdx.x;
@@ -284,16 +286,21 @@ head_kernel(const __nv_bfloat16* __restrict__ a, const float* __restrict__ w, co
     if (tid < 4) bs[tid] = b[tid];
     if (TRAIN && tid < 133) red[tid] = 0.f;
     __syncthreads();
-    float pdw[4][32];
-    float pdb[4] = { 0, 0, 0, 0 }, ploss = 0.f;
+    const int co = tid & 3, lane = tid & 31;
+    float wrow[32];
+#pragma unroll
+    for (int ci = 0; ci < 32; ++ci) wrow[ci] = ws[co][ci];
+    float pdw[32];
+    float pdb = 0.f, ploss = 0.f;
     if (TRAIN) {
 #pragma unroll
-        for (int co = 0; co < 4; ++co)
-#pragma unroll
-            for (int ci = 0; ci < 32; ++ci) pdw[co][ci] = 0.f;
+        for (int ci = 0; ci < 32; ++ci) pdw[ci] = 0.f;
     }
     const size_t total = (size_t)n_img * plane;
-    for (size_t p = blockIdx.x * (size_t)blockDim.x + tid; p < total; p += (size_t)gridDim.x * blockDim.x) {
+    for (size_t pbase = (size_t)blockIdx.x * 64; pbase < total; pbase += (size_t)gridDim.x * 64) {
+        // block-uniform trip count (the shuffles below need whole warps); a ragged tail only masks the memory ops
+        const bool valid = pbase + (tid >> 2) < total;
+        const size_t p = valid ? pbase + (tid >> 2) : total - 1;
         const size_t n = p / plane, l = p - n * plane;
         float av[32];
         const uint4* ap = reinterpret_cast<const uint4*>(a + p * 32);
@@ -304,63 +311,57 @@ head_kernel(const __nv_bfloat16* __restrict__ a, const float* __restrict__ w, co
 #pragma unroll
             for (int j = 0; j < 4; ++j) { av[g * 8 + 2 * j] = bf_lo(wv[j]); av[g * 8 + 2 * j + 1] = bf_hi(wv[j]); }
         }
-        float o[4];
+        float o = bs[co];
 #pragma unroll
-        for (int co = 0; co < 4; ++co) {
-            float s = bs[co];
-#pragma unroll
-            for (int ci = 0; ci < 32; ++ci) s = fmaf(av[ci], ws[co][ci], s);
-            o[co] = s;
-            out[(n * 4 + co) * plane + l] = s;
-        }
+        for (int ci = 0; ci < 32; ++ci) o = fmaf(av[ci], wrow[ci], o);
+        if (valid) out[(n * 4 + co) * plane + l] = o;
         if (TRAIN) {
-            float d[4];
+            const float e = valid ? o - __ldg(target + (n * 4 + co) * plane + l) : 0.f;
+            ploss += fabsf(e);
+            const float d = (e > 0.f ? inv_numel : (e < 0.f ? -inv_numel : 0.f));
+            pdb += d;
 #pragma unroll
-            for (int co = 0; co < 4; ++co) {
-                const float e = o[co] - __ldg(target + (n * 4 + co) * plane + l);
-                ploss += fabsf(e);
-                d[co] = (e > 0.f ? inv_numel : (e < 0.f ? -inv_numel : 0.f));
-                pdb[co] += d[co];
+            for (int ci = 0; ci < 32; ++ci) pdw[ci] = fmaf(d, av[ci], pdw[ci]);
+            // the pixel's four dOut values (one per lane of the 4-lane group)
+            const int base = lane & ~3;
+            const float d0 = __shfl_sync(0xffffffffu, d, base), d1 = __shfl_sync(0xffffffffu, d, base + 1);
+            const float d2 = __shfl_sync(0xffffffffu, d, base + 2), d3 = __shfl_sync(0xffffffffu, d, base + 3);
+            // this thread writes dz channels [8co, 8co+8)
+            uint32_t zo[4];
+#pragma unroll
+            for (int j = 0; j < 8; j += 2) {
+                const int c0 = co * 8 + j;
+                float g0 = d0 * ws[0][c0] + d1 * ws[1][c0] + d2 * ws[2][c0] + d3 * ws[3][c0];
+                float g1 = d0 * ws[0][c0 + 1] + d1 * ws[1][c0 + 1] + d2 * ws[2][c0 + 1] + d3 * ws[3][c0 + 1];
+                // av[] is indexed statically per co below to stay in registers
+                float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) if (q == co) { a0 = av[q * 8 + j]; a1 = av[q * 8 + j + 1]; }
+                g0 *= (a0 > 0.f ? 1.0f : 0.2f);
+                g1 *= (a1 > 0.f ? 1.0f : 0.2f);
+                zo[j >> 1] = pack_bf2(g0, g1);
             }
-            uint32_t zo[16];
-#pragma unroll
-            for (int ci = 0; ci < 32; ci += 2) {
-                float g0 = 0.f, g1 = 0.f;
-#pragma unroll
-                for (int co = 0; co < 4; ++co) { g0 = fmaf(d[co], ws[co][ci], g0); g1 = fmaf(d[co], ws[co][ci + 1], g1); }
-                g0 *= (av[ci] > 0.f ? 1.0f : 0.2f);
-                g1 *= (av[ci + 1] > 0.f ? 1.0f : 0.2f);
-                zo[ci >> 1] = pack_bf2(g0, g1);
-            }
-            uint4* zp = reinterpret_cast<uint4*>(dz + p * 32);
-#pragma unroll
-            for (int g = 0; g < 4; ++g) zp[g] = make_uint4(zo[4 * g], zo[4 * g + 1], zo[4 * g + 2], zo[4 * g + 3]);
-#pragma unroll
-            for (int co = 0; co < 4; ++co)
-#pragma unroll
-                for (int ci = 0; ci < 32; ++ci) pdw[co][ci] = fmaf(d[co], av[ci], pdw[co][ci]);
+            if (valid) reinterpret_cast<uint4*>(dz + p * 32)[co] = make_uint4(zo[0], zo[1], zo[2], zo[3]);
         }
     }
     if (TRAIN) {
-        // warp reduce then shared atomics then one global atomic per block per value
+        // reduce over the 8 lanes of a warp that share `co` (lane ^ 4, 8, 16), then shared atomics, then one global
+        // atomic per value per block
 #pragma unroll
-        for (int co = 0; co < 4; ++co) {
-#pragma unroll
-            for (int ci = 0; ci < 32; ++ci) {
-                float v = pdw[co][ci];
-#pragma unroll
-                for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
-                if ((tid & 31) == 0) atomicAdd(&red[co * 32 + ci], v);
-            }
-            float v = pdb[co];
-#pragma unroll
-            for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
-            if ((tid & 31) == 0) atomicAdd(&red[128 + co], v);
+        for (int ci = 0; ci < 32; ++ci) {
+            float v = pdw[ci];
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
+            v += __shfl_xor_sync(0xffffffffu, v, 16);
+            if (lane < 4) atomicAdd(&red[co * 32 + ci], v);
         }
-        float v = ploss;
+        float v = pdb;
+        v += __shfl_xor_sync(0xffffffffu, v, 4); v += __shfl_xor_sync(0xffffffffu, v, 8); v += __shfl_xor_sync(0xffffffffu, v, 16);
+        if (lane < 4) atomicAdd(&red[128 + co], v);
+        float ls = ploss;
 #pragma unroll
-        for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
-        if ((tid & 31) == 0) atomicAdd(&red[132], v);
+        for (int sft = 16; sft > 0; sft >>= 1) ls += __shfl_xor_sync(0xffffffffu, ls, sft);
+        if (lane == 0) atomicAdd(&red[132], ls);
         __syncthreads();
         if (tid < 128) atomicAdd(dw + tid, red[tid]);
         else if (tid < 132) atomicAdd(db + (tid - 128), red[tid]);
@@ -456,10 +457,10 @@ int launch_head(eld_ctx* ctx, const void* a, const float* w, const float* b, flo
     const size_t total = (size_t)n * plane;
     const float inv = 1.0f / (float)(total * 4);
     if (target) {
-        head_kernel<true><<<grid_for(total, 256 * 8, 2 * ctx->num_sms), 256, 0, st>>>(
+        head_kernel<true><<<grid_for(total, 64 * 16, 2 * ctx->num_sms), 256, 0, st>>>(
             static_cast<const __nv_bfloat16*>(a), w, b, out, target, static_cast<__nv_bfloat16*>(dz), dw, db, loss, n, plane, inv);
     } else {
-        head_kernel<false><<<grid_for(total, 256, 8 * ctx->num_sms), 256, 0, st>>>(
+        head_kernel<false><<<grid_for(total, 64, 8 * ctx->num_sms), 256, 0, st>>>(
             static_cast<const __nv_bfloat16*>(a), w, b, out, nullptr, nullptr, nullptr, nullptr, nullptr, n, plane, inv);
     }
     ELD_CHECK_CUDA(cudaGetLastError());
