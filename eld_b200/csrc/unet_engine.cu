@@ -34,7 +34,7 @@ enum { I_C11 = 0, I_C12, I_C21, I_C22, I_C31, I_C32, I_C41, I_C42, I_C51, I_C52,
        I_C71, I_C72, I_UP8, I_C81, I_C82, I_UP9, I_C91, I_C92, I_C10 };
 
 struct PackEntry { unsigned long long src, dst_f, dst_d; int cout, cin, type; int pad; };
-struct PackTable { PackEntry e[kNumLayers]; int n; unsigned long long first_stage, first_dst; };
+struct PackTable { PackEntry e[kNumLayers]; int n; unsigned long long first_stage, first_dst, first_wf; };
 
 // one launch packs every layer's fp32 master weights into both bf16 GEMM operands (fprop + dgrad).
 // A block moves a (32 x 32 x taps) tile through shared memory so that reads are 1 KB runs and writes are
@@ -43,6 +43,14 @@ __global__ void __launch_bounds__(256)
 pack_all_kernel(const float* __restrict__ params, __nv_bfloat16* __restrict__ packed, const __grid_constant__ PackTable T)
 {
     __shared__ float tile[32][32 * 9 + 1];
+    if ((int)blockIdx.y == T.n) {         // conv1_1: w[32][4][9] -> operand [32][9][32] (channels 4..31 stay zero)
+        const float* w1 = params + T.first_dst;
+        for (int i = blockIdx.x * 256 + threadIdx.x; i < 32 * 36; i += gridDim.x * 256) {
+            const int co = i / 36, r = i - co * 36, ci = r / 9, t = r - ci * 9;
+            packed[T.first_wf + packed_index(32, 32, 9, co, t, ci)] = __float2bfloat16_rn(w1[i]);
+        }
+        return;
+    }
     const PackEntry& e = T.e[blockIdx.y];
     const float* w = params + e.src;
     __nv_bfloat16* of = packed + e.dst_f;
@@ -163,8 +171,8 @@ static size_t layout(eld_unet* u, char* base, bool train)
     take(&u->a5_1, 4, 512); take(&u->a5_2, 4, 512);
     take(&u->a6_1, 3, 256); take(&u->a6_2, 3, 256); take(&u->a7_1, 2, 128); take(&u->a7_2, 2, 128);
     take(&u->a8_1, 1, 64); take(&u->a8_2, 1, 64); take(&u->a9_1, 0, 32); take(&u->a9_2, 0, 32);
+    take(&u->x32, 0, 32);
     if (train) {
-        take(&u->x32, 0, 32);
         take(&u->dz9_2, 0, 32); take(&u->dz9_1, 0, 32); take(&u->dcat9, 0, 64);
         take(&u->dz8_2, 1, 64); take(&u->dz8_1, 1, 64); take(&u->dcat8, 1, 128);
         take(&u->dz7_2, 2, 128); take(&u->dz7_1, 2, 128); take(&u->dcat7, 2, 256);
@@ -177,6 +185,7 @@ static size_t layout(eld_unet* u, char* base, bool train)
     }
     // packed weights
     size_t pk = 0;
+    u->L[I_C11].wf_off = pk; pk += 32 * 9 * 32;          // conv1_1: input padded to 32 channels, fprop only
     for (int i = 0; i < kNumLayers; ++i) {
         Layer& l = u->L[i];
         if (i == I_C11 || l.type == L_CONV1) continue;
@@ -267,6 +276,9 @@ extern "C" int eld_unet_create(eld_ctx* ctx, int n, int h, int w, int train, voi
     u->table.n = k;
     u->table.first_stage = u->n_params;
     u->table.first_dst = u->L[I_C11].w_off;
+    u->table.first_wf = u->L[I_C11].wf_off;
+    // the padded input channels of conv1_1's operand must be finite zeros (they multiply the zero channels of x32)
+    ELD_CHECK_CUDA(cudaMemset(u->packed + u->L[I_C11].wf_off, 0, 32 * 9 * 32 * sizeof(__nv_bfloat16)));
     // opt in to large dynamic shared memory once (not inside a captured region)
     { int rc = init_gemm_kernels(ctx); if (rc != ELD_OK) { delete u; return rc; } }
     *out = u;
@@ -402,7 +414,7 @@ struct Runner {
     int pack() const
     {
         Scope sc(u, st, "weights", "pack", 0.0, (double)u->n_params * 8);
-        dim3 grid(64, u->table.n);
+        dim3 grid(64, u->table.n + 1);
         pack_all_kernel<<<grid, 256, 0, st>>>(params, u->packed, u->table);
         ELD_CHECK_CUDA(cudaGetLastError());
         count_launch(ctx());
@@ -415,8 +427,18 @@ struct Runner {
         TRY(pack());
         {
             const double px = (double)U->n * U->H * U->W;
-            Scope sc(u, st, "conv1_1", "fprop", 2.0 * px * 32 * 36, px * (16 + 64));
-            TRY(launch_first_conv(ctx(), x, params + U->L[I_C11].w_off, bias(I_C11), U->a1_1, U->x32, U->n, U->H, U->W, st));
+            {
+                Scope sc(u, st, "input", "pack", 0.0, px * (16 + 64));
+                TRY(launch_pack_input(ctx(), x, U->x32, U->n, U->H, U->W, st));
+            }
+            // conv1_1 (4 -> 32) as a 32 -> 32 tcgen05 tile on the zero-padded input
+            GemmOp op{};
+            op.a = U->x32; op.a_pitch = 32; op.a_c0 = 0; op.a_mode = A_CONV; op.taps = 9; op.cin = 32;
+            op.n_img = U->n; op.H = U->H; op.W = U->W;
+            op.b = wf(I_C11); op.n_total = 32; op.cout = 32;
+            op.epi_mode = EPI_STORE; op.act = ACT_LRELU; op.out = U->a1_1; op.out_pitch = 32; op.out_c0 = 0; op.bias = bias(I_C11);
+            Scope sc(u, st, "conv1_1", "fprop", 2.0 * px * 32 * 36, px * (64 + 64));
+            TRY(launch_conv_gemm(ctx(), op, st));
         }
         TRY(conv(I_C12, U->a1_1, 32, 0, U->cat9, 64, 32, 0));  TRY(pool(U->cat9, 64, 32, U->p1, 32, 1));
         TRY(conv(I_C21, U->p1, 32, 0, U->a2_1, 64, 0, 1));

@@ -78,6 +78,23 @@ first_conv_kernel(const float* __restrict__ x, const float* __restrict__ w, cons
                             pack_bf2(lrelu(acc[8 * g + 4]), lrelu(acc[8 * g + 5])), pack_bf2(lrelu(acc[8 * g + 6]), lrelu(acc[8 * g + 7])));
 }
 
+// x f32 NCHW [n][4][H][W] -> x32 bf16 NHWC [n][H][W][32] (channels 4..31 zero): operand of the tcgen05 tiles for
+// conv1_1 (fprop and wgrad).  One pixel per thread: 4 coalesced plane reads, one 64-byte write.
+__global__ void __launch_bounds__(256)
+pack_input_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ x32, size_t plane, size_t total)
+{
+    for (size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x; p < total; p += (size_t)gridDim.x * blockDim.x) {
+        const size_t n = p / plane, l = p - n * plane;
+        const float* src = x + n * 4 * plane + l;
+        const float v0 = __ldg(src), v1 = __ldg(src + plane), v2 = __ldg(src + 2 * plane), v3 = __ldg(src + 3 * plane);
+        uint4* d = reinterpret_cast<uint4*>(x32 + p * 32);
+        d[0] = make_uint4(pack_bf2(v0, v1), pack_bf2(v2, v3), 0u, 0u);
+        d[1] = make_uint4(0u, 0u, 0u, 0u);
+        d[2] = make_uint4(0u, 0u, 0u, 0u);
+        d[3] = make_uint4(0u, 0u, 0u, 0u);
+    }
+}
+
 // conv1_1 weight/bias gradient: dW[32][4][3][3] += sum_p dz[p][co] x[p+tap][ci], db[co] += sum_p dz[p][co].
 // Persistent blocks over 16x16 tiles; thread (co = t&31, g = t>>5) owns k = g, g+8, ... (<36) and,
 // for g == 0, the bias.  One global atomic per accumulator per block at the end.
@@ -402,6 +419,15 @@ int launch_first_conv(eld_ctx* ctx, const float* x, const float* w, const float*
 {
     dim3 grid((W + 15) / 16, (H + 15) / 16, n);
     first_conv_kernel<<<grid, 256, 0, st>>>(x, w, b, static_cast<__nv_bfloat16*>(y), static_cast<__nv_bfloat16*>(x32), H, W);
+    ELD_CHECK_CUDA(cudaGetLastError());
+    count_launch(ctx);
+    return ELD_OK;
+}
+
+int launch_pack_input(eld_ctx* ctx, const float* x, void* x32, int n, int H, int W, cudaStream_t st)
+{
+    const size_t plane = (size_t)H * W, total = plane * n;
+    pack_input_kernel<<<grid_for(total, 256, 16 * ctx->num_sms), 256, 0, st>>>(x, static_cast<__nv_bfloat16*>(x32), plane, total);
     ELD_CHECK_CUDA(cudaGetLastError());
     count_launch(ctx);
     return ELD_OK;

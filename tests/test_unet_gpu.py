@@ -48,7 +48,7 @@ def _emulated_forward(torch, net, x):
     lre = lambda v: torch.max(0.2 * v, v)
     c = lambda name, v: _q(lre(F.conv2d(v, _q(getattr(net, name).weight), getattr(net, name).bias, padding=1)))
     up = lambda name, v: _q(F.conv_transpose2d(v, _q(getattr(net, name).weight), getattr(net, name).bias, stride=2))
-    a = _q(lre(F.conv2d(x, net.conv1_1.weight, net.conv1_1.bias, padding=1)))      # first layer: fp32 weights
+    a = _q(lre(F.conv2d(_q(x), _q(net.conv1_1.weight), net.conv1_1.bias, padding=1)))   # first layer: bf16 operands too
     c1 = c('conv1_2', a)
     c2 = c('conv2_2', c('conv2_1', F.max_pool2d(c1, 2)))
     c3 = c('conv3_2', c('conv3_1', F.max_pool2d(c2, 2)))
