@@ -46,6 +46,7 @@ struct ConvGemmParams {
     const uint8_t* b_ptr; // packed weights: blocks [n_tile][tap][chunk] in smem-image order (unet_prims.h packed_index)
     int b_stages;         // halo == 3: depth of the separate weight ring
     int l2_prefetch;      // full-halo mode: prefetch the A box this many tiles ahead into L2 (0 = off)
+    int dbg;              // experiments only (ELD_CONV_DBG): 1 = skip the global stores, 2 = skip bias, 4 = skip tcgen05.ld
     int acc_stages;       // TMEM accumulator ring depth (2..8): acc_stages * n_tile <= 512 columns
 };
 
@@ -406,8 +407,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const ConvGemmParams p
             const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc_cur * (uint32_t)p.n_tile;
             for (int c32 = 0; c32 < p.n_tile / 32; ++c32) {
                 uint32_t r[32];
-                ptx::tmem_ld32(t_addr + c32 * 32, r);
-                ptx::tmem_ld_wait();
+                if (!(p.dbg & 4)) {
+                    ptx::tmem_ld32(t_addr + c32 * 32, r);
+                    ptx::tmem_ld_wait();
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) r[j] = 0x3F800000u + j;
+                }
                 const int col = n_t * p.n_tile + c32 * 32;    // first GEMM column of this chunk
                 __nv_bfloat16* dst;
                 int bcol;
@@ -423,7 +429,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const ConvGemmParams p
                 float v[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                if (p.bias) {
+                if (p.bias && !(p.dbg & 2)) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] += __ldg(p.bias + bcol + j);
                 }
@@ -448,6 +454,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const ConvGemmParams p
                     }
                 }
                 uint4* d4 = reinterpret_cast<uint4*>(dst);
+                if (p.dbg & 1) d4 = reinterpret_cast<uint4*>(p.out + (size_t)threadIdx.x * 32);   // one hot line per thread
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
                     uint32_t w[4];

@@ -85,6 +85,7 @@ int launch_conv_gemm(eld_ctx* ctx, const GemmOp& op, cudaStream_t st)
     if (stages < 2) stages = 2;
     p.stages = stages;
     p.l2_prefetch = getenv("ELD_CONV_PREFETCH") ? atoi(getenv("ELD_CONV_PREFETCH")) : 0;
+    p.dbg = getenv("ELD_CONV_DBG") ? atoi(getenv("ELD_CONV_DBG")) : 0;
     p.acc_stages = 512 / p.n_tile;
     if (p.acc_stages > kMaxAccStages) p.acc_stages = kMaxAccStages;
     int cols = 32;
