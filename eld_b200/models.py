@@ -190,17 +190,38 @@ class ELDModel(BaseModel):
             ret_errors['Pixel'] = self.loss_pixel if getattr(self.opt, 'defer_loss_sync', False) else self.loss_pixel.item()
         return ret_errors
 
-    def eval(self, data, savedir=None, **kwargs):
-        """Minimal GPU eval: forward + PSNR (util/index.py:79 restated); the rawpy/skimage based
-        visualisation of ELD_model.py:203-307 is out of scope."""
+    @staticmethod
+    def illuminance_correct(predict, source):
+        """IlluminanceCorrect.correct (ELD_model.py:156-169) on the GPU, per frame: scalar gain
+        <p, s> / <p, p> over the pixels where source != 1, applied to clamp(predict, 0, 1)."""
+        p = predict.clamp(0, 1)
+        m = (source != 1).to(p.dtype)
+        num = (p * source * m).flatten(1).double().sum(1)
+        den = (p * p * m).flatten(1).double().sum(1)
+        return (num / den).to(p.dtype).view(-1, 1, 1, 1) * p
+
+    def eval(self, data, savedir=None, suffix=None, correct=False, crop=True, frame_id=None, **kwargs):
+        """ELDModelBase.eval (ELD_model.py:203-307) without the rawpy / PIL visualisation: centre 512x512 crop
+        (util.crop_center), forward, optional illuminance correction, PSNR exactly as tensor2im +
+        skimage.compare_psnr(data_range=255) compute it (clip(255 x, 0, 255), no rounding; util/index.py:79).
+        Everything stays on the device; one host read of the final scalar."""
         self._eval()
         self.set_input(data, 'eval')
         with torch.no_grad():
-            out = self._padded_forward(self.input) if not self.opt.chop else self.forward_chop(self.input)
-        a = (out.clamp(0, 1) * 255.0).double()
-        b = (self.target.clamp(0, 1) * 255.0).double()
-        mse = ((a - b) ** 2).mean().item()
-        return {'PSNR': 10.0 * np.log10(255.0 ** 2 / max(mse, 1e-30))}
+            x, t = self.input, self.target
+            if crop and x.shape[2] >= 512 and x.shape[3] >= 512:
+                h, w = x.shape[2:]
+                y0, x0 = h // 2 - 256, w // 2 - 256
+                x, t = x[:, :, y0:y0 + 512, x0:x0 + 512].contiguous(), t[:, :, y0:y0 + 512, x0:x0 + 512].contiguous()
+            out = self.forward_chop(x) if self.opt.chop else self._padded_forward(x)
+            if correct:
+                out = self.illuminance_correct(out, t)
+            self.output = out
+            a = (out[0:1] * 255.0).clamp(0, 255).double()          # only the 1st frame is assessed, like the reference
+            b = (t[0:1] * 255.0).clamp(0, 255).double()
+            mse = ((a - b) ** 2).mean()
+            psnr = 10.0 * torch.log10(255.0 ** 2 / mse.clamp_min(1e-30))
+        return {'PSNR': float(psnr.item())}
 
     def test(self, data, savedir=None, **kwargs):
         self._eval()

@@ -90,3 +90,25 @@ def test_eval_and_chop(torch, tmp_path):
     assert chop.shape == full.shape == (1, 4, 160, 272)
     # the quadrant interiors agree with the full-frame forward away from the replicate-padded borders
     assert (chop[:, :, 16:64, 16:120] - full[:, :, 16:64, 16:120]).abs().max().item() < 5e-2
+
+
+def test_eval_matches_reference_formulas(torch, tmp_path):
+    """eval(correct=True): IlluminanceCorrect (ELD_model.py:156-169) + tensor2im/PSNR (ELD_model.py:31-36,
+    util/index.py:79) restated in numpy float64 on the same network output."""
+    from eld_b200 import models
+    from oracle import ref_numpy
+    opt = models.default_opt(name='ev2', checkpoints_dir=str(tmp_path))
+    m = models.eld_model()
+    m.initialize(opt)
+    g = torch.Generator().manual_seed(4)
+    t = torch.rand(1, 4, 512, 512, generator=g)
+    t[0, 0, :8, :8] = 1.0                                        # saturated pixels are excluded from the gain
+    d = {'input': (t * 0.5 + 0.02 * torch.randn(1, 4, 512, 512, generator=g)).clamp(0, 1), 'target': t, 'fn': ['x']}
+    r = m.eval(d, correct=True, crop=True)
+    raw = m._padded_forward(d['input'].cuda()).cpu().numpy().astype(np.float64)
+    p = np.clip(raw, 0, 1)
+    tt = t.numpy().astype(np.float64)
+    mask = tt != 1
+    gain = (p[mask] * tt[mask]).sum() / (p[mask] * p[mask]).sum()
+    want = ref_numpy.psnr255(gain * p, tt)
+    assert abs(r['PSNR'] - want) < 1e-3, (r['PSNR'], want)
