@@ -149,6 +149,24 @@ __device__ __forceinline__ void stg_stream(float4* p, const float4& v)
                  :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+// clean-frame source: f32 packed, or the LMDB wire format - uint16 packed, y = clip(v/65535, 0, 1)
+// (dataset/lmdb_dataset.py:38-39); the de-quantised frame can be written out as the training target.
+struct U16Src { const uint16_t* src; float scale; float* clean_out; };
+
+template <int IN>
+__device__ __forceinline__ float4 load_clean(const float* cleanf, const U16Src& u, size_t idx)
+{
+    if (IN == 0) return ldg_stream(reinterpret_cast<const float4*>(cleanf + idx));
+    const uint2 r = __ldg(reinterpret_cast<const uint2*>(u.src + idx));
+    float4 v;
+    v.x = fminf(fmaxf((float)(r.x & 0xFFFFu) * u.scale, 0.f), 1.f);
+    v.y = fminf(fmaxf((float)(r.x >> 16) * u.scale, 0.f), 1.f);
+    v.z = fminf(fmaxf((float)(r.y & 0xFFFFu) * u.scale, 0.f), 1.f);
+    v.w = fminf(fmaxf((float)(r.y >> 16) * u.scale, 0.f), 1.f);
+    if (u.clean_out) stg_stream(reinterpret_cast<float4*>(u.clean_out + idx), v);
+    return v;
+}
+
 __device__ __forceinline__ Stream make_stream(const NoiseLaunch& L, int f)
 {
     const uint64_t frame = L.frame0 + (uint64_t)f;
@@ -163,10 +181,10 @@ __device__ __forceinline__ void row_normals(const Stream& s, uint32_t i, float& 
 
 // ---- packed in, aligned: w % 4 == 0 and 16-byte aligned planes ---------------------------------
 // Gaussian-only masks are issue/latency bound on MUFU chains: cap registers at 32 so 8 blocks (64 warps) fit.
-template <uint32_t MASK, int CLIP>
+template <uint32_t MASK, int CLIP, int IN = 0>
 __global__ void __launch_bounds__(256, (MASK != kRuntimeMask && !(MASK & (ELD_NOISE_P | ELD_NOISE_G))) ? 8 : 1)
 noise_packed_vec_kernel(const float* __restrict__ clean, float* __restrict__ noisy,
-                        const __grid_constant__ NoiseLaunch L)
+                        const __grid_constant__ NoiseLaunch L, const U16Src u16 = U16Src{})
 {
     const int f = blockIdx.y;
     const uint32_t plane = (uint32_t)L.h * (uint32_t)L.w;
@@ -180,7 +198,7 @@ noise_packed_vec_kernel(const float* __restrict__ clean, float* __restrict__ noi
 
     float4 v[4];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) v[c] = ldg_stream(reinterpret_cast<const float4*>(clean + base + (size_t)c * plane));
+    for (int c = 0; c < 4; ++c) v[c] = load_clean<IN>(clean, u16, base + (size_t)c * plane);
 
     float r_even = 0.f, r_odd = 0.f;
     if (mask & ELD_NOISE_R) row_normals(s, (t * 4u) / (uint32_t)L.w, r_even, r_odd);
@@ -202,10 +220,10 @@ noise_packed_vec_kernel(const float* __restrict__ clean, float* __restrict__ noi
 // acceptance, so a warp iterates ~1.2 x 16 times instead of 16 x max-over-lanes.  The per-pixel arithmetic
 // and draw order are exactly poisson_px's (same values; oracle: eld_oracle_poisson_px).  The lane's 16 rates
 // and counts live in a private shared-memory column (dynamic indexing without local memory).
-template <uint32_t MASK>
+template <uint32_t MASK, int IN = 0>
 __global__ void __launch_bounds__(256)
 noise_packed_poisson_kernel(const float* __restrict__ clean, float* __restrict__ noisy,
-                            const __grid_constant__ NoiseLaunch L)
+                            const __grid_constant__ NoiseLaunch L, const U16Src u16 = U16Src{})
 {
     __shared__ float s_buf[16][256];
     const int f = blockIdx.y;
@@ -221,7 +239,7 @@ noise_packed_poisson_kernel(const float* __restrict__ clean, float* __restrict__
 
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-        const float4 v = ldg_stream(reinterpret_cast<const float4*>(clean + base + (size_t)c * plane));
+        const float4 v = load_clean<IN>(clean, u16, base + (size_t)c * plane);
         s_buf[c * 4 + 0][tid] = (v.x * fc.scale_in) * fc.invK;
         s_buf[c * 4 + 1][tid] = (v.y * fc.scale_in) * fc.invK;
         s_buf[c * 4 + 2][tid] = (v.z * fc.scale_in) * fc.invK;
@@ -599,6 +617,37 @@ extern "C" int eld_noise_mosaic(eld_ctx* ctx, const void* mosaic, int in_dtype, 
         } else {
             noise_mosaic_generic_kernel<<<grid, 256, 0, st>>>(src, dst, cdst, M, L);
         }
+        ELD_CHECK_CUDA(cudaGetLastError());
+        count_launch(ctx);
+    }
+    return ELD_OK;
+}
+
+// LMDB wire format in: packed uint16 [n][4][h][w] -> y = clip(v * scale, 0, 1) -> noise.  clean_out (optional)
+// receives the de-quantised frame (the training target).  w % 4 == 0 and 8/16-byte aligned buffers required.
+extern "C" int eld_noise_packed_u16(eld_ctx* ctx, const uint16_t* clean_u16, float scale, float* noisy, float* clean_out,
+                                    int n, int h, int w, const eld_noise_params* params, uint32_t model_mask,
+                                    uint64_t seed, uint64_t frame_id0, int clip01, void* stream)
+{
+    int rc = check_common(ctx, clean_u16, noisy, n, h, w, params, model_mask, "eld_noise_packed_u16");
+    if (rc < 0) return rc;
+    if (rc == 1) return ELD_OK;
+    ELD_REQUIRE(w % 4 == 0, "eld_noise_packed_u16: w=%d must be a multiple of 4", w);
+    ELD_REQUIRE(reinterpret_cast<uintptr_t>(clean_u16) % 8 == 0 && reinterpret_cast<uintptr_t>(noisy) % 16 == 0 &&
+                reinterpret_cast<uintptr_t>(clean_out) % 16 == 0, "eld_noise_packed_u16: misaligned buffer");
+    ELD_CHECK_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t plane = (size_t)h * w;
+    for (int f0 = 0; f0 < n; f0 += kMaxFramesPerLaunch) {
+        const int nf = (n - f0 < kMaxFramesPerLaunch) ? n - f0 : kMaxFramesPerLaunch;
+        NoiseLaunch L{};
+        for (int f = 0; f < nf; ++f) L.fr[f] = make_consts(params[f0 + f]);
+        L.seed = seed; L.frame0 = frame_id0 + (uint64_t)f0; L.mask = model_mask; L.h = h; L.w = w; L.clip01 = clip01;
+        U16Src u{ clean_u16 + (size_t)f0 * 4 * plane, scale, clean_out ? clean_out + (size_t)f0 * 4 * plane : nullptr };
+        float* dst = noisy + (size_t)f0 * 4 * plane;
+        dim3 grid((uint32_t)((plane / 4 + 255) / 256), nf);
+        if (model_mask & ELD_NOISE_P) noise_packed_poisson_kernel<kRuntimeMask, 1><<<grid, 256, 0, st>>>(nullptr, dst, L, u);
+        else                          noise_packed_vec_kernel<kRuntimeMask, -1, 1><<<grid, 256, 0, st>>>(nullptr, dst, L, u);
         ELD_CHECK_CUDA(cudaGetLastError());
         count_launch(ctx);
     }

@@ -136,6 +136,27 @@ class NoiseModelBase:
         _lib.check(rc, 'eld_noise_mosaic')
         return noisy, clean
 
+    def lmdb_gpu(self, packed_u16, params=None, frame_id0=None, clip=True, want_clean=True, seed=None):
+        """packed_u16: cuda int16/uint16 [N,4,h,w] - the LMDB wire format (lmdb_dataset.py:24-39).  Returns
+        (noisy f32, clean f32 = clip(v/65535, 0, 1)); only 2 bytes per pixel had to cross PCIe."""
+        import torch
+        assert packed_u16.is_cuda and packed_u16.dim() == 4 and packed_u16.shape[1] == 4
+        assert packed_u16.dtype in (torch.int16, torch.uint16)
+        packed_u16 = packed_u16.contiguous()
+        n, _, h, w = packed_u16.shape
+        plist = self._frame_params(n, params)
+        if frame_id0 is None:
+            frame_id0 = int(np.random.randint(0, 2 ** 62))
+        noisy = torch.empty((n, 4, h, w), dtype=torch.float32, device=packed_u16.device)
+        clean = torch.empty_like(noisy) if want_clean else None
+        rc = _lib.load().eld_noise_packed_u16(_lib.ctx(packed_u16.device.index or 0), packed_u16.data_ptr(), 1.0 / 65535.0,
+                                              noisy.data_ptr(), clean.data_ptr() if clean is not None else None, n, h, w,
+                                              params_array(plist), _lib.model_mask(self.model),
+                                              int(self.seed if seed is None else seed), int(frame_id0), int(bool(clip)),
+                                              _cur_stream(torch))
+        _lib.check(rc, 'eld_noise_packed_u16')
+        return noisy, clean
+
     # ---- reference call signature (noise.py:149) ---------------------------------------------------
     def __call__(self, y, params=None):
         """numpy [4,h,w] float in [0,1] -> numpy float32 [4,h,w].  Not clipped (the reference clips

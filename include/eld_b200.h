@@ -97,6 +97,13 @@ int eld_noise_mosaic(eld_ctx* ctx, const void* mosaic, int in_dtype, float black
                      const eld_noise_params* params, uint32_t model_mask,
                      uint64_t seed, uint64_t frame_id0, int clip01, void* stream);
 
+/* The LMDB wire format as input (util/lmdb_data.py:184-228, dataset/lmdb_dataset.py:24-39): packed uint16
+ * [n][4][h][w], y = clip(v * scale, 0, 1) with scale = 1/65535; only 2 bytes per pixel cross PCIe.  Writes noisy
+ * and, if clean_out != NULL, the de-quantised clean frame (the training target).  w % 4 == 0. */
+int eld_noise_packed_u16(eld_ctx* ctx, const uint16_t* clean_u16, float scale, float* noisy, float* clean_out,
+                         int n, int h, int w, const eld_noise_params* params, uint32_t model_mask,
+                         uint64_t seed, uint64_t frame_id0, int clip01, void* stream);
+
 /* Number of kernels the library has launched through this ctx since creation (bench.py's
  * gpu_launches evidence). */
 int64_t eld_launch_count(const eld_ctx* ctx);

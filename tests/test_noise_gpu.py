@@ -252,3 +252,21 @@ def test_full_size_poisson_law_against_scipy(torch):
         lam_eff = float(np.float32(np.float32(lam / (sat / ratio)) * np.float32(sat / ratio)))
         d = np.abs(emp - stats.poisson.cdf(ks, lam_eff)).max()
         assert d < 1.63 / np.sqrt(x.size), (lam, d)
+
+
+@pytest.mark.parametrize('model,mask', [('p+g', 6), ('P+g', 5)])
+def test_lmdb_u16_ingest(torch, oracle, model, mask):
+    """LMDB wire format (packed uint16, lmdb_dataset.py:38-39) -> de-quantise -> noise == the f32 path on the
+    de-quantised frame (same random stream), and the de-quantised target is bit-exact clip(v/65535,0,1)."""
+    rs = np.random.RandomState(21)
+    v = rs.randint(0, 65536, size=(3, 4, 16, 24)).astype(np.uint16)
+    nm = _nm(model)
+    noisy, clean = nm.lmdb_gpu(torch.from_numpy(v.view(np.int16)).cuda(), params=SONY, frame_id0=9)
+    want_clean = np.clip(v.astype(np.float32) * np.float32(1.0 / 65535.0), 0, 1).astype(np.float32)
+    assert np.array_equal(clean.cpu().numpy(), want_clean)
+    via_f32 = nm.batch_gpu(clean, params=SONY, frame_id0=9, clip=True)
+    assert torch.equal(via_f32, noisy)
+    ref = oracle.noise_packed(want_clean, [SONY] * 3, mask, 1234, 9, True)
+    sig = _sigma(want_clean, SONY, mask)
+    bad = np.abs(noisy.cpu().numpy().astype(np.float64) - ref) > ATOL_SIGMA * sig + 1e-6
+    assert bad.mean() <= (MISMATCH_FRAC if mask & 1 else 0)
