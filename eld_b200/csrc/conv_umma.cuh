@@ -405,6 +405,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const ConvGemmParams p
             ptx::mbar_wait(&tmem_full[acc_cur], acc_ph_cur);
             ptx::tc_fence_after();
             const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc_cur * (uint32_t)p.n_tile;
+            const bool in_img = x < p.W && y < p.H;          // partial tiles at the right / bottom image border
             for (int c32 = 0; c32 < p.n_tile / 32; ++c32) {
                 uint32_t r[32];
                 if (!(p.dbg & 4)) {
@@ -436,7 +437,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const ConvGemmParams p
                 if (p.act == ACT_LRELU) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.2f * v[j]);
-                } else if (p.act == ACT_MASK) {
+                } else if (p.act == ACT_MASK && in_img) {
                     const uint4* ap = reinterpret_cast<const uint4*>(
                         p.aux + ((size_t)(img * p.H + y) * p.W + x) * p.aux_pitch + p.aux_c0 + col);
 #pragma unroll
@@ -453,6 +454,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const ConvGemmParams p
                         }
                     }
                 }
+                if (!in_img) continue;
                 uint4* d4 = reinterpret_cast<uint4*>(dst);
                 if (p.dbg & 1) d4 = reinterpret_cast<uint4*>(p.out + (size_t)threadIdx.x * 32);   // one hot line per thread
 #pragma unroll

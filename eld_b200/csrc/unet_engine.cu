@@ -252,8 +252,9 @@ extern "C" int eld_unet_create(eld_ctx* ctx, int n, int h, int w, int train, voi
 {
     ELD_REQUIRE(ctx && out && workspace, "eld_unet_create: NULL argument");
     ELD_REQUIRE(n > 0 && h > 0 && w > 0, "eld_unet_create: bad shape");
-    ELD_REQUIRE(h % 128 == 0 && w % 256 == 0,
-                "eld_unet_create: the tcgen05 tiles need H %% 128 == 0 and W %% 256 == 0 (8x16 patches at 1/16 scale); got %dx%d", h, w);
+    ELD_REQUIRE(h % 16 == 0 && w % 16 == 0, "eld_unet_create: H and W must be multiples of 16 (four 2x2 pools, like the reference); got %dx%d", h, w);
+    ELD_REQUIRE(!train || (h % 128 == 0 && w % 256 == 0),
+                "eld_unet_create: TRAINING needs H %% 128 == 0 and W %% 256 == 0 (whole 8x16 / 8x8 gradient tiles at 1/16 scale); got %dx%d", h, w);
     eld_unet* u = new (std::nothrow) eld_unet();
     ELD_REQUIRE(u, "eld_unet_create: out of host memory");
     u->ctx = ctx; u->n = n; u->H = h; u->W = w;

@@ -30,7 +30,10 @@ static int encode(eld_ctx* ctx, CUtensorMap* map, const void* ptr, int rank, con
 
 int launch_conv_gemm(eld_ctx* ctx, const GemmOp& op, cudaStream_t st)
 {
-    ELD_REQUIRE(op.H % 8 == 0 && op.W % 16 == 0, "conv tile: H=%d must be a multiple of 8 and W=%d of 16", op.H, op.W);
+    // Partial tiles are fine for the A_CONV modes (TMA zero-fills out-of-image rows, the epilogue masks its stores);
+    // the gather mode merges (image, row) into one tensor-map dimension and therefore needs whole 8-row tiles.
+    ELD_REQUIRE(op.a_mode == A_CONV || (op.H % 8 == 0 && op.W % 16 == 0),
+                "deconv dgrad tile: H=%d must be a multiple of 8 and W=%d of 16", op.H, op.W);
     ELD_REQUIRE(op.cin % 32 == 0, "conv tile: cin=%d must be a multiple of 32", op.cin);
     ELD_REQUIRE(op.n_total % 32 == 0, "conv tile: GEMM N=%d must be a multiple of 32", op.n_total);
     ELD_REQUIRE(op.a_pitch % 8 == 0 && op.out_pitch % 8 == 0, "conv tile: pitches must be multiples of 8 channels");
@@ -60,18 +63,18 @@ int launch_conv_gemm(eld_ctx* ctx, const GemmOp& op, cudaStream_t st)
     // bits, so a K-major operand may start at any 16-byte-aligned pixel row of a TMA-written tile and its
     // 8-row groups may be any stride apart (base_offset left 0; setting it to (start>>7)&7 gives wrong
     // results).  One {kc,10,18} box then serves all nine taps.
-    if (p.b_res && !getenv("ELD_CONV_NOHALO2") && op.H % 16 == 0 && op.W % 8 == 0) {
+    if (p.b_res && !getenv("ELD_CONV_NOHALO2")) {
         p.halo = 2; p.tile_w = 8;
         p.bo_mode = getenv("ELD_CONV_BO") ? atoi(getenv("ELD_CONV_BO")) : 0;
     }
     // streamed weights + full-halo activations for every other conv3x3 (two rings)
     p.b_stages = 0;
     // (measured: for n_tile == 64 the per-tap barrier round trip costs more than the rows it saves - keep halo == 1)
-    if (!p.b_res && op.a_mode == A_CONV && op.taps == 9 && p.n_tile >= 128 && !getenv("ELD_CONV_NOHALO3") &&
-        op.H % 16 == 0 && op.W % 8 == 0) {
+    if (!p.b_res && op.a_mode == A_CONV && op.taps == 9 && p.n_tile >= 128 && !getenv("ELD_CONV_NOHALO3")) {
         p.halo = 3; p.tile_w = 8;
     }
-    p.tiles_x = op.W / p.tile_w; p.tiles_y = op.H / (128 / p.tile_w);
+    p.tiles_x = (op.W + p.tile_w - 1) / p.tile_w;
+    p.tiles_y = (op.H + (128 / p.tile_w) - 1) / (128 / p.tile_w);
     const int stage_bytes = p.halo >= 2 ? ((180 * rb + 1023) & ~1023)
                                         : (p.halo ? 160 : 128) * rb + (p.b_res ? 0 : (p.halo ? 3 : 1) * b_tile);
     int stages = (budget - (p.b_res ? b_total : 0)) / stage_bytes;

@@ -167,8 +167,10 @@ class ELDModel(BaseModel):
         return output
 
     def _padded_forward(self, x):
+        """the engine runs any H, W that are multiples of 16 exactly (like the reference network); other sizes
+        are replicate-padded up to the next multiple of 16 and cropped (the reference cannot run them at all)."""
         h, w = x.shape[2:]
-        H, W = -(-h // 128) * 128, -(-w // 256) * 256
+        H, W = -(-h // 16) * 16, -(-w // 16) * 16
         if (H, W) != (h, w):
             x = torch.nn.functional.pad(x, (0, W - w, 0, H - h), mode='replicate')
         return self.netG(x.contiguous())[:, :, :h, :w]

@@ -25,7 +25,7 @@ int eld_pack_weights(eld_ctx* ctx, const float* w, void* packed_bf16, int cout, 
 
 /* y[n,h,w,y_c0:y_c0+cout] = act( conv3x3_pad1(x[n,h,w,x_c0:x_c0+cin]) + bias )   nn.Conv2d(k=3,p=1), Unet.py:11-44.
  * With ELD_PACK_CONV_DGRAD weights (cin/cout swapped) the same tile is the data gradient.
- * h % 8 == 0, w % 16 == 0, cin % 32 == 0, cout % 32 == 0.  bias may be NULL. */
+ * cin % 32 == 0, cout % 32 == 0; any h, w (partial tiles are masked).  bias may be NULL. */
 int eld_conv3x3_bf16(eld_ctx* ctx, const void* x, int x_pitch, int x_c0, int cin, const void* w_packed,
                      const float* bias, void* y, int y_pitch, int y_c0, int cout, int n, int h, int w,
                      int act, const void* aux, int aux_pitch, int aux_c0, void* stream);
@@ -62,7 +62,8 @@ typedef struct eld_unet eld_unet;
 size_t eld_unet_param_count(void);                                   /* 7,760,484 for UNetSeeInDark(4,4) */
 int    eld_unet_param_offset(const char* layer, int is_bias, size_t* offset, size_t* count);
 size_t eld_unet_workspace_bytes(int n, int h, int w, int train);     /* activations (+gradients) + packed weights */
-/* h % 128 == 0, w % 256 == 0.  The caller owns `workspace` (device memory) for the lifetime of the object. */
+/* Inference (train = 0): h % 16 == 0 and w % 16 == 0, as for the reference network.  Training (train = 1):
+ * h % 128 == 0, w % 256 == 0.  The caller owns `workspace` (device memory) for the lifetime of the object. */
 int    eld_unet_create(eld_ctx* ctx, int n, int h, int w, int train, void* workspace, size_t bytes, eld_unet** out);
 void   eld_unet_destroy(eld_unet* u);
 /* ELDModel.forward (ELD_model.py:422-432): x f32 NCHW [n][4][h][w] -> out f32 NCHW [n][4][h][w] */

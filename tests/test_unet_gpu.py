@@ -146,8 +146,24 @@ def test_state_dict_roundtrip_keeps_flat_storage(torch, nets):
     ours.load_state_dict(ref.state_dict())
 
 
+@pytest.mark.parametrize('hw', [(48, 80), (16, 16), (208, 144)])
+def test_inference_any_multiple_of_16(torch, nets, hw):
+    """Inference runs exactly on any H, W % 16 == 0 (partial tiles: TMA zero fill + masked stores), e.g. the
+    1424 x 2128 full frames of test_ELD.py; compared with the oracle incl. the image borders."""
+    ours, ref = nets
+    torch.manual_seed(5)
+    x = torch.rand(2, 4, *hw)
+    with torch.no_grad():
+        want = ref(x)
+    got = ours(x.cuda()).cpu()
+    assert _rel(got, want) <= 2e-2, _rel(got, want)
+    assert _rel(got[:, :, -4:, -4:], want[:, :, -4:, -4:]) <= 5e-2          # bottom-right corner pixels
+
+
 def test_shape_contract(torch, nets):
     from eld_b200 import _lib
     ours, _ = nets
     with pytest.raises(_lib.EldError):
-        ours(torch.rand(1, 4, 64, 64, device='cuda'))
+        ours(torch.rand(1, 4, 40, 64, device='cuda'))                        # not a multiple of 16
+    with pytest.raises(_lib.EldError):
+        ours.train_step(torch.rand(1, 4, 64, 64, device='cuda'), torch.rand(1, 4, 64, 64, device='cuda'))
