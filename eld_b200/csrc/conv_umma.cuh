@@ -46,8 +46,11 @@ struct ConvGemmParams {
     const uint8_t* b_ptr; // packed weights: blocks [n_tile][tap][chunk] in smem-image order (unet_prims.h packed_index)
     int b_stages;         // halo == 3: depth of the separate weight ring
     int l2_prefetch;      // full-halo mode: prefetch the A box this many tiles ahead into L2 (0 = off)
-    int dbg;              // experiments only (ELD_CONV_DBG): 1 = skip the global stores, 2 = skip bias, 4 = skip tcgen05.ld
-    int acc_stages;       // TMEM accumulator ring depth (2..8): acc_stages * n_tile <= 512 columns
+    int dbg;              // experiments only (ELD_CONV_DBG): 1 = skip the global stores, 2 = skip bias, 4 = skip tcgen05.ld,
+                          // 8 = skip the activation TMA loads (full-halo modes), 16 = skip the MMAs
+    int acc_stages;       // TMEM accumulator ring depth (2..8, even): acc_stages * n_tile <= 512 columns
+    int cout_shift;       // EPI_SHUFFLE: log2(cout) (cout must be a power of two)
+    int bias_smem_off;    // byte offset (from the 1024-aligned base) of the per-CTA bias copy
 };
 
 // Two tiles at once: consecutive MMAs alternate between two accumulators, so an N = 32 tile's chain of
@@ -119,6 +122,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const ConvGemmParams p
     uint64_t* bfull = bres_full + 1;               // halo == 3 weight ring (<= 8 stages)
     uint64_t* bempty = bfull + 8;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bempty + 8);
+    float* s_bias = reinterpret_cast<float*>(smem + p.bias_smem_off);      // bias staged once per CTA (16-byte aligned)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_tiles = p.n_total / p.n_tile;
@@ -136,6 +140,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const ConvGemmParams p
         ptx::fence_barrier_init();
     }
     if (warp == 2) ptx::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    if (p.bias) {
+        const int nb = p.epi_mode == EPI_STORE ? p.n_total : p.cout;
+        for (int i = threadIdx.x; i < nb; i += kConvThreads) s_bias[i] = __ldg(p.bias + i);
+    }
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
@@ -165,8 +173,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const ConvGemmParams p
                     int c = p.a_c0;
                     for (int kcI = 0; kcI < kchunks; ++kcI) {
                         ptx::mbar_wait(&empty[s], ph ^ 1u);
-                        ptx::mbar_arrive_expect_tx(&full[s], (uint32_t)(180 * row_bytes));
-                        ptx::tma_load_5d(sa, &tmA, &full[s], c, x0 - 1, y0 - 1, img, 0);
+                        if (p.dbg & 8) ptx::mbar_arrive(&full[s]);
+                        else {
+                            ptx::mbar_arrive_expect_tx(&full[s], (uint32_t)(180 * row_bytes));
+                            ptx::tma_load_5d(sa, &tmA, &full[s], c, x0 - 1, y0 - 1, img, 0);
+                        }
                         for (int tap = 0; tap < 9; ++tap) {
                             ptx::mbar_wait(&bempty[sb], bph ^ 1u);
                             ptx::mbar_arrive_expect_tx(&bfull[sb], (uint32_t)b_bytes);
@@ -196,8 +207,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const ConvGemmParams p
                     int c = p.a_c0;
                     for (int kcI = 0; kcI < kchunks; ++kcI) {
                         ptx::mbar_wait(&empty[s], ph ^ 1u);
-                        ptx::mbar_arrive_expect_tx(&full[s], (uint32_t)(180 * row_bytes));
-                        ptx::tma_load_5d(sa, &tmA, &full[s], c, x0 - 1, y0 - 1, img, 0);
+                        if (p.dbg & 8) ptx::mbar_arrive(&full[s]);
+                        else {
+                            ptx::mbar_arrive_expect_tx(&full[s], (uint32_t)(180 * row_bytes));
+                            ptx::tma_load_5d(sa, &tmA, &full[s], c, x0 - 1, y0 - 1, img, 0);
+                        }
                         c += p.kc;
                         sa += stage_bytes;
                         if (++s == p.stages) { s = 0; ph ^= 1u; sa = stage0; }
@@ -289,11 +303,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const ConvGemmParams p
                 ptx::mbar_wait(&full[s0], sph0);
                 ptx::mbar_wait(&full[s1], sph1);
                 ptx::tc_fence_after();
-                if (lane == 0) {
+                if (ptx::elect_one()) {
                     const uint32_t d0 = tmem_base + acc0 * (uint32_t)p.n_tile, d1 = tmem_base + acc1 * (uint32_t)p.n_tile;
                     const uint32_t a0_lo = (uint32_t)a_hi64 | ((a0 & 0x3FFFFu) >> 4), a1_lo = (uint32_t)a_hi64 | ((a1 & 0x3FFFFu) >> 4);
-                    if (ksub == 2) issue_halo2_pair<2>(d0, d1, a0_lo, a1_lo, a_hi, b_lo, (uint32_t)(desc_hi >> 32), b_step, idesc);
-                    else           issue_halo2_pair<4>(d0, d1, a0_lo, a1_lo, a_hi, b_lo, (uint32_t)(desc_hi >> 32), b_step, idesc);
+                    if (p.dbg & 16) { }
+                    else if (ksub == 2) issue_halo2_pair<2>(d0, d1, a0_lo, a1_lo, a_hi, b_lo, (uint32_t)(desc_hi >> 32), b_step, idesc);
+                    else                issue_halo2_pair<4>(d0, d1, a0_lo, a1_lo, a_hi, b_lo, (uint32_t)(desc_hi >> 32), b_step, idesc);
                     ptx::umma_commit(&empty[s0]);
                     ptx::umma_commit(&empty[s1]);
                     ptx::umma_commit(&tmem_full[acc0]);
@@ -321,14 +336,17 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const ConvGemmParams p
                     for (int tap = 0; tap < 9; ++tap) {
                         ptx::mbar_wait(&bfull[sb], bph);
                         ptx::tc_fence_after();
-                        if (lane == 0) {
+                        if (ptx::elect_one()) {
                             const int kh = tap / 3, kw = tap - 3 * kh;
                             const uint32_t at = a_lo + (uint32_t)(kh * 10 + kw) * krow;
                             const uint32_t bt = (uint32_t)desc_hi | (((bring_base + (uint32_t)sb * (uint32_t)b_bytes) & 0x3FFFFu) >> 4);
+                            if (p.dbg & 16) { }
+                            else {
                             if (ks == 0 && tap == 0) ptx::umma_bf16_lohi(d_tmem, at, a_hi32, bt, b_hi32, idesc, false);
                             else                     ptx::umma_bf16_lohi(d_tmem, at, a_hi32, bt, b_hi32, idesc, true);
                             for (int k = 1; k < ksub; ++k)
                                 ptx::umma_bf16_lohi(d_tmem, at + 2u * k, a_hi32, bt + 2u * k, b_hi32, idesc, true);
+                            }
                             ptx::umma_commit(&bempty[sb]);
                             if (tap == 8) {
                                 ptx::umma_commit(&empty[s]);
@@ -346,17 +364,19 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const ConvGemmParams p
             for (int ks = 0; ks < ksteps; ++ks) {
                 ptx::mbar_wait(&full[s], ph);
                 ptx::tc_fence_after();
-                if (lane == 0 && p.halo == 2) {
+                const bool leader = ptx::elect_one();
+                if (leader && p.halo == 2) {
                     // ks = channel chunk; 9 taps, each a shifted view of the same halo tile
                     const uint64_t a_hi64 = ptx::make_smem_desc(0, 16, 10u * row_bytes, layout);
                     const uint32_t a_lo = (uint32_t)a_hi64 | ((a_addr & 0x3FFFFu) >> 4);
                     const uint32_t b_lo = (uint32_t)desc_hi | (((bres_base + (uint32_t)ks * (uint32_t)b_bytes) & 0x3FFFFu) >> 4);
                     const uint32_t b_tap_step = (uint32_t)kchunks * b_step;
-                    if (ksub == 2) issue_halo2<2>(d_tmem, a_lo, (uint32_t)(a_hi64 >> 32), b_lo, (uint32_t)(desc_hi >> 32), b_tap_step, idesc, ks == 0);
+                    if (p.dbg & 16) { }
+                    else if (ksub == 2) issue_halo2<2>(d_tmem, a_lo, (uint32_t)(a_hi64 >> 32), b_lo, (uint32_t)(desc_hi >> 32), b_tap_step, idesc, ks == 0);
                     else           issue_halo2<4>(d_tmem, a_lo, (uint32_t)(a_hi64 >> 32), b_lo, (uint32_t)(desc_hi >> 32), b_tap_step, idesc, ks == 0);
                     ptx::umma_commit(&empty[s]);
                     if (ks == ksteps - 1) ptx::umma_commit(&tmem_full[acc_cur]);
-                } else if (lane == 0) {
+                } else if (leader) {
                     uint64_t ad0 = desc_hi | (uint64_t)((a_addr & 0x3FFFFu) >> 4);
                     uint64_t bd0;
                     uint32_t b_sub_step;                       // descriptor units between the B tiles of taps kh, kh+1
@@ -388,75 +408,87 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const ConvGemmParams p
         }
     } else {
         // ===================== epilogue: group 0 = warps 2..5 (even tiles), group 1 = warps 6..9 (odd tiles) =====
+        // Two warps per scheduler cannot hide ALU latency, so the per-tile instruction count IS the epilogue's
+        // speed (measured: the old ~650-instruction body bounded every N = 32 layer).  No divisions (tile
+        // coordinates advance incrementally), bias from shared memory, LeakyReLU' from the sign bit.
         const uint32_t egroup = (uint32_t)(warp - 2) >> 2;
         const int q = warp & 3;                // TMEM lane quarter this warp may read
-        const int m = q * 32 + lane;           // pixel inside the 8x16 patch
-        const int py = m / p.tile_w, px = m % p.tile_w;
-        uint32_t tile_it = 0, acc = 0, acc_ph = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_it) {
-            const uint32_t acc_cur = acc, acc_ph_cur = acc_ph;
-            if (++acc == (uint32_t)p.acc_stages) { acc = 0; acc_ph ^= 1u; }
-            if ((tile_it & 1u) != egroup) continue;
-            const int m_tile = tile / n_tiles, n_t = tile - m_tile * n_tiles;
-            const int img = m_tile / (p.tiles_x * p.tiles_y);
-            const int rem = m_tile - img * (p.tiles_x * p.tiles_y);
-            const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
-            const int x = tx * p.tile_w + px, y = ty * (128 / p.tile_w) + py;
-            ptx::mbar_wait(&tmem_full[acc_cur], acc_ph_cur);
-            ptx::tc_fence_after();
-            const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc_cur * (uint32_t)p.n_tile;
+        const int m = q * 32 + lane;           // pixel inside the patch
+        const int py = p.tile_w == 8 ? (m >> 3) : (m >> 4), px = m & (p.tile_w - 1);
+        // decomposition of this group's first tile and of its stride (2 * gridDim.x) into (n_t, tx, ty, img) digits
+        int t0 = (int)blockIdx.x + (int)egroup * (int)gridDim.x;
+        int n_t = t0 % n_tiles; t0 /= n_tiles;
+        int tx = t0 % p.tiles_x; t0 /= p.tiles_x;
+        int ty = t0 % p.tiles_y;
+        int img = t0 / p.tiles_y;
+        int g0 = 2 * (int)gridDim.x;
+        const int d_nt = g0 % n_tiles; g0 /= n_tiles;
+        const int d_tx = g0 % p.tiles_x; g0 /= p.tiles_x;
+        const int d_ty = g0 % p.tiles_y;
+        const int d_img = g0 / p.tiles_y;
+        uint32_t acc = egroup, acc_ph = 0;     // acc_stages is even: this group's accumulators are acc = egroup, +2, ...
+        const int tile_hh = 128 / p.tile_w;
+        const float4* sb4 = reinterpret_cast<const float4*>(s_bias);
+        for (int tile = (int)blockIdx.x + (int)egroup * (int)gridDim.x; tile < total_tiles; tile += 2 * (int)gridDim.x) {
+            const int x = tx * p.tile_w + px, y = ty * tile_hh + py;
             const bool in_img = x < p.W && y < p.H;          // partial tiles at the right / bottom image border
-            for (int c32 = 0; c32 < p.n_tile / 32; ++c32) {
+            const int pix = (img * p.H + y) * p.W + x;
+            const int col0 = n_t * p.n_tile;
+            const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)p.n_tile;
+            ptx::mbar_wait(&tmem_full[acc], acc_ph);
+            ptx::tc_fence_after();
+            for (int c32 = 0; c32 < p.n_tile; c32 += 32) {
                 uint32_t r[32];
-                if (!(p.dbg & 4)) {
-                    ptx::tmem_ld32(t_addr + c32 * 32, r);
-                    ptx::tmem_ld_wait();
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) r[j] = 0x3F800000u + j;
-                }
-                const int col = n_t * p.n_tile + c32 * 32;    // first GEMM column of this chunk
+                ptx::tmem_ld32(t_addr + c32, r);
+                const int col = col0 + c32;                   // first GEMM column of this chunk
                 __nv_bfloat16* dst;
                 int bcol;
                 if (p.epi_mode == EPI_STORE) {
-                    dst = p.out + ((size_t)(img * p.H + y) * p.W + x) * p.out_pitch + p.out_c0 + col;
+                    dst = p.out + (size_t)pix * p.out_pitch + (p.out_c0 + col);
                     bcol = col;
                 } else {
-                    const int sub = col / p.cout, co = col - sub * p.cout;   // sub = kh*2 + kw
+                    const int sub = col >> p.cout_shift, co = col & (p.cout - 1);   // sub = kh*2 + kw
                     const int oy = 2 * y + (sub >> 1), ox = 2 * x + (sub & 1);
                     dst = p.out + ((size_t)(img * 2 * p.H + oy) * (2 * p.W) + ox) * p.out_pitch + p.out_c0 + co;
                     bcol = co;
                 }
+                uint4 mk[4];
+                if (p.act == ACT_MASK && in_img) {
+                    const uint4* ap = reinterpret_cast<const uint4*>(p.aux + (size_t)pix * p.aux_pitch + (p.aux_c0 + col));
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) mk[g] = __ldg(ap + g);
+                }
+                ptx::tmem_ld_wait();
                 float v[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
                 if (p.bias && !(p.dbg & 2)) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] += __ldg(p.bias + bcol + j);
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 b = sb4[(bcol >> 2) + j];
+                        v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+                    }
                 }
                 if (p.act == ACT_LRELU) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.2f * v[j]);
                 } else if (p.act == ACT_MASK && in_img) {
-                    const uint4* ap = reinterpret_cast<const uint4*>(
-                        p.aux + ((size_t)(img * p.H + y) * p.W + x) * p.aux_pitch + p.aux_c0 + col);
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
-                        const uint4 a = __ldg(ap + g);
-                        const uint32_t aw[4] = { a.x, a.y, a.z, a.w };
+                        const uint32_t aw[4] = { mk[g].x, mk[g].y, mk[g].z, mk[g].w };
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            // bf16 sign bits: activation > 0 <=> pre-activation > 0 (LeakyReLU keeps sign)
-                            const bool pos_lo = !(aw[j] & 0x8000u) && (aw[j] & 0x7FFFu);
-                            const bool pos_hi = !(aw[j] & 0x80000000u) && (aw[j] & 0x7FFF0000u);
-                            v[g * 8 + 2 * j] *= pos_lo ? 1.0f : 0.2f;
-                            v[g * 8 + 2 * j + 1] *= pos_hi ? 1.0f : 0.2f;
+                            // LeakyReLU keeps the sign: slope = 0.6 + 0.4 * sign(activation) = 1 or 0.2
+                            // (activation == +0 counts as positive; the reference's tie is a measure-zero event)
+                            const float s_lo = __uint_as_float(((aw[j] << 16) & 0x80000000u) | 0x3F800000u);
+                            const float s_hi = __uint_as_float((aw[j] & 0x80000000u) | 0x3F800000u);
+                            v[g * 8 + 2 * j] *= __fmaf_rn(s_lo, 0.4f, 0.6f);
+                            v[g * 8 + 2 * j + 1] *= __fmaf_rn(s_hi, 0.4f, 0.6f);
                         }
                     }
                 }
-                if (!in_img) continue;
+                if (!in_img || (p.dbg & 1)) continue;
                 uint4* d4 = reinterpret_cast<uint4*>(dst);
-                if (p.dbg & 1) d4 = reinterpret_cast<uint4*>(p.out + (size_t)threadIdx.x * 32);   // one hot line per thread
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
                     uint32_t w[4];
@@ -470,7 +502,18 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const ConvGemmParams p
             }
             ptx::tc_fence_before();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc_cur]);
+            if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+            acc += 2;
+            if (acc >= (uint32_t)p.acc_stages) { acc -= (uint32_t)p.acc_stages; acc_ph ^= 1u; }
+            // next tile of this group: add the stride digit-wise with carries
+            n_t += d_nt;
+            int cy = 0;
+            if (n_t >= n_tiles) { n_t -= n_tiles; cy = 1; }
+            tx += d_tx + cy; cy = 0;
+            if (tx >= p.tiles_x) { tx -= p.tiles_x; cy = 1; }
+            ty += d_ty + cy; cy = 0;
+            if (ty >= p.tiles_y) { ty -= p.tiles_y; cy = 1; }
+            img += d_img + cy;
         }
     }
     ptx::tc_fence_before();

@@ -46,6 +46,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
     while (!mbar_try_wait(bar, parity)) { }
 }
 
+// one lane of a CONVERGED warp (elect.sync): unlike `lane == 0`, ptxas knows a single thread is active and
+// issues the tcgen05 / TMA instruction straight from uniform registers (no per-instruction waterfall loop)
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xFFFFFFFF;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- TMA ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m)
 {

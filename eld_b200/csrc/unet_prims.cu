@@ -116,8 +116,16 @@ int launch_conv_gemm(eld_ctx* ctx, const GemmOp& op, cudaStream_t st)
         if (rc) return rc;
     }
     p.b_ptr = static_cast<const uint8_t*>(op.b);
-    const size_t smem = (size_t)stages * stage_bytes + (p.b_res ? b_total : 0) + (size_t)p.b_stages * b_tile +
-                        1024 /*align slack*/ + 768 /*barriers*/;
+    const size_t ring_bytes = (size_t)stages * stage_bytes + (p.b_res ? b_total : 0) + (size_t)p.b_stages * b_tile;
+    p.bias_smem_off = (int)ring_bytes + 768;                      // barriers (<= 53 x 8 B + slot) live in the first 768 B
+    const int n_bias = op.epi_mode == EPI_STORE ? op.n_total : op.cout;
+    ELD_REQUIRE(n_bias <= 1024, "conv tile: %d bias entries exceed the 4 KB shared-memory copy", n_bias);
+    p.cout_shift = 0;
+    if (op.epi_mode == EPI_SHUFFLE) {
+        ELD_REQUIRE(op.cout > 0 && (op.cout & (op.cout - 1)) == 0, "deconv tile: cout=%d must be a power of two", op.cout);
+        while ((1 << p.cout_shift) < op.cout) ++p.cout_shift;
+    }
+    const size_t smem = ring_bytes + 1024 /*align slack*/ + 768 /*barriers*/ + 4096 /*bias*/;
     const int total_tiles = op.n_img * p.tiles_x * p.tiles_y * (p.n_total / p.n_tile);
     const int grid = total_tiles < ctx->num_sms ? total_tiles : ctx->num_sms;
     conv_umma_kernel<<<grid, kConvThreads, smem, st>>>(tmA, p);
@@ -129,7 +137,7 @@ int launch_conv_gemm(eld_ctx* ctx, const GemmOp& op, cudaStream_t st)
 int init_gemm_kernels(eld_ctx* ctx)
 {
     ELD_CHECK_CUDA(cudaSetDevice(ctx->device));
-    ELD_CHECK_CUDA(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    ELD_CHECK_CUDA(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     ELD_CHECK_CUDA(cudaFuncSetAttribute(wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     ELD_CHECK_CUDA(cudaFuncSetAttribute(wgrad_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     return ELD_OK;

@@ -144,7 +144,7 @@ wgrad_conv_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant
         for (int i = 0; i < nchunks; ++i) {
             ptx::mbar_wait(&full[s], ph);
             ptx::tc_fence_after();
-            if (lane == 0) {
+            if (ptx::elect_one()) {
                 const uint32_t a_st = (st_addr & 0x3FFFFu) >> 4;
                 const uint32_t b_lo0 = b_lo_c + (((st_addr + (uint32_t)p_bytes) & 0x3FFFFu) >> 4);
                 // g outermost (4 consecutive K steps per accumulator): measured faster than k-outermost on B200

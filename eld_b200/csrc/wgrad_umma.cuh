@@ -139,7 +139,7 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant
         for (int i = 0; i < nchunks; ++i) {
             ptx::mbar_wait(&full[s], ph);
             ptx::tc_fence_after();
-            if (lane == 0) {
+            if (ptx::elect_one()) {
                 uint64_t ad = a_hi | (uint64_t)((a_addr & 0x3FFFFu) >> 4);
                 uint64_t bd = b_hi | (uint64_t)(((a_addr + (uint32_t)a_bytes) & 0x3FFFFu) >> 4);
 #pragma unroll
