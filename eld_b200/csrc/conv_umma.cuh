@@ -50,6 +50,7 @@ struct ConvGemmParams {
                           // 8 = skip the activation TMA loads (full-halo modes), 16 = skip the MMAs
     int acc_stages;       // TMEM accumulator ring depth (2..8, even): acc_stages * n_tile <= 512 columns
     int cout_shift;       // EPI_SHUFFLE: log2(cout) (cout must be a power of two)
+    long long* prof;      // PROF instantiation only
     int bias_smem_off;    // byte offset (from the 1024-aligned base) of the per-CTA bias copy
 };
 
@@ -92,9 +93,20 @@ __device__ __forceinline__ void issue_halo2(uint32_t d_tmem, uint32_t a_lo, uint
     }
 }
 
+// PROF = true (ELD_CONV_PROF, debugging only): every role accumulates the cycles it spends blocked on each kind of
+// barrier and writes them to p.prof[blockIdx.x][16] - who waits for whom, per layer.
+#define ELD_WAIT(bar, par, ctr)                                                                    \
+    do {                                                                                           \
+        if (PROF) { const long long t_ = clock64(); ptx::mbar_wait((bar), (par)); (ctr) += clock64() - t_; } \
+        else ptx::mbar_wait((bar), (par));                                                         \
+    } while (0)
+
+template <bool PROF>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const ConvGemmParams p)
 {
+    long long pw0 = 0, pw1 = 0, pt0 = 0;
+    if (PROF) pt0 = clock64();
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = ptx::smem_u32(smem_raw);
     uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
@@ -172,14 +184,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const ConvGemmParams p
                 if (p.halo == 3) {
                     int c = p.a_c0;
                     for (int kcI = 0; kcI < kchunks; ++kcI) {
-                        ptx::mbar_wait(&empty[s], ph ^ 1u);
+                        ELD_WAIT(&empty[s], ph ^ 1u, pw0);
                         if (p.dbg & 8) ptx::mbar_arrive(&full[s]);
                         else {
                             ptx::mbar_arrive_expect_tx(&full[s], (uint32_t)(180 * row_bytes));
                             ptx::tma_load_5d(sa, &tmA, &full[s], c, x0 - 1, y0 - 1, img, 0);
                         }
                         for (int tap = 0; tap < 9; ++tap) {
-                            ptx::mbar_wait(&bempty[sb], bph ^ 1u);
+                            ELD_WAIT(&bempty[sb], bph ^ 1u, pw1);
                             ptx::mbar_arrive_expect_tx(&bfull[sb], (uint32_t)b_bytes);
                             ptx::bulk_load(bring0 + (size_t)sb * b_bytes,
                                            p.b_ptr + ((size_t)(n_t * 9 + tap) * kchunks + kcI) * b_bytes, (uint32_t)b_bytes, &bfull[sb]);
@@ -206,7 +218,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const ConvGemmParams p
                     }
                     int c = p.a_c0;
                     for (int kcI = 0; kcI < kchunks; ++kcI) {
-                        ptx::mbar_wait(&empty[s], ph ^ 1u);
+                        ELD_WAIT(&empty[s], ph ^ 1u, pw0);
                         if (p.dbg & 8) ptx::mbar_arrive(&full[s]);
                         else {
                             ptx::mbar_arrive_expect_tx(&full[s], (uint32_t)(180 * row_bytes));
@@ -222,7 +234,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const ConvGemmParams p
                     for (int kw = 0; kw < 3; ++kw) {
                         int c = p.a_c0;
                         for (int kcI = 0; kcI < kchunks; ++kcI) {
-                            ptx::mbar_wait(&empty[s], ph ^ 1u);
+                            ELD_WAIT(&empty[s], ph ^ 1u, pw0);
                             ptx::mbar_arrive_expect_tx(&full[s], (uint32_t)stage_bytes);
                             ptx::tma_load_5d(sa, &tmA, &full[s], c, x0 + kw - 1, y0 - 1, img, 0);
                             if (!p.b_res) {
@@ -252,7 +264,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const ConvGemmParams p
                     }
                     int c = p.a_c0;
                     for (int kcI = 0; kcI < kchunks; ++kcI) {
-                        ptx::mbar_wait(&empty[s], ph ^ 1u);
+                        ELD_WAIT(&empty[s], ph ^ 1u, pw0);
                         ptx::mbar_arrive_expect_tx(&full[s], (uint32_t)stage_bytes);
                         ptx::tma_load_5d(sa, &tmA, &full[s], c, c1, c2, c3, c4);
                         if (!p.b_res) ptx::bulk_load(sa + a_bytes, p.b_ptr + ((size_t)(n_t * p.taps + tap) * kchunks + kcI) * b_bytes,
@@ -292,16 +304,16 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const ConvGemmParams p
                 if (++acc == (uint32_t)p.acc_stages) { acc = 0; acc_ph ^= 1u; }
                 const uint32_t acc1 = acc, ph1 = acc_ph;
                 if (++acc == (uint32_t)p.acc_stages) { acc = 0; acc_ph ^= 1u; }
-                ptx::mbar_wait(&tmem_empty[acc0], ph0 ^ 1u);
-                ptx::mbar_wait(&tmem_empty[acc1], ph1 ^ 1u);
+                ELD_WAIT(&tmem_empty[acc0], ph0 ^ 1u, pw0);
+                ELD_WAIT(&tmem_empty[acc1], ph1 ^ 1u, pw0);
                 const int s0 = s; const uint32_t sph0 = ph; const uint32_t a0 = a_addr;
                 a_addr += (uint32_t)stage_bytes;
                 if (++s == p.stages) { s = 0; ph ^= 1u; a_addr = stage_base; }
                 const int s1 = s; const uint32_t sph1 = ph; const uint32_t a1 = a_addr;
                 a_addr += (uint32_t)stage_bytes;
                 if (++s == p.stages) { s = 0; ph ^= 1u; a_addr = stage_base; }
-                ptx::mbar_wait(&full[s0], sph0);
-                ptx::mbar_wait(&full[s1], sph1);
+                ELD_WAIT(&full[s0], sph0, pw1);
+                ELD_WAIT(&full[s1], sph1, pw1);
                 ptx::tc_fence_after();
                 if (ptx::elect_one()) {
                     const uint32_t d0 = tmem_base + acc0 * (uint32_t)p.n_tile, d1 = tmem_base + acc1 * (uint32_t)p.n_tile;
@@ -321,7 +333,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const ConvGemmParams p
         uint32_t bph = 0;
         const uint32_t bring_base = ptx::smem_u32(bring0);
         for (; tile < total_tiles; tile += gridDim.x, ++tile_it) {
-            ptx::mbar_wait(&tmem_empty[acc], acc_ph ^ 1u);
+            ELD_WAIT(&tmem_empty[acc], acc_ph ^ 1u, pw0);
             ptx::tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.n_tile;
             const uint32_t acc_cur = acc;
@@ -331,10 +343,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const ConvGemmParams p
                 const uint32_t a_hi32 = (uint32_t)(a_hi64 >> 32), b_hi32 = (uint32_t)(desc_hi >> 32);
                 const uint32_t krow = (uint32_t)row_bytes >> 4;
                 for (int ks = 0; ks < ksteps; ++ks) {                 // ks = channel chunk
-                    ptx::mbar_wait(&full[s], ph);
+                    ELD_WAIT(&full[s], ph, pw1);
                     const uint32_t a_lo = (uint32_t)a_hi64 | ((a_addr & 0x3FFFFu) >> 4);
                     for (int tap = 0; tap < 9; ++tap) {
-                        ptx::mbar_wait(&bfull[sb], bph);
+                        ELD_WAIT(&bfull[sb], bph, pw1);
                         ptx::tc_fence_after();
                         if (ptx::elect_one()) {
                             const int kh = tap / 3, kw = tap - 3 * kh;
@@ -362,7 +374,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const ConvGemmParams p
                 continue;
             }
             for (int ks = 0; ks < ksteps; ++ks) {
-                ptx::mbar_wait(&full[s], ph);
+                ELD_WAIT(&full[s], ph, pw1);
                 ptx::tc_fence_after();
                 const bool leader = ptx::elect_one();
                 if (leader && p.halo == 2) {
@@ -435,7 +447,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const ConvGemmParams p
             const int pix = (img * p.H + y) * p.W + x;
             const int col0 = n_t * p.n_tile;
             const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)p.n_tile;
-            ptx::mbar_wait(&tmem_full[acc], acc_ph);
+            ELD_WAIT(&tmem_full[acc], acc_ph, pw0);
             ptx::tc_fence_after();
             for (int c32 = 0; c32 < p.n_tile; c32 += 32) {
                 uint32_t r[32];
@@ -515,6 +527,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const ConvGemmParams p
             if (ty >= p.tiles_y) { ty -= p.tiles_y; cy = 1; }
             img += d_img + cy;
         }
+    }
+    if (PROF && lane == 0 && (warp <= 2 || warp == 6)) {
+        // slots: 0-2 producer (total, wait empty, wait bempty) | 3-5 MMA (total, wait tmem_empty, wait full) |
+        //        6-7 epilogue group 0 (total, wait tmem_full) | 8-9 epilogue group 1
+        const int base = warp == 0 ? 0 : warp == 1 ? 3 : warp == 2 ? 6 : 8;
+        long long* o = p.prof + (size_t)blockIdx.x * 16 + base;
+        o[0] = clock64() - pt0; o[1] = pw0;
+        if (warp <= 1) o[2] = pw1;
     }
     ptx::tc_fence_before();
     __syncthreads();

@@ -2,6 +2,8 @@
 // geometry, weight packing, and the C-ABI primitives (include/eld_b200_unet.h).
 #include "common.cuh"
 #include <cstdlib>
+#include <cstdio>
+#include <vector>
 #include "conv_umma.cuh"
 #include "wgrad_umma.cuh"
 #include "wgrad_conv.cuh"
@@ -128,7 +130,25 @@ int launch_conv_gemm(eld_ctx* ctx, const GemmOp& op, cudaStream_t st)
     const size_t smem = ring_bytes + 1024 /*align slack*/ + 768 /*barriers*/ + 4096 /*bias*/;
     const int total_tiles = op.n_img * p.tiles_x * p.tiles_y * (p.n_total / p.n_tile);
     const int grid = total_tiles < ctx->num_sms ? total_tiles : ctx->num_sms;
-    conv_umma_kernel<<<grid, kConvThreads, smem, st>>>(tmA, p);
+    if (getenv("ELD_CONV_PROF")) {          // debugging: per-role barrier-wait cycles of this launch, printed to stderr
+        long long* d = nullptr;
+        ELD_CHECK_CUDA(cudaMalloc(&d, (size_t)grid * 16 * sizeof(long long)));
+        ELD_CHECK_CUDA(cudaMemsetAsync(d, 0, (size_t)grid * 16 * sizeof(long long), st));
+        p.prof = d;
+        conv_umma_kernel<true><<<grid, kConvThreads, smem, st>>>(tmA, p);
+        ELD_CHECK_CUDA(cudaStreamSynchronize(st));
+        std::vector<long long> h((size_t)grid * 16);
+        ELD_CHECK_CUDA(cudaMemcpy(h.data(), d, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        cudaFree(d);
+        double m[16] = { 0 };
+        for (int b = 0; b < grid; ++b) for (int k = 0; k < 16; ++k) m[k] += (double)h[(size_t)b * 16 + k] / grid;
+        fprintf(stderr, "[conv prof] cin %d taps %d N %d/%d HxW %dx%d halo %d tiles/cta %.1f | kclk: prod tot %.1f wE %.1f wBE %.1f | "
+                        "mma tot %.1f wTE %.1f wF %.1f | epi0 tot %.1f wTF %.1f | epi1 tot %.1f wTF %.1f\n",
+                op.cin, op.taps, p.n_tile, p.n_total, op.H, op.W, p.halo, (double)total_tiles / grid,
+                m[0] / 1e3, m[1] / 1e3, m[2] / 1e3, m[3] / 1e3, m[4] / 1e3, m[5] / 1e3, m[6] / 1e3, m[7] / 1e3, m[8] / 1e3, m[9] / 1e3);
+    } else {
+        conv_umma_kernel<false><<<grid, kConvThreads, smem, st>>>(tmA, p);
+    }
     ELD_CHECK_CUDA(cudaGetLastError());
     count_launch(ctx);
     return ELD_OK;
@@ -137,7 +157,8 @@ int launch_conv_gemm(eld_ctx* ctx, const GemmOp& op, cudaStream_t st)
 int init_gemm_kernels(eld_ctx* ctx)
 {
     ELD_CHECK_CUDA(cudaSetDevice(ctx->device));
-    ELD_CHECK_CUDA(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    ELD_CHECK_CUDA(cudaFuncSetAttribute(conv_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    ELD_CHECK_CUDA(cudaFuncSetAttribute(conv_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     ELD_CHECK_CUDA(cudaFuncSetAttribute(wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     ELD_CHECK_CUDA(cudaFuncSetAttribute(wgrad_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     return ELD_OK;
