@@ -44,7 +44,8 @@ struct ConvGemmParams {
     int tile_w;           // 16 (8x16 patch) or 8 (16x8 patch, full-halo mode)
     int bo_mode;          // full-halo mode: 1 = put (start>>7)&7 into the descriptor's base_offset field
     const uint8_t* b_ptr; // packed weights: blocks [n_tile][tap][chunk] in smem-image order (unet_prims.h packed_index)
-    int b_stages;         // halo == 3: depth of the separate weight ring
+    int b_stages;         // halo == 3: depth of the separate weight ring (stages of b_group taps)
+    int b_group;          // halo == 3: filter taps per weight-ring stage (3, or 1 for n_tile == 256)
     int l2_prefetch;      // full-halo mode: prefetch the A box this many tiles ahead into L2 (0 = off)
     int dbg;              // experiments only (ELD_CONV_DBG): 1 = skip the global stores, 2 = skip bias, 4 = skip tcgen05.ld,
                           // 8 = skip the activation TMA loads (full-halo modes), 16 = skip the MMAs
@@ -93,6 +94,31 @@ __device__ __forceinline__ void issue_halo2(uint32_t d_tmem, uint32_t a_lo, uint
     }
 }
 
+// halo == 3: the BG filter taps of one weight-ring stage (taps T0 .. T0+BG-1 of one channel chunk), fully unrolled
+// so that every descriptor offset is an immediate.  flag0 = accumulate flag of the very first MMA (tap 0, k 0).
+template <int KSUB, int BG, int T0>
+__device__ __forceinline__ void issue_halo3_group(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                                  uint32_t b_step, uint32_t idesc, uint32_t flag0)
+{
+    constexpr uint32_t kRow = (uint32_t)(32 * KSUB) >> 4;
+#pragma unroll
+    for (int t = 0; t < BG; ++t) {
+        constexpr int dummy = 0; (void)dummy;
+        const int tap = T0 + t;
+        const uint32_t a_tap = a_lo + (uint32_t)((tap / 3) * 10 + (tap % 3)) * kRow;
+        const uint32_t b_tap = b_lo + (uint32_t)t * b_step;
+#pragma unroll
+        for (int k = 0; k < KSUB; ++k) {
+            if (T0 == 0 && t == 0 && k == 0) {
+                const uint64_t ad = ((uint64_t)a_hi << 32) | a_tap, bd = ((uint64_t)b_hi << 32) | b_tap;
+                ptx::umma_bf16(d_tmem, ad, bd, idesc, flag0);
+            } else {
+                ptx::umma_bf16_lohi(d_tmem, a_tap + 2u * k, a_hi, b_tap + 2u * k, b_hi, idesc, true);
+            }
+        }
+    }
+}
+
 // PROF = true (ELD_CONV_PROF, debugging only): every role accumulates the cycles it spends blocked on each kind of
 // barrier and writes them to p.prof[blockIdx.x][16] - who waits for whom, per layer.
 #define ELD_WAIT(bar, par, ctr)                                                                    \
@@ -125,7 +151,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const ConvGemmParams p
     const int bres_bytes = p.b_res ? p.taps * kchunks * b_bytes : 0;
     uint8_t* stage0 = smem + bres_bytes;
     uint8_t* bring0 = stage0 + (size_t)p.stages * stage_bytes;
-    const int bring_bytes = p.halo == 3 ? p.b_stages * b_bytes : 0;
+    const int bring_bytes = p.halo == 3 ? p.b_stages * p.b_group * b_bytes : 0;
     uint64_t* full = reinterpret_cast<uint64_t*>(bring0 + bring_bytes);
     uint64_t* empty = full + p.stages;
     uint64_t* tmem_full = empty + p.stages;
@@ -190,11 +216,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const ConvGemmParams p
                             ptx::mbar_arrive_expect_tx(&full[s], (uint32_t)(180 * row_bytes));
                             ptx::tma_load_5d(sa, &tmA, &full[s], c, x0 - 1, y0 - 1, img, 0);
                         }
-                        for (int tap = 0; tap < 9; ++tap) {
+                        for (int tap = 0; tap < 9; tap += p.b_group) {     // one ring stage = b_group taps
                             ELD_WAIT(&bempty[sb], bph ^ 1u, pw1);
-                            ptx::mbar_arrive_expect_tx(&bfull[sb], (uint32_t)b_bytes);
-                            ptx::bulk_load(bring0 + (size_t)sb * b_bytes,
-                                           p.b_ptr + ((size_t)(n_t * 9 + tap) * kchunks + kcI) * b_bytes, (uint32_t)b_bytes, &bfull[sb]);
+                            ptx::mbar_arrive_expect_tx(&bfull[sb], (uint32_t)(p.b_group * b_bytes));
+                            for (int t = 0; t < p.b_group; ++t)
+                                ptx::bulk_load(bring0 + ((size_t)sb * p.b_group + t) * b_bytes,
+                                               p.b_ptr + ((size_t)(n_t * 9 + tap + t) * kchunks + kcI) * b_bytes, (uint32_t)b_bytes, &bfull[sb]);
                             if (++sb == p.b_stages) { sb = 0; bph ^= 1u; }
                         }
                         c += p.kc;
@@ -341,33 +368,46 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const ConvGemmParams p
             if (p.halo == 3) {
                 const uint64_t a_hi64 = ptx::make_smem_desc(0, 16, 10u * row_bytes, layout);
                 const uint32_t a_hi32 = (uint32_t)(a_hi64 >> 32), b_hi32 = (uint32_t)(desc_hi >> 32);
-                const uint32_t krow = (uint32_t)row_bytes >> 4;
+                const uint32_t b_ring_lo = (uint32_t)desc_hi | ((bring_base & 0x3FFFFu) >> 4);
+                const uint32_t b_stage_step = (uint32_t)p.b_group * b_step;
                 for (int ks = 0; ks < ksteps; ++ks) {                 // ks = channel chunk
                     ELD_WAIT(&full[s], ph, pw1);
                     const uint32_t a_lo = (uint32_t)a_hi64 | ((a_addr & 0x3FFFFu) >> 4);
-                    for (int tap = 0; tap < 9; ++tap) {
-                        ELD_WAIT(&bfull[sb], bph, pw1);
-                        ptx::tc_fence_after();
-                        if (ptx::elect_one()) {
-                            const int kh = tap / 3, kw = tap - 3 * kh;
-                            const uint32_t at = a_lo + (uint32_t)(kh * 10 + kw) * krow;
-                            const uint32_t bt = (uint32_t)desc_hi | (((bring_base + (uint32_t)sb * (uint32_t)b_bytes) & 0x3FFFFu) >> 4);
-                            if (p.dbg & 16) { }
-                            else {
-                            if (ks == 0 && tap == 0) ptx::umma_bf16_lohi(d_tmem, at, a_hi32, bt, b_hi32, idesc, false);
-                            else                     ptx::umma_bf16_lohi(d_tmem, at, a_hi32, bt, b_hi32, idesc, true);
-                            for (int k = 1; k < ksub; ++k)
-                                ptx::umma_bf16_lohi(d_tmem, at + 2u * k, a_hi32, bt + 2u * k, b_hi32, idesc, true);
-                            }
-                            ptx::umma_commit(&bempty[sb]);
-                            if (tap == 8) {
-                                ptx::umma_commit(&empty[s]);
-                                if (ks == ksteps - 1) ptx::umma_commit(&tmem_full[acc_cur]);
-                            }
-                        }
-                        __syncwarp();
-                        if (++sb == p.b_stages) { sb = 0; bph ^= 1u; }
+                    const bool last = ks == ksteps - 1;
+                    const uint32_t flag0 = ks != 0 ? 1u : 0u;
+                    // one iteration per weight-ring stage; the taps of a stage are issued from a fully unrolled body
+#define ELD_H3_STAGE(KSUB_, BG_, T0_, LAST_)                                                                       \
+                    {                                                                                                  \
+                        ELD_WAIT(&bfull[sb], bph, pw1);                                                                \
+                        ptx::tc_fence_after();                                                                         \
+                        if (ptx::elect_one()) {                                                                        \
+                            if (!(p.dbg & 16))                                                                         \
+                                issue_halo3_group<KSUB_, BG_, T0_>(d_tmem, a_lo, a_hi32, b_ring_lo + (uint32_t)sb * b_stage_step, \
+                                                                   b_hi32, b_step, idesc, flag0);                     \
+                            ptx::umma_commit(&bempty[sb]);                                                             \
+                            if (LAST_) {                                                                               \
+                                ptx::umma_commit(&empty[s]);                                                           \
+                                if (last) ptx::umma_commit(&tmem_full[acc_cur]);                                       \
+                            }                                                                                          \
+                        }                                                                                              \
+                        __syncwarp();                                                                                  \
+                        if (++sb == p.b_stages) { sb = 0; bph ^= 1u; }                                                 \
                     }
+                    if (p.b_group == 3) {
+                        if (ksub == 4) { ELD_H3_STAGE(4, 3, 0, false) ELD_H3_STAGE(4, 3, 3, false) ELD_H3_STAGE(4, 3, 6, true) }
+                        else           { ELD_H3_STAGE(2, 3, 0, false) ELD_H3_STAGE(2, 3, 3, false) ELD_H3_STAGE(2, 3, 6, true) }
+                    } else {
+                        if (ksub == 4) {
+                            ELD_H3_STAGE(4, 1, 0, false) ELD_H3_STAGE(4, 1, 1, false) ELD_H3_STAGE(4, 1, 2, false)
+                            ELD_H3_STAGE(4, 1, 3, false) ELD_H3_STAGE(4, 1, 4, false) ELD_H3_STAGE(4, 1, 5, false)
+                            ELD_H3_STAGE(4, 1, 6, false) ELD_H3_STAGE(4, 1, 7, false) ELD_H3_STAGE(4, 1, 8, true)
+                        } else {
+                            ELD_H3_STAGE(2, 1, 0, false) ELD_H3_STAGE(2, 1, 1, false) ELD_H3_STAGE(2, 1, 2, false)
+                            ELD_H3_STAGE(2, 1, 3, false) ELD_H3_STAGE(2, 1, 4, false) ELD_H3_STAGE(2, 1, 5, false)
+                            ELD_H3_STAGE(2, 1, 6, false) ELD_H3_STAGE(2, 1, 7, false) ELD_H3_STAGE(2, 1, 8, true)
+                        }
+                    }
+#undef ELD_H3_STAGE
                     a_addr += (uint32_t)stage_bytes;
                     if (++s == p.stages) { s = 0; ph ^= 1u; a_addr = stage_base; }
                 }

@@ -71,9 +71,11 @@ int launch_conv_gemm(eld_ctx* ctx, const GemmOp& op, cudaStream_t st)
     }
     // streamed weights + full-halo activations for every other conv3x3 (two rings)
     p.b_stages = 0;
-    // (measured: for n_tile == 64 the per-tap barrier round trip costs more than the rows it saves - keep halo == 1)
-    if (!p.b_res && op.a_mode == A_CONV && op.taps == 9 && p.n_tile >= 128 && !getenv("ELD_CONV_NOHALO3")) {
+    // one weight-ring stage = 3 taps for n_tile <= 128 (12 MMAs per barrier round trip), 1 tap for n_tile == 256
+    p.b_group = 1;
+    if (!p.b_res && op.a_mode == A_CONV && op.taps == 9 && p.n_tile >= 64 && !getenv("ELD_CONV_NOHALO3")) {
         p.halo = 3; p.tile_w = 8;
+        p.b_group = p.n_tile <= 128 ? 3 : 1;
     }
     p.tiles_x = (op.W + p.tile_w - 1) / p.tile_w;
     p.tiles_y = (op.H + (128 / p.tile_w) - 1) / (128 / p.tile_w);
@@ -82,8 +84,10 @@ int launch_conv_gemm(eld_ctx* ctx, const GemmOp& op, cudaStream_t st)
     int stages = (budget - (p.b_res ? b_total : 0)) / stage_bytes;
     if (p.halo == 3) {
         stages = 3;                                              // activations: 3 x 23 KB (kc = 64)
-        int bs = (216 * 1024 - stages * stage_bytes) / b_tile;   // weights: the rest, one tap per stage
+        int bs = (216 * 1024 - stages * stage_bytes) / (p.b_group * b_tile);   // weights: the rest
         if (bs > 8) bs = 8;
+        if (bs < 2) { stages = 2; bs = (216 * 1024 - stages * stage_bytes) / (p.b_group * b_tile); }
+        ELD_REQUIRE(bs >= 2, "conv tile: weight ring does not fit (n_tile %d, kc %d)", p.n_tile, p.kc);
         p.b_stages = bs;
     }
     if (stages > 8) stages = 8;
@@ -118,7 +122,7 @@ int launch_conv_gemm(eld_ctx* ctx, const GemmOp& op, cudaStream_t st)
         if (rc) return rc;
     }
     p.b_ptr = static_cast<const uint8_t*>(op.b);
-    const size_t ring_bytes = (size_t)stages * stage_bytes + (p.b_res ? b_total : 0) + (size_t)p.b_stages * b_tile;
+    const size_t ring_bytes = (size_t)stages * stage_bytes + (p.b_res ? b_total : 0) + (size_t)p.b_stages * p.b_group * b_tile;
     p.bias_smem_off = (int)ring_bytes + 768;                      // barriers (<= 53 x 8 B + slot) live in the first 768 B
     const int n_bias = op.epi_mode == EPI_STORE ? op.n_total : op.cout;
     ELD_REQUIRE(n_bias <= 1024, "conv tile: %d bias entries exceed the 4 KB shared-memory copy", n_bias);
