@@ -164,8 +164,21 @@ int init_gemm_kernels(eld_ctx* ctx)
     ELD_CHECK_CUDA(cudaFuncSetAttribute(conv_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     ELD_CHECK_CUDA(cudaFuncSetAttribute(conv_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     ELD_CHECK_CUDA(cudaFuncSetAttribute(wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    ELD_CHECK_CUDA(cudaFuncSetAttribute(wgrad_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+#define ELD_WG2_ATTR(PR, A, B) ELD_CHECK_CUDA(cudaFuncSetAttribute(wgrad_conv_kernel<PR, A, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    ELD_WG2_ATTR(false, 64, 64) ELD_WG2_ATTR(false, 64, 128) ELD_WG2_ATTR(false, 128, 64) ELD_WG2_ATTR(false, 128, 128)
+    ELD_WG2_ATTR(true, 64, 64) ELD_WG2_ATTR(true, 64, 128) ELD_WG2_ATTR(true, 128, 64) ELD_WG2_ATTR(true, 128, 128)
+#undef ELD_WG2_ATTR
     return ELD_OK;
+}
+
+template <bool PROF>
+static void launch_wg2(int grid, size_t smem, cudaStream_t st, const CUtensorMap& tmP, const CUtensorMap& tmQ, const Wgrad2Params& p)
+{
+    const int rbp = p.box_ch * 2, rbq = p.q_box_ch * 2;
+    if (rbp == 64 && rbq == 64)        wgrad_conv_kernel<PROF, 64, 64><<<grid, kWg2Threads, smem, st>>>(tmP, tmQ, p);
+    else if (rbp == 64 && rbq == 128)  wgrad_conv_kernel<PROF, 64, 128><<<grid, kWg2Threads, smem, st>>>(tmP, tmQ, p);
+    else if (rbp == 128 && rbq == 64)  wgrad_conv_kernel<PROF, 128, 64><<<grid, kWg2Threads, smem, st>>>(tmP, tmQ, p);
+    else                               wgrad_conv_kernel<PROF, 128, 128><<<grid, kWg2Threads, smem, st>>>(tmP, tmQ, p);
 }
 
 // conv3x3 weight gradient, full-halo generation (wgrad_conv.cuh)
@@ -205,7 +218,7 @@ static int launch_wgrad_conv(eld_ctx* ctx, const WgradOp& op, cudaStream_t st)
     p.ksplit = ksplit;
     p.dw = op.dw;
     p.out_tco = op.out_tco;
-    p.db = op.db;
+    p.db = getenv("ELD_WGRAD_NOBIAS") ? nullptr : op.db;     // (debugging: time the tile without the fused bias gradient)
     CUtensorMap tmP, tmQ;
     const cuuint64_t eb = 2;
     {
@@ -225,7 +238,28 @@ static int launch_wgrad_conv(eld_ctx* ctx, const WgradOp& op, cudaStream_t st)
         if (rc) return rc;
     }
     const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
-    wgrad_conv_kernel<<<items * p.ksplit, kWg2Threads, smem, st>>>(tmP, tmQ, p);
+    if (getenv("ELD_CONV_PROF")) {
+        const int grid = items * p.ksplit;
+        long long* d = nullptr;
+        ELD_CHECK_CUDA(cudaMalloc(&d, (size_t)grid * 8 * sizeof(long long)));
+        ELD_CHECK_CUDA(cudaMemsetAsync(d, 0, (size_t)grid * 8 * sizeof(long long), st));
+        p.prof = d;
+        launch_wg2<true>(grid, smem, st, tmP, tmQ, p);
+        ELD_CHECK_CUDA(cudaStreamSynchronize(st));
+        std::vector<long long> h((size_t)grid * 8);
+        ELD_CHECK_CUDA(cudaMemcpy(h.data(), d, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        cudaFree(d);
+        double m[8] = { 0 }, mx = 0;
+        for (int b = 0; b < grid; ++b) for (int k = 0; k < 8; ++k) m[k] += (double)h[(size_t)b * 8 + k] / grid;
+        for (int b = 0; b < grid; ++b) if ((double)h[(size_t)b * 8 + 4] > mx) mx = (double)h[(size_t)b * 8 + 4];
+        fprintf(stderr, "[wgrad prof] slowest cta %.1f kclk | ", mx / 1e3);
+        fprintf(stderr, "[wgrad prof] cin %d cout %d HxW %dx%d kind %d G %d groups %d n_tile %d items %d ksplit %d grid %d stages %d chunks/cta %.1f | kclk: "
+                        "prod tot %.1f wE %.1f | mma tot %.1f wF %.1f | epi tot %.1f red %.1f\n",
+                op.p_ch, op.q_ch, op.H, op.W, p.kind, p.G, p.groups, p.n_tile, items, p.ksplit, grid, p.stages,
+                (double)total_chunks / p.ksplit, m[0] / 1e3, m[1] / 1e3, m[2] / 1e3, m[3] / 1e3, m[4] / 1e3, m[5] / 1e3);
+    } else {
+        launch_wg2<false>(items * p.ksplit, smem, st, tmP, tmQ, p);
+    }
     ELD_CHECK_CUDA(cudaGetLastError());
     count_launch(ctx);
     return ELD_OK;

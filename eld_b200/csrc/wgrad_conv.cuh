@@ -31,6 +31,7 @@ struct Wgrad2Params {
     int ksplit, stages, tmem_cols;
     float* dw;
     int out_tco;                // 0: dw is OIHW [co][ci][3][3], scalar red.add; 1: dw is [tap][ci][co], 16-byte vector red.add
+    long long* prof;            // PROF instantiation only
     float* db;                  // optional bias gradient: db[co] += sum over pixels of dZ (column sums of the Q tiles,
                                 // computed by the otherwise idle epilogue warps of the cp == 0, grp == 0 CTAs)
 };
@@ -40,6 +41,9 @@ constexpr int kWg2MaxG = 8;
 
 __device__ __forceinline__ int tap_row_offset(int t) { return (t / 3) * 10 + (t % 3); }
 
+// RBP / RBQ: bytes per pixel row of the X (P) and dZ (Q) boxes (64 or 128) - compile-time so that the K-step
+// descriptor increments of the MMA issue loop are immediates (uniform-datapath adds instead of R2UR chains).
+template <bool PROF, int RBP, int RBQ>
 __global__ void __launch_bounds__(kWg2Threads, 1)
 wgrad_conv_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmQ,
                   const Wgrad2Params p)
@@ -47,8 +51,10 @@ wgrad_conv_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = ptx::smem_u32(smem_raw);
     uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+    long long pw0 = 0, pt0 = 0, pt1 = 0;
+    if (PROF) pt0 = clock64();
 
-    const int rb_p = p.box_ch * 2, rb_q = p.q_box_ch * 2;
+    constexpr int rb_p = RBP, rb_q = RBQ;
     const int p_box = (100 * rb_p + 1023) & ~1023;
     const int q_box = 64 * rb_q;
     const int p_bytes = p.p_boxes * p_box;
@@ -101,7 +107,8 @@ wgrad_conv_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant
             uint8_t* sa = smem;
             for (int i = 0; i < nchunks; ++i) {
                 const int x0 = cx * 8, y0 = cy * 8;
-                ptx::mbar_wait(&empty[s], ph ^ 1u);
+                if (PROF) { const long long t_ = clock64(); ptx::mbar_wait(&empty[s], ph ^ 1u); pw0 += clock64() - t_; }
+                else ptx::mbar_wait(&empty[s], ph ^ 1u);
                 ptx::mbar_arrive_expect_tx(&full[s], tx_bytes);
                 for (int b = 0; b < p.p_boxes; ++b)
                     ptx::tma_load_5d(sa + b * p_box, &tmP, &full[s], pc0 + b * p.box_ch, x0 - 1, y0 - 1, img, 0);
@@ -135,29 +142,32 @@ wgrad_conv_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant
         const uint64_t b_desc0 = ptx::make_smem_desc(0, (uint32_t)q_box, 8u * rb_q, b_layout);
         const uint32_t b_hi = (uint32_t)(b_desc0 >> 32);
         const uint32_t b_lo_c = (uint32_t)b_desc0;
-        const uint32_t a_kstep = (uint32_t)(20 * rb_p) >> 4;          // 16 pixels = 2 patch rows of the 10-wide halo box
-        const uint32_t b_kstep = (uint32_t)(16 * rb_q) >> 4;          // 2 rows of the dense 8-wide box
+        constexpr uint32_t a_kstep = (uint32_t)(20 * rb_p) >> 4;      // 16 pixels = 2 patch rows of the 10-wide halo box
+        constexpr uint32_t b_kstep = (uint32_t)(16 * rb_q) >> 4;      // 2 rows of the dense 8-wide box
+        uint32_t d_tm[kWg2MaxG];
+#pragma unroll
+        for (int g = 0; g < kWg2MaxG; ++g) d_tm[g] = tmem_base + (uint32_t)(g * p.n_tile);
         const uint32_t smem_base = ptx::smem_u32(smem);
         uint32_t st_addr = smem_base;
         int s = 0;
         uint32_t ph = 0;
         for (int i = 0; i < nchunks; ++i) {
-            ptx::mbar_wait(&full[s], ph);
+            if (PROF) { const long long t_ = clock64(); ptx::mbar_wait(&full[s], ph); pw0 += clock64() - t_; }
+            else ptx::mbar_wait(&full[s], ph);
             ptx::tc_fence_after();
             if (ptx::elect_one()) {
                 const uint32_t a_st = (st_addr & 0x3FFFFu) >> 4;
                 const uint32_t b_lo0 = b_lo_c + (((st_addr + (uint32_t)p_bytes) & 0x3FFFFu) >> 4);
                 // g outermost (4 consecutive K steps per accumulator): measured faster than k-outermost on B200
+                const uint32_t flag0 = i != 0 ? 1u : 0u;
 #pragma unroll
                 for (int g = 0; g < kWg2MaxG; ++g) {
                     if (g < g_cnt) {
-                        const uint32_t d_tmem = tmem_base + (uint32_t)(g * p.n_tile);
                         const uint32_t a_lo0 = a_lo_c[g] + a_st;
-                        if (i == 0) ptx::umma_bf16_lohi(d_tmem, a_lo0, a_hi, b_lo0, b_hi, idesc, false);
-                        else        ptx::umma_bf16_lohi(d_tmem, a_lo0, a_hi, b_lo0, b_hi, idesc, true);
+                        ptx::umma_bf16(d_tm[g], ((uint64_t)a_hi << 32) | a_lo0, ((uint64_t)b_hi << 32) | b_lo0, idesc, flag0);
 #pragma unroll
                         for (int k = 1; k < 4; ++k)
-                            ptx::umma_bf16_lohi(d_tmem, a_lo0 + k * a_kstep, a_hi, b_lo0 + k * b_kstep, b_hi, idesc, true);
+                            ptx::umma_bf16_lohi(d_tm[g], a_lo0 + k * a_kstep, a_hi, b_lo0 + k * b_kstep, b_hi, idesc, true);
                     }
                 }
                 ptx::umma_commit(&empty[s]);
@@ -204,6 +214,7 @@ wgrad_conv_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant
         // ===================== epilogue: TMEM -> red.add into dW =====================
         ptx::mbar_wait(acc_full, 0);
         ptx::tc_fence_after();
+        if (PROF) pt1 = clock64();
         for (int g = 0; g < g_cnt; ++g) {
             const int mt = mt0 + g;
             int tap, ci;
@@ -233,6 +244,12 @@ wgrad_conv_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant
                 }
             }
         }
+    }
+    if (PROF && lane == 0 && warp <= 2) {
+        // slots: 0-1 producer (total, wait empty) | 2-3 MMA (total, wait full) | 4-5 epilogue warp 2 (total, time in the red.add phase)
+        long long* o = p.prof + (size_t)blockIdx.x * 8 + warp * 2;
+        const long long t = clock64();
+        o[0] = t - pt0; o[1] = warp == 2 ? t - pt1 : pw0;
     }
     ptx::tc_fence_before();
     __syncthreads();
