@@ -218,6 +218,7 @@ static int launch_wgrad_conv(eld_ctx* ctx, const WgradOp& op, cudaStream_t st)
     p.ksplit = ksplit;
     p.dw = op.dw;
     p.out_tco = op.out_tco;
+    p.dbg = getenv("ELD_CONV_DBG") ? atoi(getenv("ELD_CONV_DBG")) : 0;
     p.db = getenv("ELD_WGRAD_NOBIAS") ? nullptr : op.db;     // (debugging: time the tile without the fused bias gradient)
     CUtensorMap tmP, tmQ;
     const cuuint64_t eb = 2;
@@ -254,9 +255,9 @@ static int launch_wgrad_conv(eld_ctx* ctx, const WgradOp& op, cudaStream_t st)
         for (int b = 0; b < grid; ++b) if ((double)h[(size_t)b * 8 + 4] > mx) mx = (double)h[(size_t)b * 8 + 4];
         fprintf(stderr, "[wgrad prof] slowest cta %.1f kclk | ", mx / 1e3);
         fprintf(stderr, "[wgrad prof] cin %d cout %d HxW %dx%d kind %d G %d groups %d n_tile %d items %d ksplit %d grid %d stages %d chunks/cta %.1f | kclk: "
-                        "prod tot %.1f wE %.1f | mma tot %.1f wF %.1f | epi tot %.1f red %.1f\n",
+                        "prod tot %.1f wE %.1f | mma tot %.1f wF %.1f issue %.1f commit %.1f | epi tot %.1f red %.1f\n",
                 op.p_ch, op.q_ch, op.H, op.W, p.kind, p.G, p.groups, p.n_tile, items, p.ksplit, grid, p.stages,
-                (double)total_chunks / p.ksplit, m[0] / 1e3, m[1] / 1e3, m[2] / 1e3, m[3] / 1e3, m[4] / 1e3, m[5] / 1e3);
+                (double)total_chunks / p.ksplit, m[0] / 1e3, m[1] / 1e3, m[2] / 1e3, m[3] / 1e3, m[6] / 1e3, m[7] / 1e3, m[4] / 1e3, m[5] / 1e3);
     } else {
         launch_wg2<false>(items * p.ksplit, smem, st, tmP, tmQ, p);
     }

@@ -32,6 +32,7 @@ struct Wgrad2Params {
     float* dw;
     int out_tco;                // 0: dw is OIHW [co][ci][3][3], scalar red.add; 1: dw is [tap][ci][co], 16-byte vector red.add
     long long* prof;            // PROF instantiation only
+    int dbg;                    // experiments only (ELD_CONV_DBG): 8 = skip the TMA loads
     float* db;                  // optional bias gradient: db[co] += sum over pixels of dZ (column sums of the Q tiles,
                                 // computed by the otherwise idle epilogue warps of the cp == 0, grp == 0 CTAs)
 };
@@ -40,6 +41,60 @@ constexpr int kWg2Threads = 192;
 constexpr int kWg2MaxG = 8;
 
 __device__ __forceinline__ int tap_row_offset(int t) { return (t / 3) * 10 + (t % 3); }
+
+struct Wg2Issue {
+    uint64_t *full, *empty, *acc_full;
+    int nchunks, stages;
+    uint32_t smem_base, stage_bytes, p_bytes, a_hi, b_hi, b_lo_c, idesc;
+};
+
+// The MMA issuer's chunk loop for a CTA with G accumulators.  The readiness of the NEXT stage is probed
+// (mbarrier.try_wait, ~100 cycles round trip) before this stage's MMAs are issued, so the probe's latency hides
+// behind the issue work instead of leaving the tensor pipe idle between chunks.
+template <int G, int RBP, int RBQ, bool PROF>
+__device__ __forceinline__ void wg2_issue_loop(const Wg2Issue& W, const uint32_t* a_lo_c, const uint32_t* d_tm, long long& pw0,
+                                               long long& pw_issue, long long& pw_commit)
+{
+    constexpr uint32_t a_kstep = (uint32_t)(20 * RBP) >> 4;      // 16 pixels = 2 patch rows of the 10-wide halo box
+    constexpr uint32_t b_kstep = (uint32_t)(16 * RBQ) >> 4;      // 2 rows of the dense 8-wide box
+    uint32_t st_addr = W.smem_base;
+    int s = 0;
+    uint32_t ph = 0;
+    bool ready = W.nchunks > 0 && ptx::mbar_try_wait(&W.full[0], 0);
+    for (int i = 0; i < W.nchunks; ++i) {
+        if (!ready) {
+            if (PROF) { const long long t_ = clock64(); ptx::mbar_wait(&W.full[s], ph); pw0 += clock64() - t_; }
+            else ptx::mbar_wait(&W.full[s], ph);
+        }
+        ptx::tc_fence_after();
+        int s1 = s + 1;
+        uint32_t ph1 = ph, st1 = st_addr + W.stage_bytes;
+        if (s1 == W.stages) { s1 = 0; ph1 ^= 1u; st1 = W.smem_base; }
+        ready = (i + 1 < W.nchunks) && ptx::mbar_try_wait(&W.full[s1], ph1);
+        if (ptx::elect_one()) {
+            long long ta_ = 0, tb_ = 0;
+            if (PROF) ta_ = clock64();
+            const uint32_t a_st = (st_addr & 0x3FFFFu) >> 4;
+            const uint32_t b_lo0 = W.b_lo_c + (((st_addr + W.p_bytes) & 0x3FFFFu) >> 4);
+            const uint32_t flag0 = i != 0 ? 1u : 0u;
+            // g outermost (4 consecutive K steps per accumulator): measured faster than k-outermost on B200
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                const uint32_t a_lo0 = a_lo_c[g] + a_st;
+                ptx::umma_bf16(d_tm[g], ((uint64_t)W.a_hi << 32) | a_lo0, ((uint64_t)W.b_hi << 32) | b_lo0, W.idesc, flag0);
+#pragma unroll
+                for (int k = 1; k < 4; ++k)
+                    ptx::umma_bf16_lohi(d_tm[g], a_lo0 + k * a_kstep, W.a_hi, b_lo0 + k * b_kstep, W.b_hi, W.idesc, true);
+            }
+            if (PROF) tb_ = clock64();
+            ptx::umma_commit(&W.empty[s]);
+            if (i == W.nchunks - 1) ptx::umma_commit(W.acc_full);
+            if (PROF) { pw_issue += tb_ - ta_; pw_commit += clock64() - tb_; }
+        }
+        __syncwarp();
+        s = s1; ph = ph1; st_addr = st1;
+    }
+}
 
 // RBP / RBQ: bytes per pixel row of the X (P) and dZ (Q) boxes (64 or 128) - compile-time so that the K-step
 // descriptor increments of the MMA issue loop are immediates (uniform-datapath adds instead of R2UR chains).
@@ -51,7 +106,7 @@ wgrad_conv_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = ptx::smem_u32(smem_raw);
     uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
-    long long pw0 = 0, pt0 = 0, pt1 = 0;
+    long long pw0 = 0, pt0 = 0, pt1 = 0, pw_issue = 0, pw_commit = 0;
     if (PROF) pt0 = clock64();
 
     constexpr int rb_p = RBP, rb_q = RBQ;
@@ -109,11 +164,14 @@ wgrad_conv_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant
                 const int x0 = cx * 8, y0 = cy * 8;
                 if (PROF) { const long long t_ = clock64(); ptx::mbar_wait(&empty[s], ph ^ 1u); pw0 += clock64() - t_; }
                 else ptx::mbar_wait(&empty[s], ph ^ 1u);
+                if (p.dbg & 8) ptx::mbar_arrive(&full[s]);        // experiments only: no loads
+                else {
                 ptx::mbar_arrive_expect_tx(&full[s], tx_bytes);
                 for (int b = 0; b < p.p_boxes; ++b)
                     ptx::tma_load_5d(sa + b * p_box, &tmP, &full[s], pc0 + b * p.box_ch, x0 - 1, y0 - 1, img, 0);
                 for (int b = 0; b < p.q_boxes; ++b)
                     ptx::tma_load_5d(sa + p_bytes + b * q_box, &tmQ, &full[s], qc0 + b * p.q_box_ch, x0, y0, img, 0);
+                }
                 sa += stage_bytes;
                 if (++s == p.stages) { s = 0; ph ^= 1u; sa = smem; }
                 if (++cx == p.chunks_x) { cx = 0; if (++cy == p.chunks_y) { cy = 0; ++img; } }
@@ -142,40 +200,22 @@ wgrad_conv_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant
         const uint64_t b_desc0 = ptx::make_smem_desc(0, (uint32_t)q_box, 8u * rb_q, b_layout);
         const uint32_t b_hi = (uint32_t)(b_desc0 >> 32);
         const uint32_t b_lo_c = (uint32_t)b_desc0;
-        constexpr uint32_t a_kstep = (uint32_t)(20 * rb_p) >> 4;      // 16 pixels = 2 patch rows of the 10-wide halo box
-        constexpr uint32_t b_kstep = (uint32_t)(16 * rb_q) >> 4;      // 2 rows of the dense 8-wide box
         uint32_t d_tm[kWg2MaxG];
 #pragma unroll
         for (int g = 0; g < kWg2MaxG; ++g) d_tm[g] = tmem_base + (uint32_t)(g * p.n_tile);
         const uint32_t smem_base = ptx::smem_u32(smem);
-        uint32_t st_addr = smem_base;
-        int s = 0;
-        uint32_t ph = 0;
-        for (int i = 0; i < nchunks; ++i) {
-            if (PROF) { const long long t_ = clock64(); ptx::mbar_wait(&full[s], ph); pw0 += clock64() - t_; }
-            else ptx::mbar_wait(&full[s], ph);
-            ptx::tc_fence_after();
-            if (ptx::elect_one()) {
-                const uint32_t a_st = (st_addr & 0x3FFFFu) >> 4;
-                const uint32_t b_lo0 = b_lo_c + (((st_addr + (uint32_t)p_bytes) & 0x3FFFFu) >> 4);
-                // g outermost (4 consecutive K steps per accumulator): measured faster than k-outermost on B200
-                const uint32_t flag0 = i != 0 ? 1u : 0u;
-#pragma unroll
-                for (int g = 0; g < kWg2MaxG; ++g) {
-                    if (g < g_cnt) {
-                        const uint32_t a_lo0 = a_lo_c[g] + a_st;
-                        ptx::umma_bf16(d_tm[g], ((uint64_t)a_hi << 32) | a_lo0, ((uint64_t)b_hi << 32) | b_lo0, idesc, flag0);
-#pragma unroll
-                        for (int k = 1; k < 4; ++k)
-                            ptx::umma_bf16_lohi(d_tm[g], a_lo0 + k * a_kstep, a_hi, b_lo0 + k * b_kstep, b_hi, idesc, true);
-                    }
-                }
-                ptx::umma_commit(&empty[s]);
-                if (i == nchunks - 1) ptx::umma_commit(acc_full);
-            }
-            __syncwarp();
-            st_addr += (uint32_t)stage_bytes;
-            if (++s == p.stages) { s = 0; ph ^= 1u; st_addr = smem_base; }
+        const Wg2Issue W{ full, empty, acc_full, nchunks, p.stages, smem_base, (uint32_t)stage_bytes, (uint32_t)p_bytes,
+                          a_hi, b_hi, b_lo_c, idesc };
+        // one fully unrolled instantiation per accumulator count: no per-group branch inside the chunk loop
+        switch (g_cnt) {
+            case 1: wg2_issue_loop<1, RBP, RBQ, PROF>(W, a_lo_c, d_tm, pw0, pw_issue, pw_commit); break;
+            case 2: wg2_issue_loop<2, RBP, RBQ, PROF>(W, a_lo_c, d_tm, pw0, pw_issue, pw_commit); break;
+            case 3: wg2_issue_loop<3, RBP, RBQ, PROF>(W, a_lo_c, d_tm, pw0, pw_issue, pw_commit); break;
+            case 4: wg2_issue_loop<4, RBP, RBQ, PROF>(W, a_lo_c, d_tm, pw0, pw_issue, pw_commit); break;
+            case 5: wg2_issue_loop<5, RBP, RBQ, PROF>(W, a_lo_c, d_tm, pw0, pw_issue, pw_commit); break;
+            case 6: wg2_issue_loop<6, RBP, RBQ, PROF>(W, a_lo_c, d_tm, pw0, pw_issue, pw_commit); break;
+            case 7: wg2_issue_loop<7, RBP, RBQ, PROF>(W, a_lo_c, d_tm, pw0, pw_issue, pw_commit); break;
+            default: wg2_issue_loop<8, RBP, RBQ, PROF>(W, a_lo_c, d_tm, pw0, pw_issue, pw_commit); break;
         }
     } else if (nchunks > 0) {
         const int q = warp & 3;
@@ -250,6 +290,7 @@ wgrad_conv_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant
         long long* o = p.prof + (size_t)blockIdx.x * 8 + warp * 2;
         const long long t = clock64();
         o[0] = t - pt0; o[1] = warp == 2 ? t - pt1 : pw0;
+        if (warp == 1) { p.prof[(size_t)blockIdx.x * 8 + 6] = pw_issue; p.prof[(size_t)blockIdx.x * 8 + 7] = pw_commit; }
     }
     ptx::tc_fence_before();
     __syncthreads();

@@ -1,7 +1,6 @@
 mkdir -p gpurun_out/prof
-bash tools/quick.sh q3 > gpurun_out/prof/q3.out 2>&1
-ELD_WGRAD_NOBIAS=1 python tools/profile_layers.py 8 > gpurun_out/prof/layers_nobias.txt 2>&1
-ELD_CONV_PROF=1 python - > gpurun_out/prof/convprof.txt 2>&1 <<'PY'
+for d in 0 8; do
+ELD_CONV_DBG=$d ELD_WGRAD_NOBIAS=1 ELD_CONV_PROF=1 python - > gpurun_out/prof/convprof_dbg$d.txt 2>&1 <<'PY'
 import torch, sys
 sys.path.insert(0, '.')
 from eld_b200 import arch
@@ -15,5 +14,5 @@ print('----- second step', file=sys.stderr, flush=True)
 net.train_step(x, t, loss_out=loss)
 torch.cuda.synchronize()
 PY
-cat gpurun_out/prof/q3.out; tail -9 gpurun_out/prof/layers_nobias.txt | head -3
-grep -A200 "second step" gpurun_out/prof/convprof.txt | grep wgrad | cut -c1-400
+echo "== dbg $d"; grep -A200 "second step" gpurun_out/prof/convprof_dbg$d.txt | grep wgrad | cut -c40-130,215-400 | head -9
+done
