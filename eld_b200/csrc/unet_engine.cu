@@ -34,7 +34,21 @@ enum { I_C11 = 0, I_C12, I_C21, I_C22, I_C31, I_C32, I_C41, I_C42, I_C51, I_C52,
        I_C71, I_C72, I_UP8, I_C81, I_C82, I_UP9, I_C91, I_C92, I_C10 };
 
 struct PackEntry { unsigned long long src, dst_f, dst_d; int cout, cin, type; int pad; };
-struct PackTable { PackEntry e[kNumLayers]; int n; unsigned long long first_stage, first_dst, first_wf; };
+struct PackTable {
+    PackEntry e[kNumLayers];
+    int tile0[kNumLayers + 1];   // prefix sum of (cout/32 x cin/32) tiles per entry: one block per tile, whatever the layer
+    int n;
+    unsigned long long first_stage, first_dst, first_wf;
+};
+
+// flattened tile id -> (entry, tile inside the entry)
+__device__ __forceinline__ int find_entry(const PackTable& T, int tile, int& local)
+{
+    int k = 0;
+    while (k + 1 < T.n && tile >= T.tile0[k + 1]) ++k;
+    local = tile - T.tile0[k];
+    return k;
+}
 
 // one launch packs every layer's fp32 master weights into both bf16 GEMM operands (fprop + dgrad).
 // A block moves a (32 x 32 x taps) tile through shared memory so that reads are 1 KB runs and writes are
@@ -43,23 +57,24 @@ __global__ void __launch_bounds__(256)
 pack_all_kernel(const float* __restrict__ params, __nv_bfloat16* __restrict__ packed, const __grid_constant__ PackTable T)
 {
     __shared__ float tile[32][32 * 9 + 1];
-    if ((int)blockIdx.y == T.n) {         // conv1_1: w[32][4][9] -> operand [32][9][32] (channels 4..31 stay zero)
+    if ((int)blockIdx.x >= T.tile0[T.n]) {   // conv1_1: w[32][4][9] -> operand [32][9][32] (channels 4..31 stay zero)
         const float* w1 = params + T.first_dst;
-        for (int i = blockIdx.x * 256 + threadIdx.x; i < 32 * 36; i += gridDim.x * 256) {
+        const int b = (int)blockIdx.x - T.tile0[T.n], nb = (int)gridDim.x - T.tile0[T.n];
+        for (int i = b * 256 + threadIdx.x; i < 32 * 36; i += nb * 256) {
             const int co = i / 36, r = i - co * 36, ci = r / 9, t = r - ci * 9;
             packed[T.first_wf + packed_index(32, 32, 9, co, t, ci)] = __float2bfloat16_rn(w1[i]);
         }
         return;
     }
-    const PackEntry& e = T.e[blockIdx.y];
+    int tl;
+    const PackEntry& e = T.e[find_entry(T, (int)blockIdx.x, tl)];
     const float* w = params + e.src;
     __nv_bfloat16* of = packed + e.dst_f;
     __nv_bfloat16* od = packed + e.dst_d;
     if (e.type == L_CONV3) {              // w[co][ci][t]
-        const int ct = e.cout / 32, it = e.cin / 32;
-        for (int tl = blockIdx.x; tl < ct * it; tl += gridDim.x) {
+        const int it = e.cin / 32;
+        {
             const int co0 = (tl / it) * 32, ci0 = (tl % it) * 32;
-            __syncthreads();
             for (int i = threadIdx.x; i < 32 * 288; i += 256) {
                 const int co = i / 288, r = i - co * 288;              // r = ci*9 + t
                 tile[co][r] = w[((size_t)(co0 + co) * e.cin + ci0) * 9 + r];
@@ -75,10 +90,9 @@ pack_all_kernel(const float* __restrict__ params, __nv_bfloat16* __restrict__ pa
             }
         }
     } else {                              // deconv wt[ci][co][s]
-        const int ct = e.cout / 32, it = e.cin / 32;
-        for (int tl = blockIdx.x; tl < ct * it; tl += gridDim.x) {
+        const int ct = e.cout / 32;
+        {
             const int ci0 = (tl / ct) * 32, co0 = (tl % ct) * 32;
-            __syncthreads();
             for (int i = threadIdx.x; i < 32 * 128; i += 256) {
                 const int ci = i / 128, r = i - ci * 128;              // r = co*4 + s
                 tile[ci][r] = w[((size_t)(ci0 + ci) * e.cout + co0) * 4 + r];
@@ -101,20 +115,21 @@ __global__ void __launch_bounds__(256)
 wgrad_permute_kernel(const float* __restrict__ gtmp, float* __restrict__ grads, const __grid_constant__ PackTable T)
 {
     __shared__ float tile[9][32][33];
-    if ((int)blockIdx.y == T.n) {   // conv1_1: staging is [9][32 (4 real)][32] behind the regular area; dst [32][4][9] at offset 0
+    if ((int)blockIdx.x >= T.tile0[T.n]) {   // conv1_1: staging is [9][32 (4 real)][32] behind the regular area; dst [32][4][9] at offset 0
         const float* src = gtmp + T.first_stage;
-        for (int i = blockIdx.x * 256 + threadIdx.x; i < 32 * 36; i += gridDim.x * 256) {
+        const int b = (int)blockIdx.x - T.tile0[T.n], nb = (int)gridDim.x - T.tile0[T.n];
+        for (int i = b * 256 + threadIdx.x; i < 32 * 36; i += nb * 256) {
             const int co = i / 36, r = i - co * 36, ci = r / 9, tap = r - ci * 9;
             grads[T.first_dst + i] = src[(tap * 32 + ci) * 32 + co];
         }
         return;
     }
-    const PackEntry& e = T.e[blockIdx.y];
+    int t;
+    const PackEntry& e = T.e[find_entry(T, (int)blockIdx.x, t)];
     if (e.type != L_CONV3) return;
-    const int ct = e.cout / 32, it = e.cin / 32;
-    for (int t = blockIdx.x; t < ct * it; t += gridDim.x) {
+    const int ct = e.cout / 32;
+    {
         const int co0 = (t % ct) * 32, ci0 = (t / ct) * 32;
-        __syncthreads();
         for (int i = threadIdx.x; i < 9 * 32 * 32; i += 256) {
             const int co = i & 31, ci = (i >> 5) & 31, tap = i >> 10;
             tile[tap][ci][co] = gtmp[e.src + ((size_t)tap * e.cin + ci0 + ci) * e.cout + co0 + co];
@@ -272,8 +287,10 @@ extern "C" int eld_unet_create(eld_ctx* ctx, int n, int h, int w, int train, voi
     for (int i = 0; i < kNumLayers; ++i) {
         const Layer& l = u->L[i];
         if (i == I_C11 || l.type == L_CONV1) continue;
+        u->table.tile0[k] = k == 0 ? 0 : u->table.tile0[k - 1] + (u->table.e[k - 1].cout / 32) * (u->table.e[k - 1].cin / 32);
         u->table.e[k++] = PackEntry{ l.w_off, l.wf_off, l.wd_off, l.cout, l.cin, l.type, 0 };
     }
+    u->table.tile0[k] = u->table.tile0[k - 1] + (u->table.e[k - 1].cout / 32) * (u->table.e[k - 1].cin / 32);
     u->table.n = k;
     u->table.first_stage = u->n_params;
     u->table.first_dst = u->L[I_C11].w_off;
@@ -415,8 +432,7 @@ struct Runner {
     int pack() const
     {
         Scope sc(u, st, "weights", "pack", 0.0, (double)u->n_params * 8);
-        dim3 grid(64, u->table.n + 1);
-        pack_all_kernel<<<grid, 256, 0, st>>>(params, u->packed, u->table);
+        pack_all_kernel<<<u->table.tile0[u->table.n] + 2, 256, 0, st>>>(params, u->packed, u->table);
         ELD_CHECK_CUDA(cudaGetLastError());
         count_launch(ctx());
         return ELD_OK;
@@ -525,8 +541,7 @@ struct Runner {
         }
         {
             Scope sc(u, st, "weights", "gperm", 0.0, (double)U->n_params * 8);
-            dim3 grid(32, U->table.n + 1);
-            wgrad_permute_kernel<<<grid, 256, 0, st>>>(U->gtmp, g, U->table);
+            wgrad_permute_kernel<<<U->table.tile0[U->table.n] + 2, 256, 0, st>>>(U->gtmp, g, U->table);
             ELD_CHECK_CUDA(cudaGetLastError());
             count_launch(ctx());
         }

@@ -164,9 +164,11 @@ int init_gemm_kernels(eld_ctx* ctx)
     ELD_CHECK_CUDA(cudaFuncSetAttribute(conv_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     ELD_CHECK_CUDA(cudaFuncSetAttribute(conv_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     ELD_CHECK_CUDA(cudaFuncSetAttribute(wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-#define ELD_WG2_ATTR(PR, A, B) ELD_CHECK_CUDA(cudaFuncSetAttribute(wgrad_conv_kernel<PR, A, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    ELD_WG2_ATTR(false, 64, 64) ELD_WG2_ATTR(false, 64, 128) ELD_WG2_ATTR(false, 128, 64) ELD_WG2_ATTR(false, 128, 128)
-    ELD_WG2_ATTR(true, 64, 64) ELD_WG2_ATTR(true, 64, 128) ELD_WG2_ATTR(true, 128, 64) ELD_WG2_ATTR(true, 128, 128)
+#define ELD_WG2_ATTR(PR, A, N) ELD_CHECK_CUDA(cudaFuncSetAttribute(wgrad_conv_kernel<PR, A, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    ELD_WG2_ATTR(false, 64, 32) ELD_WG2_ATTR(false, 64, 64) ELD_WG2_ATTR(false, 64, 128) ELD_WG2_ATTR(false, 64, 256)
+    ELD_WG2_ATTR(false, 128, 32) ELD_WG2_ATTR(false, 128, 64) ELD_WG2_ATTR(false, 128, 128) ELD_WG2_ATTR(false, 128, 256)
+    ELD_WG2_ATTR(true, 64, 32) ELD_WG2_ATTR(true, 64, 64) ELD_WG2_ATTR(true, 64, 128) ELD_WG2_ATTR(true, 64, 256)
+    ELD_WG2_ATTR(true, 128, 32) ELD_WG2_ATTR(true, 128, 64) ELD_WG2_ATTR(true, 128, 128) ELD_WG2_ATTR(true, 128, 256)
 #undef ELD_WG2_ATTR
     return ELD_OK;
 }
@@ -174,11 +176,11 @@ int init_gemm_kernels(eld_ctx* ctx)
 template <bool PROF>
 static void launch_wg2(int grid, size_t smem, cudaStream_t st, const CUtensorMap& tmP, const CUtensorMap& tmQ, const Wgrad2Params& p)
 {
-    const int rbp = p.box_ch * 2, rbq = p.q_box_ch * 2;
-    if (rbp == 64 && rbq == 64)        wgrad_conv_kernel<PROF, 64, 64><<<grid, kWg2Threads, smem, st>>>(tmP, tmQ, p);
-    else if (rbp == 64 && rbq == 128)  wgrad_conv_kernel<PROF, 64, 128><<<grid, kWg2Threads, smem, st>>>(tmP, tmQ, p);
-    else if (rbp == 128 && rbq == 64)  wgrad_conv_kernel<PROF, 128, 64><<<grid, kWg2Threads, smem, st>>>(tmP, tmQ, p);
-    else                               wgrad_conv_kernel<PROF, 128, 128><<<grid, kWg2Threads, smem, st>>>(tmP, tmQ, p);
+    const int rbp = p.box_ch * 2;
+#define ELD_WG2_CASE(A, N) if (rbp == A && p.n_tile == N) { wgrad_conv_kernel<PROF, A, N><<<grid, kWg2Threads, smem, st>>>(tmP, tmQ, p); return; }
+    ELD_WG2_CASE(64, 32) ELD_WG2_CASE(64, 64) ELD_WG2_CASE(64, 128) ELD_WG2_CASE(64, 256)
+    ELD_WG2_CASE(128, 32) ELD_WG2_CASE(128, 64) ELD_WG2_CASE(128, 128) ELD_WG2_CASE(128, 256)
+#undef ELD_WG2_CASE
 }
 
 // conv3x3 weight gradient, full-halo generation (wgrad_conv.cuh)
@@ -197,10 +199,24 @@ static int launch_wgrad_conv(eld_ctx* ctx, const WgradOp& op, cudaStream_t st)
     p.q_boxes = p.n_tile / p.q_box_ch;
     int gmax = 512 / p.n_tile;
     if (gmax > kWg2MaxG) gmax = kWg2MaxG;
-    p.groups = (p.m_tiles + gmax - 1) / gmax;
-    p.G = (p.m_tiles + p.groups - 1) / p.groups;
+    // the issue loop is specialised (wgrad_conv.cuh, WV_*): kind 0 -> 3 filter rows; kind 1 -> 5 / 3+2 / 2+2+1 tap pairs;
+    // kind 2 -> one filter row (3 taps) per CTA for N <= 128, tap pairs for N == 256
+    if (p.kind == 2) gmax = p.n_tile <= 128 ? 3 : 2;
+    if (p.kind == 1) gmax = p.n_tile <= 64 ? 5 : (p.n_tile == 128 ? 3 : 2);
+    if (p.kind == 0) gmax = 3;
+    p.G = gmax;
+    p.groups = (p.m_tiles + p.G - 1) / p.G;
     const int rb_p = p.box_ch * 2, rb_q = p.q_box_ch * 2;
-    const int stage_bytes = p.p_boxes * ((100 * rb_p + 1023) & ~1023) + p.q_boxes * 64 * rb_q;
+    const int chunk_bytes = p.p_boxes * ((100 * rb_p + 1023) & ~1023) + p.q_boxes * 64 * rb_q;
+    // chunks per stage: as many as still leave a 3-deep ring (small-N layers are bound by the issuing thread's
+    // per-stage barrier round trip, not by the tensor pipe)
+    int cps_stage = (200 * 1024) / (3 * chunk_bytes);
+    if (cps_stage > 4) cps_stage = 4;
+    if (cps_stage < 1) cps_stage = 1;
+    if (p.kind == 0) cps_stage = 1;      // measured: the 32-channel layers lose with multi-chunk stages, the others gain
+    if (getenv("ELD_WGRAD_CPS") && atoi(getenv("ELD_WGRAD_CPS")) < cps_stage) cps_stage = atoi(getenv("ELD_WGRAD_CPS"));   // (experiments: cap)
+    p.cps_stage = cps_stage;
+    const int stage_bytes = cps_stage * chunk_bytes;
     int stages = (200 * 1024) / stage_bytes;
     if (stages > 8) stages = 8;
     if (stages < 2) stages = 2;
@@ -212,7 +228,9 @@ static int launch_wgrad_conv(eld_ctx* ctx, const WgradOp& op, cudaStream_t st)
     const int total_chunks = op.n_img * p.chunks_x * p.chunks_y;
     // split-K: every split adds its whole [9*cin x cout] tile with red.add, so big outputs get one wave only
     const size_t outputs = (size_t)9 * op.p_ch * op.q_ch;
-    int ksplit = ((outputs > (1u << 18) ? 1 : 2) * ctx->num_sms) / items;
+    int waves = outputs > (1u << 18) ? 1 : 2;
+    if (getenv("ELD_WGRAD_WAVES")) waves = atoi(getenv("ELD_WGRAD_WAVES"));
+    int ksplit = (waves * ctx->num_sms) / items;
     if (ksplit < 1) ksplit = 1;
     if (ksplit > total_chunks) ksplit = total_chunks;
     p.ksplit = ksplit;
@@ -269,7 +287,8 @@ static int launch_wgrad_conv(eld_ctx* ctx, const WgradOp& op, cudaStream_t st)
 int launch_wgrad(eld_ctx* ctx, const WgradOp& op, cudaStream_t st)
 {
     if (op.mode == WG_CONV && op.H % 8 == 0 && op.W % 8 == 0 && (op.p_ch == 32 || op.p_ch == 64 || op.p_ch % 128 == 0) &&
-        op.q_ch % 32 == 0 && !getenv("ELD_WGRAD_V1"))
+        (op.q_ch == 32 || op.q_ch == 64 || op.q_ch == 128 || op.q_ch % 256 == 0) && !(op.p_ch == 32 && op.q_ch > 128) &&
+        !getenv("ELD_WGRAD_V1"))
         return launch_wgrad_conv(ctx, op, st);
     ELD_REQUIRE(op.db == nullptr, "wgrad tile: fused bias gradient needs the full-halo conv generation");
     ELD_REQUIRE(op.H % 4 == 0 && op.W % 16 == 0, "wgrad tile: H=%d must be a multiple of 4 and W=%d of 16", op.H, op.W);
