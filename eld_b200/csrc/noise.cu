@@ -31,6 +31,7 @@ struct NoiseLaunch {
     uint32_t mask;
     int h, w;         // packed plane
     int clip01;
+    uint8_t aug[kMaxFramesPerLaunch];   // AUG kernels: bit 0 flip rows, bit 1 flip columns, bit 2 transpose (sid_dataset.py:344-352)
 };
 
 static FrameConsts make_consts(const eld_noise_params& p)
@@ -149,6 +150,28 @@ __device__ __forceinline__ void stg_stream(float4* p, const float4& v)
                  :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+// ELDTrainDataset's augmentation (dataset/sid_dataset.py:340-352) as a store-side index map: the noise of a pixel is
+// keyed by its SOURCE position, the value lands at  out = transpose?(flipW?(flipH?(x)))  - the reference's order.
+// Flips keep float4 stores (component order reversed for a column flip); a transpose scatters four scalars.
+__device__ __forceinline__ void store_aug(float* __restrict__ plane_out, uint32_t flags, uint32_t i, uint32_t j0,
+                                          uint32_t h, uint32_t w, const float4& v)
+{
+    const uint32_t fi = (flags & 1u) ? h - 1u - i : i;
+    if (!(flags & 4u)) {
+        if (flags & 2u) stg_stream(reinterpret_cast<float4*>(plane_out + (size_t)fi * w + (w - 4u - j0)), make_float4(v.w, v.z, v.y, v.x));
+        else            stg_stream(reinterpret_cast<float4*>(plane_out + (size_t)fi * w + j0), v);
+    } else {
+        // transposed output has h' = w rows of w' = h pixels: out[fj][fi] = x[i][j]
+        const float vv[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t j = j0 + (uint32_t)k;
+            const uint32_t fj = (flags & 2u) ? w - 1u - j : j;
+            plane_out[(size_t)fj * h + fi] = vv[k];
+        }
+    }
+}
+
 // clean-frame source: f32 packed, or the LMDB wire format - uint16 packed, y = clip(v/65535, 0, 1)
 // (dataset/lmdb_dataset.py:38-39); the de-quantised frame can be written out as the training target.
 struct U16Src { const uint16_t* src; float scale; float* clean_out; };
@@ -181,10 +204,10 @@ __device__ __forceinline__ void row_normals(const Stream& s, uint32_t i, float& 
 
 // ---- packed in, aligned: w % 4 == 0 and 16-byte aligned planes ---------------------------------
 // Gaussian-only masks are issue/latency bound on MUFU chains: cap registers at 32 so 8 blocks (64 warps) fit.
-template <uint32_t MASK, int CLIP, int IN = 0>
+template <uint32_t MASK, int CLIP, int IN = 0, bool AUG = false>
 __global__ void __launch_bounds__(256, (MASK != kRuntimeMask && !(MASK & (ELD_NOISE_P | ELD_NOISE_G))) ? 8 : 1)
 noise_packed_vec_kernel(const float* __restrict__ clean, float* __restrict__ noisy,
-                        const __grid_constant__ NoiseLaunch L, const U16Src u16 = U16Src{})
+                        const __grid_constant__ NoiseLaunch L, const U16Src u16 = U16Src{}, float* __restrict__ target_out = nullptr)
 {
     const int f = blockIdx.y;
     const uint32_t plane = (uint32_t)L.h * (uint32_t)L.w;
@@ -209,6 +232,12 @@ noise_packed_vec_kernel(const float* __restrict__ clean, float* __restrict__ noi
         const float rr = (c < 2) ? r_even : r_odd;
         const float rown[4] = { rr, rr, rr, rr };
         form_quad<MASK, CLIP>(fc, s, L.mask, (uint32_t)c, t * 4u, rown, L.clip01, y);
+        if (AUG) {
+            const uint32_t i = (t * 4u) / (uint32_t)L.w, j0 = t * 4u - i * (uint32_t)L.w;
+            const size_t pbase = ((size_t)f * 4 + c) * plane;
+            store_aug(noisy + pbase, L.aug[f], i, j0, (uint32_t)L.h, (uint32_t)L.w, make_float4(y[0], y[1], y[2], y[3]));
+            if (target_out) store_aug(target_out + pbase, L.aug[f], i, j0, (uint32_t)L.h, (uint32_t)L.w, v[c]);
+        } else
         stg_stream(reinterpret_cast<float4*>(noisy + base + (size_t)c * plane), make_float4(y[0], y[1], y[2], y[3]));
     }
 }
@@ -220,10 +249,10 @@ noise_packed_vec_kernel(const float* __restrict__ clean, float* __restrict__ noi
 // acceptance, so a warp iterates ~1.2 x 16 times instead of 16 x max-over-lanes.  The per-pixel arithmetic
 // and draw order are exactly poisson_px's (same values; oracle: eld_oracle_poisson_px).  The lane's 16 rates
 // and counts live in a private shared-memory column (dynamic indexing without local memory).
-template <uint32_t MASK, int IN = 0>
+template <uint32_t MASK, int IN = 0, bool AUG = false>
 __global__ void __launch_bounds__(256)
 noise_packed_poisson_kernel(const float* __restrict__ clean, float* __restrict__ noisy,
-                            const __grid_constant__ NoiseLaunch L, const U16Src u16 = U16Src{})
+                            const __grid_constant__ NoiseLaunch L, const U16Src u16 = U16Src{}, float* __restrict__ target_out = nullptr)
 {
     __shared__ float s_buf[16][256];
     const int f = blockIdx.y;
@@ -240,62 +269,55 @@ noise_packed_poisson_kernel(const float* __restrict__ clean, float* __restrict__
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
         const float4 v = load_clean<IN>(clean, u16, base + (size_t)c * plane);
+        if (AUG && target_out) {
+            const uint32_t i = (t * 4u) / (uint32_t)L.w, j0 = t * 4u - i * (uint32_t)L.w;
+            store_aug(target_out + ((size_t)f * 4 + c) * plane, L.aug[f], i, j0, (uint32_t)L.h, (uint32_t)L.w, v);
+        }
         s_buf[c * 4 + 0][tid] = (v.x * fc.scale_in) * fc.invK;
         s_buf[c * 4 + 1][tid] = (v.y * fc.scale_in) * fc.invK;
         s_buf[c * 4 + 2][tid] = (v.z * fc.scale_in) * fc.invK;
         s_buf[c * 4 + 3][tid] = (v.w * fc.scale_in) * fc.invK;
     }
 
-    // ---- lane-persistent Poisson ----
-    int cur = 0;
-    bool fresh = true;
-    int mode = 0;                 // 1 = inversion, 2 = PTRS
-    float lam = 0.f, u = 0.f, pp = 0.f, F = 0.f, k = 0.f, pb = 0.f, pa = 0.f, invalpha = 0.f, vr = 0.f;
-    uint32_t att = 0, l = 0, c = 0;
-    uint4 x = make_uint4(0, 0, 0, 0);
-    while (cur < 16) {
-        bool done = false;
-        float result = 0.f;
-        if (fresh) {
-            fresh = false;
-            lam = s_buf[cur][tid];
-            l = t * 4u + (uint32_t)(cur & 3);
-            c = (uint32_t)cur >> 2;
-            if (!(lam > 0.0f)) { done = true; result = 0.f; mode = 0; }
-            else if (lam < 10.0f) {
-                x = draw(s, l, DOM_PIX, c, 0);
-                u = u24(x.x);
-                pp = __expf(-lam); F = pp; k = 0.f; mode = 1;
-            } else {
+    // ---- lane-persistent Poisson, one sampler at a time ----
+    // Two passes, so that a warp never executes both samplers in one iteration (the mixed loop paid for the
+    // inversion body, the PTRS body and two Philox calls every iteration): pass 1 walks this lane's pixels with
+    // rate >= 10 (one PTRS attempt per iteration), pass 2 those with 0 < rate < 10 (up to eight search steps per
+    // iteration).  Same arithmetic and draw order per pixel as poisson_px / eld_oracle_poisson_px.
+    uint32_t big = 0, small = 0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const float lamj = s_buf[j][tid];
+        if (lamj >= 10.0f) big |= 1u << j;
+        else if (lamj > 0.0f) small |= 1u << j;
+        else s_buf[j][tid] = 0.0f;
+    }
+    {
+        int cur = -1;
+        float lam = 0.f, pb = 0.f, pa = 0.f, invalpha = 0.f, vr = 0.f;
+        uint32_t att = 0, l = 0, c = 0;
+        uint4 x = make_uint4(0, 0, 0, 0);
+        while (big) {
+            if (cur < 0) {
+                cur = __ffs((int)big) - 1;
+                lam = s_buf[cur][tid];
+                l = t * 4u + (uint32_t)(cur & 3);
+                c = (uint32_t)cur >> 2;
                 const float slam = fast_sqrt(lam);
                 pb = __fmaf_rn(2.53f, slam, 0.931f);
                 pa = __fmaf_rn(0.02483f, pb, -0.059f);
                 invalpha = 1.1239f + __fdividef(1.1328f, pb - 3.4f);
                 vr = 0.9277f - __fdividef(3.6224f, pb - 2.0f);
-                att = 0; mode = 2;
+                att = 0;
             }
-        }
-        if (mode == 1) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (!done) {
-                    if (u > F) {
-                        k += 1.0f;
-                        pp = __fmul_rn(pp, __fdividef(lam, k));
-                        F = __fadd_rn(F, pp);
-                        if (pp < 1e-9f && k > lam) done = true;
-                    } else done = true;
-                }
-            }
-            result = k;
-        } else if (mode == 2) {
             if ((att & 1u) == 0) x = draw(s, l, DOM_PIX, c, att >> 1);
             const uint32_t xa = (att & 1u) ? x.z : x.x, xb = (att & 1u) ? x.w : x.y;
             const float U = __fadd_rn(u_open(xa), -0.5f);
             const float V = u01(xb);
             const float us = __fadd_rn(0.5f, -fabsf(U));
             const float kf = floorf(__fmaf_rn(__fadd_rn(__fdividef(2.0f * pa, us), pb), U, __fadd_rn(lam, 0.43f)));
-            result = kf;
+            bool done = false;
+            float result = kf;
             if (us >= 0.07f && V <= vr) done = true;
             else if (!(kf < 0.0f || (us < 0.013f && V > us))) {
                 const float lhs = __logf(__fdividef(V * invalpha, __fdividef(pa, us * us) + pb));
@@ -312,11 +334,41 @@ noise_packed_poisson_kernel(const float* __restrict__ clean, float* __restrict__
             }
             ++att;
             if (!done && att == 16u) { done = true; result = floorf(lam + 0.5f); }
+            if (done) {
+                s_buf[cur][tid] = result * fc.K;
+                big &= big - 1u;
+                cur = -1;
+            }
         }
-        if (done) {
-            s_buf[cur][tid] = result * fc.K;
-            ++cur;
-            fresh = true;
+    }
+    {
+        int cur = -1;
+        float lam = 0.f, u = 0.f, pp = 0.f, F = 0.f, k = 0.f;
+        while (small) {
+            if (cur < 0) {
+                cur = __ffs((int)small) - 1;
+                lam = s_buf[cur][tid];
+                const uint4 x = draw(s, t * 4u + (uint32_t)(cur & 3), DOM_PIX, (uint32_t)cur >> 2, 0);
+                u = u24(x.x);
+                pp = __expf(-lam); F = pp; k = 0.f;
+            }
+            bool done = false;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (!done) {
+                    if (u > F) {
+                        k += 1.0f;
+                        pp = __fmul_rn(pp, __fdividef(lam, k));
+                        F = __fadd_rn(F, pp);
+                        if (pp < 1e-9f && k > lam) done = true;
+                    } else done = true;
+                }
+            }
+            if (done) {
+                s_buf[cur][tid] = k * fc.K;
+                small &= small - 1u;
+                cur = -1;
+            }
         }
     }
 
@@ -329,6 +381,10 @@ noise_packed_poisson_kernel(const float* __restrict__ clean, float* __restrict__
         const float rr = (cc < 2) ? r_even : r_odd;
         const float rown[4] = { rr, rr, rr, rr };
         post_shot<MASK>(fc, s, L.mask, (uint32_t)cc, t * 4u, rown, L.clip01, z);
+        if (AUG) {
+            const uint32_t i = (t * 4u) / (uint32_t)L.w, j0 = t * 4u - i * (uint32_t)L.w;
+            store_aug(noisy + ((size_t)f * 4 + cc) * plane, L.aug[f], i, j0, (uint32_t)L.h, (uint32_t)L.w, make_float4(z[0], z[1], z[2], z[3]));
+        } else
         stg_stream(reinterpret_cast<float4*>(noisy + base + (size_t)cc * plane), make_float4(z[0], z[1], z[2], z[3]));
     }
 }
@@ -648,6 +704,45 @@ extern "C" int eld_noise_packed_u16(eld_ctx* ctx, const uint16_t* clean_u16, flo
         dim3 grid((uint32_t)((plane / 4 + 255) / 256), nf);
         if (model_mask & ELD_NOISE_P) noise_packed_poisson_kernel<kRuntimeMask, 1><<<grid, 256, 0, st>>>(nullptr, dst, L, u);
         else                          noise_packed_vec_kernel<kRuntimeMask, -1, 1><<<grid, 256, 0, st>>>(nullptr, dst, L, u);
+        ELD_CHECK_CUDA(cudaGetLastError());
+        count_launch(ctx);
+    }
+    return ELD_OK;
+}
+
+// Noise + ELDTrainDataset's augmentation (random row flip, column flip, transpose of BOTH input and target,
+// dataset/sid_dataset.py:340-356) in one pass: noisy = aug(noise(clean)), target_out = aug(clean).
+// aug_flags: host array, one byte per frame: bit 0 flip rows, bit 1 flip columns, bit 2 transpose (needs h == w).
+extern "C" int eld_noise_packed_aug(eld_ctx* ctx, const float* clean, float* noisy, float* target_out, int n, int h, int w,
+                                    const eld_noise_params* params, uint32_t model_mask, uint64_t seed, uint64_t frame_id0,
+                                    int clip01, const uint8_t* aug_flags, void* stream)
+{
+    int rc = check_common(ctx, clean, noisy, n, h, w, params, model_mask, "eld_noise_packed_aug");
+    if (rc < 0) return rc;
+    if (rc == 1) return ELD_OK;
+    ELD_REQUIRE(aug_flags != nullptr, "eld_noise_packed_aug: aug_flags is NULL");
+    ELD_REQUIRE(w % 4 == 0, "eld_noise_packed_aug: w=%d must be a multiple of 4", w);
+    ELD_REQUIRE((reinterpret_cast<uintptr_t>(clean) | reinterpret_cast<uintptr_t>(noisy) | reinterpret_cast<uintptr_t>(target_out)) % 16 == 0,
+                "eld_noise_packed_aug: buffers must be 16-byte aligned");
+    ELD_REQUIRE(clean != noisy && clean != target_out, "eld_noise_packed_aug: the index map cannot run in place");
+    for (int f = 0; f < n; ++f) {
+        ELD_REQUIRE((aug_flags[f] & ~7u) == 0, "eld_noise_packed_aug: aug_flags[%d] = %u has unknown bits", f, aug_flags[f]);
+        ELD_REQUIRE(!(aug_flags[f] & 4u) || h == w, "eld_noise_packed_aug: transpose needs square frames (h=%d w=%d)", h, w);
+    }
+    ELD_CHECK_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t plane = (size_t)h * w;
+    for (int f0 = 0; f0 < n; f0 += kMaxFramesPerLaunch) {
+        const int nf = (n - f0 < kMaxFramesPerLaunch) ? n - f0 : kMaxFramesPerLaunch;
+        NoiseLaunch L{};
+        for (int f = 0; f < nf; ++f) { L.fr[f] = make_consts(params[f0 + f]); L.aug[f] = aug_flags[f0 + f]; }
+        L.seed = seed; L.frame0 = frame_id0 + (uint64_t)f0; L.mask = model_mask; L.h = h; L.w = w; L.clip01 = clip01;
+        const float* src = clean + (size_t)f0 * 4 * plane;
+        float* dst = noisy + (size_t)f0 * 4 * plane;
+        float* tdst = target_out ? target_out + (size_t)f0 * 4 * plane : nullptr;
+        dim3 grid((uint32_t)((plane / 4 + 255) / 256), nf);
+        if (model_mask & ELD_NOISE_P) noise_packed_poisson_kernel<kRuntimeMask, 0, true><<<grid, 256, 0, st>>>(src, dst, L, U16Src{}, tdst);
+        else                          noise_packed_vec_kernel<kRuntimeMask, -1, 0, true><<<grid, 256, 0, st>>>(src, dst, L, U16Src{}, tdst);
         ELD_CHECK_CUDA(cudaGetLastError());
         count_launch(ctx);
     }

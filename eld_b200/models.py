@@ -27,7 +27,7 @@ def default_opt(**kw):
              resume_epoch=None, seed=2018, chop=False, no_log=True, no_verbose=True, netG='unet', channels=4,
              stage_in='raw', stage_out='raw', model_path=None, include=4, crf=False, batchSize=1, lr=1e-4,
              beta1=0.9, wd=0.0, loss='l1', noise='g', isTrain=True, save_epoch_freq=100, noise_on_gpu=False,
-             defer_loss_sync=False)
+             augment_on_gpu=False, defer_loss_sync=False)
     o.update(kw)
     return SimpleNamespace(**o)
 
@@ -129,7 +129,12 @@ class ELDModel(BaseModel):
             n = target.shape[0]
             fid0 = (self._frame_counter * self.world + self.rank) * n
             self._frame_counter += 1
-            input = self.noise_maker.batch_gpu(target, frame_id0=fid0, clip=True)
+            if getattr(self.opt, 'augment_on_gpu', False):
+                # ELDTrainDataset's flips / transpose / clip (sid_dataset.py:340-356) fused into the noise kernel:
+                # both the synthesised input and the target come back augmented, one pass over the frames
+                input, target = self.noise_maker.batch_gpu_augmented(target, frame_id0=fid0, clip=True)
+            else:
+                input = self.noise_maker.batch_gpu(target, frame_id0=fid0, clip=True)
         else:
             input = input.to(device=self.device, dtype=torch.float32, non_blocking=True)
         self.input, self.target, self.data_name = input, target, data_name

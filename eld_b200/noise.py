@@ -107,6 +107,43 @@ class NoiseModelBase:
         _lib.check(rc, 'eld_noise_packed')
         return out
 
+    @staticmethod
+    def sample_augment(n):
+        """The three coin flips of ELDTrainDataset.__getitem__ (dataset/sid_dataset.py:344-350), per frame, drawn from
+        numpy's global RNG in the reference's order: flip rows, flip columns, transpose -> bit flags 1 | 2 | 4."""
+        flags = np.zeros(n, dtype=np.uint8)
+        for f in range(n):
+            for bit in (1, 2, 4):
+                if np.random.randint(2, size=1)[0] == 1:
+                    flags[f] |= bit
+        return flags
+
+    def batch_gpu_augmented(self, clean, aug=None, params=None, frame_id0=None, clip=True, seed=None):
+        """SynDataset + ELDTrainDataset in one kernel (sid_dataset.py:269-277, 340-356): returns
+        (input, target) = (aug(clip(noise(clean))), aug(clean)), aug = per-frame flip rows / flip columns / transpose.
+        `aug`: uint8 flags per frame (bit 0 rows, 1 columns, 2 transpose) or None to draw them like the reference."""
+        import ctypes
+        import torch
+        assert clean.is_cuda and clean.dtype == torch.float32 and clean.dim() == 4 and clean.shape[1] == 4
+        clean = clean.contiguous()
+        n, _, h, w = clean.shape
+        plist = self._frame_params(n, params)
+        if aug is None:
+            aug = self.sample_augment(n)
+        aug = np.ascontiguousarray(aug, dtype=np.uint8)
+        assert aug.shape == (n,)
+        if frame_id0 is None:
+            frame_id0 = int(np.random.randint(0, 2 ** 62))
+        noisy = torch.empty_like(clean)
+        target = torch.empty_like(clean)
+        lib = _lib.load()
+        rc = lib.eld_noise_packed_aug(_lib.ctx(clean.device.index or 0), clean.data_ptr(), noisy.data_ptr(), target.data_ptr(),
+                                      n, h, w, params_array(plist), _lib.model_mask(self.model),
+                                      int(self.seed if seed is None else seed), int(frame_id0), int(bool(clip)),
+                                      aug.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), _cur_stream(torch))
+        _lib.check(rc, 'eld_noise_packed_aug')
+        return noisy, target
+
     def mosaic_gpu(self, mosaic, black=0.0, white=65535.0, params=None, frame_id0=None, clip=True,
                    want_clean=True, seed=None):
         """mosaic: cuda uint16/int16-bit-pattern or float32 [N,H,W] Bayer frames -> (noisy, clean)

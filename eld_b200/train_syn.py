@@ -39,6 +39,7 @@ def main():
     ap.add_argument('-b', '--batchSize', type=int, default=8); ap.add_argument('--seed', type=int, default=2018)
     ap.add_argument('--epochs', type=int, default=1); ap.add_argument('--iters', type=int, default=20)
     ap.add_argument('--lr', type=float, default=1e-4); ap.add_argument('--name', default='eld_b200_syn')
+    ap.add_argument('--no-augment', action='store_true', help='skip ELDTrainDataset flips/transpose (sid_dataset.py:340-352)')
     a = ap.parse_args()
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
@@ -48,7 +49,7 @@ def main():
     rank = dist.get_rank() if world > 1 else 0
     torch.manual_seed(a.seed); np.random.seed(a.seed)                        # base_options.py:31-34
     opt = models.default_opt(name=a.name, gpu_ids=[local], noise=a.noise, include=a.include, batchSize=a.batchSize,
-                             lr=a.lr, noise_on_gpu=True, defer_loss_sync=True)
+                             lr=a.lr, noise_on_gpu=True, augment_on_gpu=not a.no_augment, defer_loss_sync=True)
     noise_model = NoiseModel(model=opt.noise, include=opt.include, seed=a.seed, verbose=rank == 0)   # train_syn.py:38
     ds = SyntheticClean(a.iters * a.batchSize * world, a.seed)
     sampler = torch.utils.data.distributed.DistributedSampler(ds, world, rank, shuffle=True) if world > 1 else None

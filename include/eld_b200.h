@@ -104,6 +104,19 @@ int eld_noise_packed_u16(eld_ctx* ctx, const uint16_t* clean_u16, float scale, f
                          int n, int h, int w, const eld_noise_params* params, uint32_t model_mask,
                          uint64_t seed, uint64_t frame_id0, int clip01, void* stream);
 
+/* Noise fused with ELDTrainDataset's augmentation (dataset/sid_dataset.py:340-356): three independent coin flips per
+ * frame - flip rows (np.flip axis 1), flip columns (axis 2), transpose (0,2,1) - applied in that order to BOTH the
+ * noisy input and the clean target, then the clip.  The noise of a pixel is keyed by its SOURCE position, so
+ *   noisy = aug(eld_noise_packed(clean)),  target_out = aug(clean)   bit for bit, in one pass over the frame.
+ * aug_flags: HOST array, one byte per frame: bit 0 rows, bit 1 columns, bit 2 transpose (needs h == w).
+ * target_out may be NULL.  Not in place.  w % 4 == 0, 16-byte aligned buffers. */
+#define ELD_AUG_FLIP_H     1u
+#define ELD_AUG_FLIP_W     2u
+#define ELD_AUG_TRANSPOSE  4u
+int eld_noise_packed_aug(eld_ctx* ctx, const float* clean, float* noisy, float* target_out, int n, int h, int w,
+                         const eld_noise_params* params, uint32_t model_mask, uint64_t seed, uint64_t frame_id0,
+                         int clip01, const uint8_t* aug_flags, void* stream);
+
 /* Number of kernels the library has launched through this ctx since creation (bench.py's
  * gpu_launches evidence). */
 int64_t eld_launch_count(const eld_ctx* ctx);

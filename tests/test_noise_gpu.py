@@ -270,3 +270,53 @@ def test_lmdb_u16_ingest(torch, oracle, model, mask):
     sig = _sigma(want_clean, SONY, mask)
     bad = np.abs(noisy.cpu().numpy().astype(np.float64) - ref) > ATOL_SIGMA * sig + 1e-6
     assert bad.mean() <= (MISMATCH_FRAC if mask & 1 else 0)
+
+
+def _np_augment(x, flags):
+    """ELDTrainDataset.__getitem__ (dataset/sid_dataset.py:344-352) on one [4,h,w] frame."""
+    if flags & 1:
+        x = np.flip(x, axis=1)
+    if flags & 2:
+        x = np.flip(x, axis=2)
+    if flags & 4:
+        x = np.transpose(x, (0, 2, 1))
+    return np.ascontiguousarray(x)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('model', ['p+g', 'P+g'])
+def test_fused_augmentation_is_an_exact_index_map(torch, model):
+    """noise + flips/transpose/clip in one pass == numpy's flips applied to the un-augmented kernel
+    output (bit for bit), for all 8 flag combinations; the target is the same map of the clean frame."""
+    from eld_b200.noise import NoiseModel
+    nm = NoiseModel(model, include=4, verbose=False, seed=31)
+    rs = np.random.RandomState(5)
+    y = rs.rand(8, 4, 64, 64).astype(np.float32)
+    clean = torch.from_numpy(y).cuda()
+    flags = np.arange(8, dtype=np.uint8)
+    plain = nm.batch_gpu(clean, params=SONY, frame_id0=100, clip=True).cpu().numpy()
+    noisy, target = nm.batch_gpu_augmented(clean, aug=flags, params=SONY, frame_id0=100, clip=True)
+    noisy, target = noisy.cpu().numpy(), target.cpu().numpy()
+    for f in range(8):
+        assert np.array_equal(noisy[f], _np_augment(plain[f], int(flags[f]))), 'input, flags %d' % flags[f]
+        assert np.array_equal(target[f], _np_augment(y[f], int(flags[f]))), 'target, flags %d' % flags[f]
+    # non-square frames: flips only; transpose is refused
+    y2 = rs.rand(2, 4, 32, 48).astype(np.float32)
+    c2 = torch.from_numpy(y2).cuda()
+    p2 = nm.batch_gpu(c2, params=SONY, frame_id0=7).cpu().numpy()
+    n2, t2 = nm.batch_gpu_augmented(c2, aug=np.array([3, 1], dtype=np.uint8), params=SONY, frame_id0=7)
+    assert np.array_equal(n2.cpu().numpy()[0], _np_augment(p2[0], 3)) and np.array_equal(t2.cpu().numpy()[1], _np_augment(y2[1], 1))
+    from eld_b200._lib import EldError
+    with pytest.raises(EldError):
+        nm.batch_gpu_augmented(c2, aug=np.array([4, 0], dtype=np.uint8), params=SONY, frame_id0=7)
+
+
+@pytest.mark.gpu
+def test_sample_augment_follows_the_reference_rng_order(torch):
+    """Three randint(2) draws per frame in the reference's order (sid_dataset.py:344,347,350)."""
+    from eld_b200.noise import NoiseModel
+    np.random.seed(77)
+    got = NoiseModel.sample_augment(5)
+    np.random.seed(77)
+    want = [sum(b for b in (1, 2, 4) if np.random.randint(2, size=1)[0] == 1) for _ in range(5)]
+    assert got.tolist() == want
