@@ -228,7 +228,8 @@ static int launch_wgrad_conv(eld_ctx* ctx, const WgradOp& op, cudaStream_t st)
     const int total_chunks = op.n_img * p.chunks_x * p.chunks_y;
     // split-K: every split adds its whole [9*cin x cout] tile with red.add, so big outputs get one wave only
     const size_t outputs = (size_t)9 * op.p_ch * op.q_ch;
-    int waves = outputs > (1u << 18) ? 1 : 2;
+    // measured (profiles/): two waves of CTAs only pay for the full-resolution thin layers (>= 16K chunks, small outputs)
+    int waves = (outputs > (1u << 18) || total_chunks < 16384) ? 1 : 2;
     if (getenv("ELD_WGRAD_WAVES")) waves = atoi(getenv("ELD_WGRAD_WAVES"));
     int ksplit = (waves * ctx->num_sms) / items;
     if (ksplit < 1) ksplit = 1;
