@@ -137,11 +137,11 @@ def reference_arm(a):
     else:
         import torch
         from oracle import unet_ref
-        torch.set_num_threads(nproc)
-        fps_unet = unet_ref.cpu_train_fps(steps=max(1, min(a.steps, 3)), warmup=1, batch=1)
+        fps_unet, nthr = unet_ref.cpu_train_fps_best(steps=max(1, min(a.steps, 3)), warmup=1, batch=1)
         fps = 1.0 / (1.0 / noise_fps + 1.0 / fps_unet)
-        sample = ('noise: %d frames/step in a %d-process pool; U-Net: torch CPU fp32 fwd+L1+bwd+Adam batch 1 x %d steps on %d threads'
-                  % (per_step, nproc, max(1, min(a.steps, 3)), nproc))
+        sample = ('noise: %d frames/step in a %d-process pool; U-Net: torch CPU fp32 fwd+L1+bwd+Adam batch 1 x %d steps on %d threads '
+                  '(best of min(nproc, 16/32/64); nproc = %d)'
+                  % (per_step, nproc, max(1, min(a.steps, 3)), nthr, nproc))
     out.update({'value': fps, 'ms_per_step': 1000.0 / fps,
                 'cpu_baseline': {'value': fps, 'unit': 'frames/s', 'cores': nproc, 'kind': 'port', 'sample': sample},
                 'e2e': {'value': fps, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
@@ -302,12 +302,10 @@ def cpu_baseline(a):
     import torch
     from oracle import unet_ref
     nb = cpu_noise_baseline(a.model, seconds=6.0)
-    nthr = os.cpu_count() or 1
-    torch.set_num_threads(nthr)
-    fps_unet = unet_ref.cpu_train_fps(steps=2, warmup=1, batch=1)
+    fps_unet, nthr = unet_ref.cpu_train_fps_best(steps=2, warmup=1, batch=1)
     fps = 1.0 / (1.0 / nb['value'] + 1.0 / fps_unet)
     return {'value': fps, 'unit': 'frames/s', 'cores': nthr, 'kind': 'port',
-            'sample': nb['sample'] + '; U-Net torch CPU fp32 fwd+L1+bwd+Adam, batch 1 x 2 steps, %d threads (noise leg 1 thread)' % nthr}
+            'sample': nb['sample'] + '; U-Net torch CPU fp32 fwd+L1+bwd+Adam, batch 1 x 2 steps, %d threads - best of 16/32/64 (noise leg 1 thread)' % nthr}
 
 
 if __name__ == '__main__':

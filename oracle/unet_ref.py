@@ -92,3 +92,21 @@ def cpu_train_fps(steps=2, warmup=1, batch=1, h=512, w=512):
     for _ in range(steps):
         l1_train_step(net, opt, x, t)
     return batch * steps / (time.perf_counter() - t0)
+
+
+def cpu_train_fps_best(steps=2, warmup=1, batch=1, candidates=None):
+    """The reference step on the thread count that serves it best: torch's default (all logical cores) oversubscribes the
+    small convolutions badly on many-core hosts (128 threads: ~37 s per frame; 32 threads: a few seconds), so a few
+    counts are probed with one step each and the best is kept.  Returns (frames/s, threads)."""
+    import os
+    n = os.cpu_count() or 1
+    if candidates is None:
+        candidates = sorted({min(n, c) for c in (16, 32, 64)})
+    best = (0.0, candidates[0])
+    for th in candidates:
+        torch.set_num_threads(th)
+        f = cpu_train_fps(steps=1, warmup=1, batch=batch)
+        if f > best[0]:
+            best = (f, th)
+    torch.set_num_threads(best[1])
+    return cpu_train_fps(steps=steps, warmup=0, batch=batch), best[1]
