@@ -80,13 +80,16 @@ pack_all_kernel(const float* __restrict__ params, __nv_bfloat16* __restrict__ pa
                 tile[co][r] = w[((size_t)(co0 + co) * e.cin + ci0) * 9 + r];
             }
             __syncthreads();
-            for (int i = threadIdx.x; i < 32 * 288; i += 256) {       // fprop: [co][t][ci]
-                const int ci = i & 31, t = (i >> 5) % 9, co = i / 288;
-                of[packed_index(e.cout, e.cin, 9, co0 + co, t, ci0 + ci)] = __float2bfloat16_rn(tile[co][ci * 9 + t]);
+            // two adjacent K elements per thread: 4-byte stores (pairs never straddle a 16-byte swizzle chunk)
+            for (int i = threadIdx.x; i < 32 * 144; i += 256) {       // fprop: [co][t][ci]
+                const int ci = (i & 15) * 2, t = (i >> 4) % 9, co = i / 144;
+                const __nv_bfloat162 v2 = __floats2bfloat162_rn(tile[co][ci * 9 + t], tile[co][(ci + 1) * 9 + t]);
+                *reinterpret_cast<__nv_bfloat162*>(of + packed_index(e.cout, e.cin, 9, co0 + co, t, ci0 + ci)) = v2;
             }
-            for (int i = threadIdx.x; i < 32 * 288; i += 256) {       // dgrad: [ci][8-t][co]
-                const int co = i & 31, t = (i >> 5) % 9, ci = i / 288;
-                od[packed_index(e.cin, e.cout, 9, ci0 + ci, 8 - t, co0 + co)] = __float2bfloat16_rn(tile[co][ci * 9 + t]);
+            for (int i = threadIdx.x; i < 32 * 144; i += 256) {       // dgrad: [ci][8-t][co]
+                const int co = (i & 15) * 2, t = (i >> 4) % 9, ci = i / 144;
+                const __nv_bfloat162 v2 = __floats2bfloat162_rn(tile[co][ci * 9 + t], tile[co + 1][ci * 9 + t]);
+                *reinterpret_cast<__nv_bfloat162*>(od + packed_index(e.cin, e.cout, 9, ci0 + ci, 8 - t, co0 + co)) = v2;
             }
         }
     } else {                              // deconv wt[ci][co][s]

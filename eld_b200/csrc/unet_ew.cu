@@ -286,10 +286,14 @@ colsum_kernel(const __nv_bfloat16* __restrict__ g, int pitch, int c0, int C, siz
 //   dw[co][ci] += dout[co] a[p][ci] ; db[co] += dout[co]
 // One pixel per thread per iteration, persistent blocks; per-thread partial dW in registers.
 // ---------------------------------------------------------------------------------------------------
-// Four threads per pixel (thread = one output channel co): 32 dW accumulators per thread instead of 128,
-// so two 256-thread blocks fit per SM and the loads of many pixels are in flight.
+// Four threads per pixel; thread q owns input channels [8q, 8q+8) - it loads ONLY its own 16 bytes of the pixel (no
+// redundant loads), forms the partial sums of all four outputs over its slice, and a two-step butterfly over the four
+// lanes completes them.  Lane q then plays output channel q (bias, loss, dOut), every lane accumulates its 4 x 8 block
+// of dW and writes its own 8 channels of dZ.  ~80 registers -> three 256-thread blocks per SM, and the next pixel's
+// loads are issued before the current pixel's arithmetic (the kernel is HBM-latency bound: 160 B per pixel).
+constexpr int kHeadThreads = 128;      // 32 pixels per block iteration; 5 blocks per SM at <= 102 registers
 template <bool TRAIN>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(kHeadThreads, 5)
 head_kernel(const __nv_bfloat16* __restrict__ a, const float* __restrict__ w, const float* __restrict__ b,
             float* __restrict__ out, const float* __restrict__ target, __nv_bfloat16* __restrict__ dz,
             float* __restrict__ dw, float* __restrict__ db, float* __restrict__ loss,
@@ -301,88 +305,120 @@ head_kernel(const __nv_bfloat16* __restrict__ a, const float* __restrict__ w, co
     const int tid = threadIdx.x;
     if (tid < 128) ws[tid >> 5][tid & 31] = w[tid];
     if (tid < 4) bs[tid] = b[tid];
-    if (TRAIN && tid < 133) red[tid] = 0.f;
+    if (TRAIN) for (int i = tid; i < 133; i += kHeadThreads) red[i] = 0.f;
     __syncthreads();
-    const int co = tid & 3, lane = tid & 31;
-    float wrow[32];
+    const int q = tid & 3, lane = tid & 31;
+    float w4[4][8];
 #pragma unroll
-    for (int ci = 0; ci < 32; ++ci) wrow[ci] = ws[co][ci];
-    float pdw[32];
+    for (int co = 0; co < 4; ++co)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) w4[co][j] = ws[co][q * 8 + j];
+    const float bq = bs[q];
+    float pdw[4][8];
     float pdb = 0.f, ploss = 0.f;
     if (TRAIN) {
 #pragma unroll
-        for (int ci = 0; ci < 32; ++ci) pdw[ci] = 0.f;
+        for (int co = 0; co < 4; ++co)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) pdw[co][j] = 0.f;
     }
     const size_t total = (size_t)n_img * plane;
-    for (size_t pbase = (size_t)blockIdx.x * 64; pbase < total; pbase += (size_t)gridDim.x * 64) {
-        // block-uniform trip count (the shuffles below need whole warps); a ragged tail only masks the memory ops
-        const bool valid = pbase + (tid >> 2) < total;
-        const size_t p = valid ? pbase + (tid >> 2) : total - 1;
+    constexpr int kPix = kHeadThreads / 4;
+    const size_t stride = (size_t)gridDim.x * kPix;
+    // block-uniform trip count (the shuffles below need whole warps); a ragged tail only masks the memory ops
+    size_t pbase = (size_t)blockIdx.x * kPix;
+    auto locate = [&](size_t pb, bool& valid, size_t& p, size_t& oidx) {
+        valid = pb + (tid >> 2) < total;
+        p = valid ? pb + (tid >> 2) : total - 1;
         const size_t n = p / plane, l = p - n * plane;
-        float av[32];
-        const uint4* ap = reinterpret_cast<const uint4*>(a + p * 32);
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-            const uint4 v = __ldg(ap + g);
-            const uint32_t wv[4] = { v.x, v.y, v.z, v.w };
-#pragma unroll
-            for (int j = 0; j < 4; ++j) { av[g * 8 + 2 * j] = bf_lo(wv[j]); av[g * 8 + 2 * j + 1] = bf_hi(wv[j]); }
+        oidx = (n * 4 + q) * plane + l;
+    };
+    bool valid, nvalid = false;
+    size_t p, oidx, np = 0, noidx = 0;
+    uint4 v = make_uint4(0, 0, 0, 0), nv = make_uint4(0, 0, 0, 0);
+    float tg = 0.f, ntg = 0.f;
+    if (pbase < total) {
+        locate(pbase, valid, p, oidx);
+        v = __ldg(reinterpret_cast<const uint4*>(a + p * 32) + q);
+        if (TRAIN) tg = __ldg(target + oidx);
+    }
+    for (; pbase < total; pbase += stride) {
+        if (pbase + stride < total) {                     // prefetch the next pixel of this thread
+            locate(pbase + stride, nvalid, np, noidx);
+            nv = __ldg(reinterpret_cast<const uint4*>(a + np * 32) + q);
+            if (TRAIN) ntg = __ldg(target + noidx);
         }
-        float o = bs[co];
+        const uint32_t wv[4] = { v.x, v.y, v.z, v.w };
+        float av[8];
 #pragma unroll
-        for (int ci = 0; ci < 32; ++ci) o = fmaf(av[ci], wrow[ci], o);
-        if (valid) out[(n * 4 + co) * plane + l] = o;
+        for (int j = 0; j < 4; ++j) { av[2 * j] = bf_lo(wv[j]); av[2 * j + 1] = bf_hi(wv[j]); }
+        float o[4];
+#pragma unroll
+        for (int co = 0; co < 4; ++co) {
+            float acc = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc = fmaf(av[j], w4[co][j], acc);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+            o[co] = acc;
+        }
+        const float mine = (q == 0 ? o[0] : q == 1 ? o[1] : q == 2 ? o[2] : o[3]) + bq;
+        if (valid) out[oidx] = mine;
         if (TRAIN) {
-            const float e = valid ? o - __ldg(target + (n * 4 + co) * plane + l) : 0.f;
+            const float e = valid ? mine - tg : 0.f;
             ploss += fabsf(e);
             const float d = (e > 0.f ? inv_numel : (e < 0.f ? -inv_numel : 0.f));
             pdb += d;
-#pragma unroll
-            for (int ci = 0; ci < 32; ++ci) pdw[ci] = fmaf(d, av[ci], pdw[ci]);
             // the pixel's four dOut values (one per lane of the 4-lane group)
             const int base = lane & ~3;
-            const float d0 = __shfl_sync(0xffffffffu, d, base), d1 = __shfl_sync(0xffffffffu, d, base + 1);
-            const float d2 = __shfl_sync(0xffffffffu, d, base + 2), d3 = __shfl_sync(0xffffffffu, d, base + 3);
-            // this thread writes dz channels [8co, 8co+8)
+            float dd[4];
+#pragma unroll
+            for (int co = 0; co < 4; ++co) dd[co] = __shfl_sync(0xffffffffu, d, base + co);
             uint32_t zo[4];
 #pragma unroll
             for (int j = 0; j < 8; j += 2) {
-                const int c0 = co * 8 + j;
-                float g0 = d0 * ws[0][c0] + d1 * ws[1][c0] + d2 * ws[2][c0] + d3 * ws[3][c0];
-                float g1 = d0 * ws[0][c0 + 1] + d1 * ws[1][c0 + 1] + d2 * ws[2][c0 + 1] + d3 * ws[3][c0 + 1];
-                // av[] is indexed statically per co below to stay in registers
-                float a0 = 0.f, a1 = 0.f;
+                float g0 = 0.f, g1 = 0.f;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) if (q == co) { a0 = av[q * 8 + j]; a1 = av[q * 8 + j + 1]; }
-                g0 *= (a0 > 0.f ? 1.0f : 0.2f);
-                g1 *= (a1 > 0.f ? 1.0f : 0.2f);
+                for (int co = 0; co < 4; ++co) {
+                    pdw[co][j] = fmaf(dd[co], av[j], pdw[co][j]);
+                    pdw[co][j + 1] = fmaf(dd[co], av[j + 1], pdw[co][j + 1]);
+                    g0 = fmaf(dd[co], w4[co][j], g0);
+                    g1 = fmaf(dd[co], w4[co][j + 1], g1);
+                }
+                g0 *= (av[j] > 0.f ? 1.0f : 0.2f);
+                g1 *= (av[j + 1] > 0.f ? 1.0f : 0.2f);
                 zo[j >> 1] = pack_bf2(g0, g1);
             }
-            if (valid) reinterpret_cast<uint4*>(dz + p * 32)[co] = make_uint4(zo[0], zo[1], zo[2], zo[3]);
+            if (valid) reinterpret_cast<uint4*>(dz + p * 32)[q] = make_uint4(zo[0], zo[1], zo[2], zo[3]);
         }
+        v = nv; tg = ntg; valid = nvalid; p = np; oidx = noidx;
     }
     if (TRAIN) {
-        // reduce over the 8 lanes of a warp that share `co` (lane ^ 4, 8, 16), then shared atomics, then one global
+        // reduce over the 8 lanes of a warp that share `q` (lane ^ 4, 8, 16), then shared atomics, then one global
         // atomic per value per block
 #pragma unroll
-        for (int ci = 0; ci < 32; ++ci) {
-            float v = pdw[ci];
-            v += __shfl_xor_sync(0xffffffffu, v, 4);
-            v += __shfl_xor_sync(0xffffffffu, v, 8);
-            v += __shfl_xor_sync(0xffffffffu, v, 16);
-            if (lane < 4) atomicAdd(&red[co * 32 + ci], v);
-        }
-        float v = pdb;
-        v += __shfl_xor_sync(0xffffffffu, v, 4); v += __shfl_xor_sync(0xffffffffu, v, 8); v += __shfl_xor_sync(0xffffffffu, v, 16);
-        if (lane < 4) atomicAdd(&red[128 + co], v);
+        for (int co = 0; co < 4; ++co)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float x = pdw[co][j];
+                x += __shfl_xor_sync(0xffffffffu, x, 4);
+                x += __shfl_xor_sync(0xffffffffu, x, 8);
+                x += __shfl_xor_sync(0xffffffffu, x, 16);
+                if (lane < 4) atomicAdd(&red[co * 32 + q * 8 + j], x);
+            }
+        float x = pdb;
+        x += __shfl_xor_sync(0xffffffffu, x, 4); x += __shfl_xor_sync(0xffffffffu, x, 8); x += __shfl_xor_sync(0xffffffffu, x, 16);
+        if (lane < 4) atomicAdd(&red[128 + q], x);
         float ls = ploss;
 #pragma unroll
         for (int sft = 16; sft > 0; sft >>= 1) ls += __shfl_xor_sync(0xffffffffu, ls, sft);
         if (lane == 0) atomicAdd(&red[132], ls);
         __syncthreads();
-        if (tid < 128) atomicAdd(dw + tid, red[tid]);
-        else if (tid < 132) atomicAdd(db + (tid - 128), red[tid]);
-        else if (tid == 132) atomicAdd(loss, red[132] * inv_numel);
+        for (int i = tid; i < 133; i += kHeadThreads) {
+            if (i < 128) atomicAdd(dw + i, red[i]);
+            else if (i < 132) atomicAdd(db + (i - 128), red[i]);
+            else atomicAdd(loss, red[132] * inv_numel);
+        }
     }
 }
 
@@ -483,10 +519,10 @@ int launch_head(eld_ctx* ctx, const void* a, const float* w, const float* b, flo
     const size_t total = (size_t)n * plane;
     const float inv = 1.0f / (float)(total * 4);
     if (target) {
-        head_kernel<true><<<grid_for(total, 64 * 16, 2 * ctx->num_sms), 256, 0, st>>>(
+        head_kernel<true><<<grid_for(total, 32 * 16, 5 * ctx->num_sms), kHeadThreads, 0, st>>>(
             static_cast<const __nv_bfloat16*>(a), w, b, out, target, static_cast<__nv_bfloat16*>(dz), dw, db, loss, n, plane, inv);
     } else {
-        head_kernel<false><<<grid_for(total, 64, 8 * ctx->num_sms), 256, 0, st>>>(
+        head_kernel<false><<<grid_for(total, 32, 10 * ctx->num_sms), kHeadThreads, 0, st>>>(
             static_cast<const __nv_bfloat16*>(a), w, b, out, nullptr, nullptr, nullptr, nullptr, nullptr, n, plane, inv);
     }
     ELD_CHECK_CUDA(cudaGetLastError());
