@@ -186,6 +186,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const ConvGemmParams p
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // PDL: everything above touched only this launch's parameters, the bias and nothing the previous kernel writes;
+    // the activations (TMA loads, mask reads) and the output must wait for it.  The packed weights were written before
+    // the forward pass started and only conv / wgrad tiles release their successor early, so they are stable too.
+    ptx::grid_dep_wait();
+    ptx::grid_dep_launch();
 
     if (warp == 0) {
         // ===================== TMA producer =====================

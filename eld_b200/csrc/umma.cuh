@@ -55,6 +55,13 @@ __device__ __forceinline__ bool elect_one()
     return pred != 0;
 }
 
+// ---- programmatic dependent launch (PDL) -----------------------------------------------------------------
+// grid_dep_wait(): block until every grid this launch depends on has completed and flushed (no-op for a normal launch).
+// grid_dep_launch(): let the next kernel in the stream start launching (its CTAs become resident as ours retire and
+// run their prologue - barrier init, TMEM alloc, bias / resident-weight loads - before blocking in grid_dep_wait()).
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- TMA ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m)
 {

@@ -11,6 +11,21 @@
 
 namespace eld {
 
+// Launch with programmatic stream serialization (PDL): the kernel may start while its predecessor drains; it blocks in
+// griddepcontrol.wait before touching anything the predecessor writes.  ELD_NO_PDL=1 restores plain launches.
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, Args... args)
+{
+    static const bool no_pdl = getenv("ELD_NO_PDL") != nullptr;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = no_pdl ? 0 : 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 static int encode(eld_ctx* ctx, CUtensorMap* map, const void* ptr, int rank, const cuuint64_t* dims,
                   const cuuint64_t* strides_bytes, const cuuint32_t* box, int inner_bytes)
 {
@@ -151,7 +166,7 @@ int launch_conv_gemm(eld_ctx* ctx, const GemmOp& op, cudaStream_t st)
                 op.cin, op.taps, p.n_tile, p.n_total, op.H, op.W, p.halo, (double)total_tiles / grid,
                 m[0] / 1e3, m[1] / 1e3, m[2] / 1e3, m[3] / 1e3, m[4] / 1e3, m[5] / 1e3, m[6] / 1e3, m[7] / 1e3, m[8] / 1e3, m[9] / 1e3);
     } else {
-        conv_umma_kernel<false><<<grid, kConvThreads, smem, st>>>(tmA, p);
+        ELD_CHECK_CUDA(launch_pdl(conv_umma_kernel<false>, grid, kConvThreads, smem, st, tmA, p));
     }
     ELD_CHECK_CUDA(cudaGetLastError());
     count_launch(ctx);
@@ -177,7 +192,7 @@ template <bool PROF>
 static void launch_wg2(int grid, size_t smem, cudaStream_t st, const CUtensorMap& tmP, const CUtensorMap& tmQ, const Wgrad2Params& p)
 {
     const int rbp = p.box_ch * 2;
-#define ELD_WG2_CASE(A, N) if (rbp == A && p.n_tile == N) { wgrad_conv_kernel<PROF, A, N><<<grid, kWg2Threads, smem, st>>>(tmP, tmQ, p); return; }
+#define ELD_WG2_CASE(A, N) if (rbp == A && p.n_tile == N) { (void)launch_pdl(wgrad_conv_kernel<PROF, A, N>, grid, kWg2Threads, smem, st, tmP, tmQ, p); return; }
     ELD_WG2_CASE(64, 32) ELD_WG2_CASE(64, 64) ELD_WG2_CASE(64, 128) ELD_WG2_CASE(64, 256)
     ELD_WG2_CASE(128, 32) ELD_WG2_CASE(128, 64) ELD_WG2_CASE(128, 128) ELD_WG2_CASE(128, 256)
 #undef ELD_WG2_CASE
