@@ -11,21 +11,6 @@
 
 namespace eld {
 
-// Launch with programmatic stream serialization (PDL): the kernel may start while its predecessor drains; it blocks in
-// griddepcontrol.wait before touching anything the predecessor writes.  ELD_NO_PDL=1 restores plain launches.
-template <typename... KArgs, typename... Args>
-static cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, Args... args)
-{
-    static const bool no_pdl = getenv("ELD_NO_PDL") != nullptr;
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = no_pdl ? 0 : 1;
-    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
-}
-
 static int encode(eld_ctx* ctx, CUtensorMap* map, const void* ptr, int rank, const cuuint64_t* dims,
                   const cuuint64_t* strides_bytes, const cuuint32_t* box, int inner_bytes)
 {
@@ -365,7 +350,7 @@ int launch_wgrad(eld_ctx* ctx, const WgradOp& op, cudaStream_t st)
     }
     const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
     const int grid = p.m_tiles * p.n_tiles * p.ksplit;
-    wgrad_umma_kernel<<<grid, kWgradThreads, smem, st>>>(tmP, tmQ, p);
+    ELD_CHECK_CUDA(launch_pdl(wgrad_umma_kernel, grid, kWgradThreads, smem, st, tmP, tmQ, p));
     ELD_CHECK_CUDA(cudaGetLastError());
     count_launch(ctx);
     return ELD_OK;

@@ -84,6 +84,8 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    ptx::grid_dep_wait();       // PDL: the prologue above overlapped the previous kernel's tail
+    ptx::grid_dep_launch();
 
     if (warp == 0) {
         if (lane == 0 && nchunks > 0) {
