@@ -41,6 +41,7 @@ def _declare(lib):
     lib.eld_noise_mosaic.argtypes = [vp, vp, i32, f32, f32, vp, vp, i32, i32, i32, c.POINTER(NoiseParams),
                                      u32, u64, u64, i32, vp]
     lib.eld_noise_packed_u16.argtypes = [vp, vp, f32, vp, vp, i32, i32, i32, c.POINTER(NoiseParams), u32, u64, u64, i32, vp]
+    lib.eld_isp_process.argtypes = [vp, vp, vp, i32, i32, i32, c.POINTER(c.c_float), c.POINTER(c.c_float), f32, vp, vp, i32, vp]
     lib.eld_noise_packed_aug.argtypes = [vp, vp, vp, vp, i32, i32, i32, c.POINTER(NoiseParams), u32, u64, u64, i32,
                                          c.POINTER(c.c_uint8), vp]
     from . import _unet_abi

@@ -117,6 +117,19 @@ int eld_noise_packed_aug(eld_ctx* ctx, const float* clean, float* noisy, float* 
                          const eld_noise_params* params, uint32_t model_mask, uint64_t seed, uint64_t frame_id0,
                          int clip01, const uint8_t* aug_flags, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Raw -> sRGB rendering of the `--stage_in srgb` branch (train_syn.py:55-58): replaces util/process.py:51-68
+ * `process` - apply_gains (:15-19), clip, binning RGBG->RGB (:41-48), apply_ccms (:22-31), clip,
+ * gamma_compression (:34-39) or camera_response_function (:71-84) with its 8-bit quantisation - and the clips of
+ * ISPDataset.__getitem__ (dataset/sid_dataset.py:309,311), as one elementwise kernel.
+ *   packed: device f32 [n][4][h][w] (RGBG planes)   rgb: device f32 [n][3][h][w]
+ *   wb: HOST [n][4] white-balance gains   ccm: HOST [n][9] cam2rgb, row-major   gamma: 2.2 in the reference
+ *   crf_len == 0: gamma curve.  crf_len >= 2: crf_E device [crf_len] (irradiance grid, ascending),
+ *   crf_f device [3][crf_len] (per-channel response) - linear interpolation with torchinterp1d's formula. */
+int eld_isp_process(eld_ctx* ctx, const float* packed, float* rgb, int n, int h, int w,
+                    const float* wb, const float* ccm, float gamma,
+                    const float* crf_E, const float* crf_f, int crf_len, void* stream);
+
 /* Number of kernels the library has launched through this ctx since creation (bench.py's
  * gpu_launches evidence). */
 int64_t eld_launch_count(const eld_ctx* ctx);

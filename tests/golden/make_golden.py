@@ -18,6 +18,8 @@ Outputs
   unet_kat.npz        UNetSeeInDark(4,4) with torch.manual_seed(2018) default init:
                       input (seed 7, 1x4x32x32), target (seed 8), output, L1 loss and
                       per-parameter gradient sums/abs-sums, first-16 values of every param
+  isp_kat.npz         util/process.py `process` (gamma branch) on a seeded 2x4x16x16 RGBG batch: inputs, wb, ccm, output
+                      (torchinterp1d, needed only by the CRF branch, is stubbed at import)
   camera_params.json  the calibration dictionaries of camera_params/release/*.npy as JSON
                       (data, not code) so the GPU box needs no pickle and no reference tree
 """
@@ -139,5 +141,30 @@ def main():
     print('wrote goldens; nparam', nparam, 'loss', loss.item(), 'deconv err', arrays['deconv_identity_err'])
 
 
+def isp_golden():
+    """Run the UNMODIFIED util/process.py `process` (gamma branch).  The module imports torchinterp1d at the top
+    (process.py:9), which is not installed: a stub module satisfies the import; the gamma branch never calls it."""
+    import types
+    import torch
+    stub = types.ModuleType('torchinterp1d')
+    stub.Interp1d = object
+    sys.modules['torchinterp1d'] = stub
+    spec = importlib.util.spec_from_file_location('ref_process', os.path.join(REF, 'util', 'process.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    rs = np.random.RandomState(2018)
+    x = (rs.rand(2, 4, 16, 16) * 1.3 - 0.1).astype(np.float32)          # some values outside [0,1]: exercises the clips
+    wb = np.array([[2.1, 1.0, 1.6, 1.0], [1.8, 1.0, 2.2, 1.0]], dtype=np.float32)
+    ccm = np.array([[[1.7, -0.5, -0.2], [-0.3, 1.6, -0.3], [0.0, -0.6, 1.6]],
+                    [[1.5, -0.3, -0.2], [-0.2, 1.4, -0.2], [0.1, -0.5, 1.4]]], dtype=np.float32)
+    with torch.no_grad():
+        y = mod.process(torch.from_numpy(x), torch.from_numpy(wb), torch.from_numpy(ccm), gamma=2.2, CRF=None).numpy()
+    np.savez_compressed(os.path.join(HERE, 'isp_kat.npz'), x=x, wb=wb, ccm=ccm, y=y.astype(np.float32))
+    print('isp_kat.npz: out mean %.6f' % y.mean())
+
+
 if __name__ == '__main__':
+    if len(sys.argv) > 1 and sys.argv[1] == 'isp':
+        isp_golden()
+        sys.exit(0)
     main()
