@@ -211,7 +211,6 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const ConvGemmParams p
                 const int rem = m_tile - img * tiles_xy;
                 const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
                 const int x0 = tx * p.tile_w, y0 = ty * tile_h;
-                const int n0 = n_t * p.n_tile;
                 if (p.halo == 3) {
                     int c = p.a_c0;
                     for (int kcI = 0; kcI < kchunks; ++kcI) {

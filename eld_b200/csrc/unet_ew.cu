@@ -16,68 +16,6 @@ __device__ __forceinline__ uint32_t pack_bf2(float a, float b)
     return *reinterpret_cast<const uint32_t*>(&h);
 }
 
-// ---------------------------------------------------------------------------------------------------
-// conv1_1: x f32 NCHW [n][4][H][W] -> y bf16 NHWC [n][H][W][32] = lrelu(conv3x3(x) + b)   (Unet.py:11,49)
-// block = 16x16 pixels, halo tile in smem, weights in smem as [tap*4+ci][32].
-// ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-first_conv_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
-                  __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ x32, int H, int W)
-{
-    __shared__ float xs[4][18][18];
-    __shared__ __align__(16) float ws[36][32];
-    __shared__ float bs[32];
-    const int n = blockIdx.z, x0 = blockIdx.x * 16, y0 = blockIdx.y * 16;
-    const int tid = threadIdx.x;
-    for (int i = tid; i < 36 * 32; i += 256) {
-        const int co = i & 31, k = i >> 5;          // k = tap*4 + ci
-        const int tap = k >> 2, ci = k & 3;
-        ws[k][co] = w[(co * 4 + ci) * 9 + tap];
-    }
-    if (tid < 32) bs[tid] = b[tid];
-    const size_t plane = (size_t)H * W;
-    for (int i = tid; i < 4 * 18 * 18; i += 256) {
-        const int c = i / 324, r = (i % 324) / 18, q = i % 18;
-        const int yy = y0 + r - 1, xx = x0 + q - 1;
-        xs[c][r][q] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? x[((size_t)n * 4 + c) * plane + (size_t)yy * W + xx] : 0.0f;
-    }
-    __syncthreads();
-    const int px = tid & 15, py = tid >> 4;
-    if (y0 + py >= H || x0 + px >= W) return;
-    float acc[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) acc[j] = bs[j];
-#pragma unroll
-    for (int tap = 0; tap < 9; ++tap) {
-#pragma unroll
-        for (int ci = 0; ci < 4; ++ci) {
-            const float v = xs[ci][py + tap / 3][px + tap % 3];
-            const float4* wr = reinterpret_cast<const float4*>(&ws[tap * 4 + ci][0]);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float4 w4 = wr[j];
-                acc[4 * j] = fmaf(v, w4.x, acc[4 * j]);
-                acc[4 * j + 1] = fmaf(v, w4.y, acc[4 * j + 1]);
-                acc[4 * j + 2] = fmaf(v, w4.z, acc[4 * j + 2]);
-                acc[4 * j + 3] = fmaf(v, w4.w, acc[4 * j + 3]);
-            }
-        }
-    }
-    if (x32) {   // the input as a 32-channel NHWC bf16 tensor (channels 4..31 zero): operand of the tcgen05 wgrad
-        uint4* d32 = reinterpret_cast<uint4*>(x32 + (((size_t)n * H + (y0 + py)) * W + (x0 + px)) * 32);
-        d32[0] = make_uint4(pack_bf2(xs[0][py + 1][px + 1], xs[1][py + 1][px + 1]),
-                            pack_bf2(xs[2][py + 1][px + 1], xs[3][py + 1][px + 1]), 0u, 0u);
-        d32[1] = make_uint4(0u, 0u, 0u, 0u);
-        d32[2] = make_uint4(0u, 0u, 0u, 0u);
-        d32[3] = make_uint4(0u, 0u, 0u, 0u);
-    }
-    uint4* dst = reinterpret_cast<uint4*>(y + (((size_t)n * H + (y0 + py)) * W + (x0 + px)) * 32);
-#pragma unroll
-    for (int g = 0; g < 4; ++g)
-        dst[g] = make_uint4(pack_bf2(lrelu(acc[8 * g]), lrelu(acc[8 * g + 1])), pack_bf2(lrelu(acc[8 * g + 2]), lrelu(acc[8 * g + 3])),
-                            pack_bf2(lrelu(acc[8 * g + 4]), lrelu(acc[8 * g + 5])), pack_bf2(lrelu(acc[8 * g + 6]), lrelu(acc[8 * g + 7])));
-}
-
 // x f32 NCHW [n][4][H][W] -> x32 bf16 NHWC [n][H][W][32] (channels 4..31 zero): operand of the tcgen05 tiles for
 // conv1_1 (fprop and wgrad).  One pixel per thread: 4 coalesced plane reads, one 64-byte write.
 __global__ void __launch_bounds__(256)
@@ -93,62 +31,6 @@ pack_input_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ x32, 
         d[2] = make_uint4(0u, 0u, 0u, 0u);
         d[3] = make_uint4(0u, 0u, 0u, 0u);
     }
-}
-
-// conv1_1 weight/bias gradient: dW[32][4][3][3] += sum_p dz[p][co] x[p+tap][ci], db[co] += sum_p dz[p][co].
-// Persistent blocks over 16x16 tiles; thread (co = t&31, g = t>>5) owns k = g, g+8, ... (<36) and,
-// for g == 0, the bias.  One global atomic per accumulator per block at the end.
-__global__ void __launch_bounds__(256)
-first_conv_wgrad_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dz,
-                        float* __restrict__ dw, float* __restrict__ db, int n_img, int H, int W)
-{
-    __shared__ float xs[4][18][18];
-    __shared__ __nv_bfloat16 dzs[256][32 + 2];   // +2: pad the row to 68 B to spread banks
-    const int tid = threadIdx.x, co = tid & 31, g = tid >> 5;
-    const int tiles_x = W / 16, tiles_y = H / 16;
-    const int total = n_img * tiles_x * tiles_y;
-    const size_t plane = (size_t)H * W;
-    float acc[5] = { 0.f, 0.f, 0.f, 0.f, 0.f }, accb = 0.f;
-    int kk[5], koff[5];
-#pragma unroll
-    for (int j = 0; j < 5; ++j) {
-        const int k = g + 8 * j;                     // k = tap*4 + ci
-        kk[j] = k;
-        const int tap = (k < 36 ? k : 0) >> 2, ci = k & 3;
-        koff[j] = ci * 324 + (tap / 3) * 18 + (tap % 3);
-    }
-    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-        const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, n = tile / (tiles_x * tiles_y);
-        const int x0 = tx * 16, y0 = ty * 16;
-        __syncthreads();
-        for (int i = tid; i < 4 * 324; i += 256) {
-            const int c = i / 324, r = (i % 324) / 18, q = i % 18;
-            const int yy = y0 + r - 1, xx = x0 + q - 1;
-            xs[c][r][q] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? x[((size_t)n * 4 + c) * plane + (size_t)yy * W + xx] : 0.0f;
-        }
-        for (int i = tid; i < 256 * 16; i += 256) {   // 256 px x 16 words (32 ch)
-            const int p = i >> 4, wv = i & 15;
-            const uint32_t v = reinterpret_cast<const uint32_t*>(dz + (((size_t)n * H + (y0 + (p >> 4))) * W + (x0 + (p & 15))) * 32)[wv];
-            reinterpret_cast<uint32_t*>(&dzs[p][0])[wv] = v;
-        }
-        __syncthreads();
-        const float* xflat = &xs[0][0][0];
-        for (int p = 0; p < 256; ++p) {
-            const float d = __bfloat162float(dzs[p][co]);
-            const int pbase = (p >> 4) * 18 + (p & 15);
-            accb += d;
-#pragma unroll
-            for (int j = 0; j < 5; ++j) acc[j] = fmaf(d, xflat[koff[j] + pbase], acc[j]);
-        }
-    }
-#pragma unroll
-    for (int j = 0; j < 5; ++j) {
-        if (kk[j] < 36) {
-            const int tap = kk[j] >> 2, ci = kk[j] & 3;
-            atomicAdd(dw + (co * 4 + ci) * 9 + tap, acc[j]);
-        }
-    }
-    if (g == 0) atomicAdd(db + co, accb);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -451,30 +333,10 @@ static inline int grid_for(size_t work, int per_block, int cap)
     return (int)b;
 }
 
-int launch_first_conv(eld_ctx* ctx, const float* x, const float* w, const float* b, void* y, void* x32, int n, int H, int W, cudaStream_t st)
-{
-    dim3 grid((W + 15) / 16, (H + 15) / 16, n);
-    first_conv_kernel<<<grid, 256, 0, st>>>(x, w, b, static_cast<__nv_bfloat16*>(y), static_cast<__nv_bfloat16*>(x32), H, W);
-    ELD_CHECK_CUDA(cudaGetLastError());
-    count_launch(ctx);
-    return ELD_OK;
-}
-
 int launch_pack_input(eld_ctx* ctx, const float* x, void* x32, int n, int H, int W, cudaStream_t st)
 {
     const size_t plane = (size_t)H * W, total = plane * n;
     pack_input_kernel<<<grid_for(total, 256, 16 * ctx->num_sms), 256, 0, st>>>(x, static_cast<__nv_bfloat16*>(x32), plane, total);
-    ELD_CHECK_CUDA(cudaGetLastError());
-    count_launch(ctx);
-    return ELD_OK;
-}
-
-int launch_first_conv_wgrad(eld_ctx* ctx, const float* x, const void* dz, float* dw, float* db, int n, int H, int W, cudaStream_t st)
-{
-    ELD_REQUIRE(H % 16 == 0 && W % 16 == 0, "first-layer wgrad: H, W must be multiples of 16");
-    const int tiles = n * (H / 16) * (W / 16);
-    const int grid = tiles < 2 * ctx->num_sms ? tiles : 2 * ctx->num_sms;
-    first_conv_wgrad_kernel<<<grid, 256, 0, st>>>(x, static_cast<const __nv_bfloat16*>(dz), dw, db, n, H, W);
     ELD_CHECK_CUDA(cudaGetLastError());
     count_launch(ctx);
     return ELD_OK;

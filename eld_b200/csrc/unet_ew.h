@@ -3,9 +3,7 @@
 #include "common.cuh"
 
 namespace eld {
-int launch_first_conv(eld_ctx* ctx, const float* x, const float* w, const float* b, void* y, void* x32, int n, int H, int W, cudaStream_t st);
 int launch_pack_input(eld_ctx* ctx, const float* x, void* x32, int n, int H, int W, cudaStream_t st);
-int launch_first_conv_wgrad(eld_ctx* ctx, const float* x, const void* dz, float* dw, float* db, int n, int H, int W, cudaStream_t st);
 int launch_maxpool(eld_ctx* ctx, const void* in, int in_pitch, int in_c0, void* out, int C, int n, int Ho, int Wo, cudaStream_t st);
 int launch_maxpool_bwd(eld_ctx* ctx, const void* A, const void* dskip, int a_pitch, int a_c0, const void* dP, void* dZ,
                        int C, int n, int Ho, int Wo, cudaStream_t st);
