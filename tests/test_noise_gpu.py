@@ -320,3 +320,57 @@ def test_sample_augment_follows_the_reference_rng_order(torch):
     np.random.seed(77)
     want = [sum(b for b in (1, 2, 4) if np.random.randint(2, size=1)[0] == 1) for _ in range(5)]
     assert got.tolist() == want
+
+
+def test_config3_full_eld_batch32_structure(torch):
+    """BASELINE configs[3]: full ELD noise (P + Tukey-lambda read + row + quantisation [+ colour bias]), batch 32 of
+    4x512x512, sharded 4 frames per rank over 8 ranks.  Size-independent properties: the frames do not depend on the
+    sharding (global frame ids), row noise is ONE draw per sensor row (planes 0,1 share row 2i; planes 3,2 share row
+    2i+1, noise.py:16-19) with the calibrated sigma, quantisation noise stays within half a step."""
+    from eld_b200.noise import NoiseModel
+    nm = NoiseModel('P+G+B+R+U', include=4, verbose=False, seed=99)
+    y = torch.rand(32, 4, 512, 512, device='cuda')
+    whole = nm.batch_gpu(y, params=FULL, frame_id0=640, clip=True)
+    for rank in range(8):
+        part = nm.batch_gpu(y[4 * rank:4 * rank + 4], params=FULL, frame_id0=640 + 4 * rank, clip=True)
+        assert torch.equal(part, whole[4 * rank:4 * rank + 4]), 'rank %d' % rank
+    assert torch.isfinite(whole).all() and whole.min() >= 0 and whole.max() <= 1
+    sat, ratio = FULL['saturation'], FULL['ratio']
+    flat = torch.full((2, 4, 512, 512), 0.5, device='cuda')
+    r = (NoiseModel('R', include=4, verbose=False, seed=5).batch_gpu(flat, params=FULL, frame_id0=0, clip=False) - flat) * sat / ratio
+    assert (r - r[..., :1]).abs().max() < 1e-3                       # constant along a packed row
+    assert torch.allclose(r[:, 0], r[:, 1], atol=1e-3) and torch.allclose(r[:, 3], r[:, 2], atol=1e-3)
+    assert not torch.allclose(r[:, 0], r[:, 2], atol=1e-3)           # even and odd sensor rows are independent draws
+    rows = torch.cat([r[:, 0, :, 0], r[:, 2, :, 0]]).double()       # 2 frames x 512 x 2 independent normals
+    assert abs(rows.std().item() / FULL['R_scale'] - 1) < 0.06 and abs(rows.mean().item()) < 0.1
+    u = (NoiseModel('U', include=4, verbose=False, seed=5).batch_gpu(flat, params=FULL, frame_id0=0, clip=False) - flat) * sat / ratio
+    assert u.abs().max() <= 0.5 * FULL['q_step'] + 1e-3
+    assert abs(u.double().var().item() / (FULL['q_step'] ** 2 / 12) - 1) < 0.01
+
+
+def test_config4_full_frame_camera_sweep(torch):
+    """BASELINE configs[4]: 4-camera parameter sweep on full 4256x2848 frames (packed 4x1424x2128), frames sharded
+    round-robin.  One launch over the four frames == four single-frame launches; moments per camera as calibrated."""
+    from eld_b200.noise import NoiseModel
+    frames, plist = [], []
+    for cam in range(1, 5):                                  # include = 1..4 (noise.py:179-182)
+        nm_c = NoiseModel('p+g', include=cam, verbose=False, seed=7)
+        np.random.seed(100 + cam)
+        plist.append(nm_c._sample_params())
+    nm = NoiseModel('p+g', include=4, verbose=False, seed=7)
+    y = torch.full((4, 4, 1424, 2128), 0.25, device='cuda')
+    z = nm.batch_gpu(y, params=plist, frame_id0=1000, clip=False)
+    for f in range(4):
+        one = nm.batch_gpu(y[f:f + 1], params=[plist[f]], frame_id0=1000 + f, clip=False)
+        assert torch.equal(one[0], z[f])
+        K, g, sat, ratio = plist[f]
+        var = (ratio / sat) ** 2 * (K * 0.25 * sat / ratio + g * g)
+        zf = z[f].double()
+        assert abs(zf.mean().item() - 0.25) < 6 * (var / zf.numel()) ** 0.5
+        assert abs(zf.var().item() / var - 1) < 0.01
+    # the mosaic entry point on the same full frames: bit-equal to packing first (noise.py:10-20)
+    m = torch.rand(1, 2848, 4256, device='cuda')
+    packed = torch.stack([m[:, 0::2, 0::2], m[:, 0::2, 1::2], m[:, 1::2, 1::2], m[:, 1::2, 0::2]], dim=1).contiguous()
+    a, clean = nm.mosaic_gpu(m, black=0.0, white=1.0, params=[plist[0]], frame_id0=5, clip=True)
+    b = nm.batch_gpu(packed, params=[plist[0]], frame_id0=5, clip=True)
+    assert torch.equal(clean, packed) and torch.equal(a, b)
