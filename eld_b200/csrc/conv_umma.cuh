@@ -51,6 +51,8 @@ struct ConvGemmParams {
                           // 8 = skip the activation TMA loads (full-halo modes), 16 = skip the MMAs
     int acc_stages;       // TMEM accumulator ring depth (2..8, even): acc_stages * n_tile <= 512 columns
     int cout_shift;       // EPI_SHUFFLE: log2(cout) (cout must be a power of two)
+    __nv_bfloat16* pool_out;   // optional fused MaxPool2d(2) of the (activated) output: bf16 NHWC [n][H/2][W/2][pool_pitch]
+    int pool_pitch;
     long long* prof;      // PROF instantiation only
     int bias_smem_off;    // byte offset (from the 1024-aligned base) of the per-CTA bias copy
 };
@@ -540,6 +542,30 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const ConvGemmParams p
                             const float s_hi = __uint_as_float((aw[j] & 0x80000000u) | 0x3F800000u);
                             v[g * 8 + 2 * j] *= __fmaf_rn(s_lo, 0.4f, 0.6f);
                             v[g * 8 + 2 * j + 1] *= __fmaf_rn(s_hi, 0.4f, 0.6f);
+                        }
+                    }
+                }
+                if (p.pool_out) {
+                    // MaxPool2d(2) (Unet.py:13,51-63) fused: the 2x2 window of pixel (x, y) lives in lanes ^1 (x) and ^tile_w (y)
+                    // of this warp.  max commutes with the monotone bf16 rounding, so pooling the fp32 values and rounding once
+                    // equals pooling the stored bf16 activations.  H, W and the tile origin are even: a window is wholly in or out.
+                    float pm[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float a = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 1));
+                        pm[j] = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, p.tile_w));
+                    }
+                    if (in_img && !((x | y) & 1)) {
+                        uint4* q4 = reinterpret_cast<uint4*>(p.pool_out + ((size_t)(img * (p.H >> 1) + (y >> 1)) * (p.W >> 1) + (x >> 1)) * p.pool_pitch + col);
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            uint32_t w[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const __nv_bfloat162 h = __floats2bfloat162_rn(pm[g * 8 + 2 * j], pm[g * 8 + 2 * j + 1]);
+                                w[j] = *reinterpret_cast<const uint32_t*>(&h);
+                            }
+                            q4[g] = make_uint4(w[0], w[1], w[2], w[3]);
                         }
                     }
                 }

@@ -50,6 +50,29 @@ __device__ __forceinline__ int find_entry(const PackTable& T, int tile, int& loc
     return k;
 }
 
+// packed_index (unet_prims.h) with everything that is uniform over a 32 x 32 tile hoisted: rows n0..n0+31 and K
+// channels c0..c0+31 stay inside one n-tile and one channel chunk, so only the row / in-chunk channel vary.
+struct PackTileBase { size_t base0, tap_stride; int r0, cc0, kc; };
+__device__ __forceinline__ PackTileBase pack_tile_base(int rows, int ck, int taps, int n0, int c0)
+{
+    const int n_tile = rows <= 256 ? rows : 256;
+    const int kc = (ck % 64 == 0) ? 64 : 32;
+    const int kchunks = ck / kc;
+    const int nt = n0 / n_tile, chunk = c0 / kc;
+    PackTileBase b;
+    b.tap_stride = (size_t)kchunks * n_tile * kc;
+    b.base0 = ((size_t)nt * taps * kchunks + chunk) * ((size_t)n_tile * kc);
+    b.r0 = n0 - nt * n_tile; b.cc0 = c0 - chunk * kc; b.kc = kc;
+    return b;
+}
+__device__ __forceinline__ size_t pack_tile_index(const PackTileBase& b, int tap, int dn, int dc)
+{
+    const int r = b.r0 + dn, cc = b.cc0 + dc, rb = b.kc * 2;
+    const int swz = rb == 128 ? (r & 7) : ((r >> 1) & 3);
+    const int byte = r * rb + ((((cc * 2) >> 4) ^ swz) << 4) + ((cc * 2) & 15);
+    return b.base0 + (size_t)tap * b.tap_stride + (size_t)(byte >> 1);
+}
+
 // one launch packs every layer's fp32 master weights into both bf16 GEMM operands (fprop + dgrad).
 // A block moves a (32 x 32 x taps) tile through shared memory so that reads are 1 KB runs and writes are
 // 64-byte runs in both destination layouts.
@@ -81,15 +104,16 @@ pack_all_kernel(const float* __restrict__ params, __nv_bfloat16* __restrict__ pa
             }
             __syncthreads();
             // two adjacent K elements per thread: 4-byte stores (pairs never straddle a 16-byte swizzle chunk)
+            const PackTileBase bf = pack_tile_base(e.cout, e.cin, 9, co0, ci0), bd = pack_tile_base(e.cin, e.cout, 9, ci0, co0);
             for (int i = threadIdx.x; i < 32 * 144; i += 256) {       // fprop: [co][t][ci]
                 const int ci = (i & 15) * 2, t = (i >> 4) % 9, co = i / 144;
                 const __nv_bfloat162 v2 = __floats2bfloat162_rn(tile[co][ci * 9 + t], tile[co][(ci + 1) * 9 + t]);
-                *reinterpret_cast<__nv_bfloat162*>(of + packed_index(e.cout, e.cin, 9, co0 + co, t, ci0 + ci)) = v2;
+                *reinterpret_cast<__nv_bfloat162*>(of + pack_tile_index(bf, t, co, ci)) = v2;
             }
             for (int i = threadIdx.x; i < 32 * 144; i += 256) {       // dgrad: [ci][8-t][co]
                 const int co = (i & 15) * 2, t = (i >> 4) % 9, ci = i / 144;
                 const __nv_bfloat162 v2 = __floats2bfloat162_rn(tile[co][ci * 9 + t], tile[co + 1][ci * 9 + t]);
-                *reinterpret_cast<__nv_bfloat162*>(od + packed_index(e.cin, e.cout, 9, ci0 + ci, 8 - t, co0 + co)) = v2;
+                *reinterpret_cast<__nv_bfloat162*>(od + pack_tile_index(bd, 8 - t, ci, co)) = v2;
             }
         }
     } else {                              // deconv wt[ci][co][s]
@@ -339,7 +363,8 @@ struct Runner {
     const __nv_bfloat16* wd(int i) const { return u->packed + u->L[i].wd_off; }
     const float* bias(int i) const { return params + u->L[i].b_off; }
 
-    int conv(int li, const void* x, int xp, int xc0, void* y, int yp, int yc0, int lvl) const
+    // pool_dst != nullptr: MaxPool2d(2) of the output fused into the tile's epilogue (pooled tensor has cout channels)
+    int conv(int li, const void* x, int xp, int xc0, void* y, int yp, int yc0, int lvl, void* pool_dst = nullptr) const
     {
         const Layer& l = u->L[li];
         GemmOp op{};
@@ -347,6 +372,7 @@ struct Runner {
         op.n_img = u->n; op.H = u->H >> lvl; op.W = u->W >> lvl;
         op.b = wf(li); op.n_total = l.cout; op.cout = l.cout;
         op.epi_mode = EPI_STORE; op.act = ACT_LRELU; op.out = y; op.out_pitch = yp; op.out_c0 = yc0; op.bias = bias(li);
+        op.pool_out = pool_dst; op.pool_pitch = l.cout;
         const double px = (double)u->n * op.H * op.W;
         Scope sc(u, st, l.name, "fprop", 2.0 * px * l.cout * 9 * l.cin, px * 2 * (l.cin + l.cout) + 18.0 * l.cin * l.cout);
         return launch_conv_gemm(ctx(), op, st);
@@ -444,6 +470,7 @@ struct Runner {
     int forward(const float* x) const
     {
         eld_unet* U = u;
+        static const bool fuse_pool = getenv("ELD_NO_FUSED_POOL") == nullptr;   // (A/B: the stand-alone pool kernel)
         TRY(pack());
         {
             const double px = (double)U->n * U->H * U->W;
@@ -460,13 +487,13 @@ struct Runner {
             Scope sc(u, st, "conv1_1", "fprop", 2.0 * px * 32 * 36, px * (64 + 64));
             TRY(launch_conv_gemm(ctx(), op, st));
         }
-        TRY(conv(I_C12, U->a1_1, 32, 0, U->cat9, 64, 32, 0));  TRY(pool(U->cat9, 64, 32, U->p1, 32, 1));
+        if (fuse_pool) { TRY(conv(I_C12, U->a1_1, 32, 0, U->cat9, 64, 32, 0, U->p1)); } else { TRY(conv(I_C12, U->a1_1, 32, 0, U->cat9, 64, 32, 0)); TRY(pool(U->cat9, 64, 32, U->p1, 32, 1)); }      // + pool (Unet.py:51)
         TRY(conv(I_C21, U->p1, 32, 0, U->a2_1, 64, 0, 1));
-        TRY(conv(I_C22, U->a2_1, 64, 0, U->cat8, 128, 64, 1)); TRY(pool(U->cat8, 128, 64, U->p2, 64, 2));
+        if (fuse_pool) { TRY(conv(I_C22, U->a2_1, 64, 0, U->cat8, 128, 64, 1, U->p2)); } else { TRY(conv(I_C22, U->a2_1, 64, 0, U->cat8, 128, 64, 1)); TRY(pool(U->cat8, 128, 64, U->p2, 64, 2)); }     // + pool (Unet.py:55)
         TRY(conv(I_C31, U->p2, 64, 0, U->a3_1, 128, 0, 2));
-        TRY(conv(I_C32, U->a3_1, 128, 0, U->cat7, 256, 128, 2)); TRY(pool(U->cat7, 256, 128, U->p3, 128, 3));
+        if (fuse_pool) { TRY(conv(I_C32, U->a3_1, 128, 0, U->cat7, 256, 128, 2, U->p3)); } else { TRY(conv(I_C32, U->a3_1, 128, 0, U->cat7, 256, 128, 2)); TRY(pool(U->cat7, 256, 128, U->p3, 128, 3)); }   // + pool (Unet.py:59)
         TRY(conv(I_C41, U->p3, 128, 0, U->a4_1, 256, 0, 3));
-        TRY(conv(I_C42, U->a4_1, 256, 0, U->cat6, 512, 256, 3)); TRY(pool(U->cat6, 512, 256, U->p4, 256, 4));
+        if (fuse_pool) { TRY(conv(I_C42, U->a4_1, 256, 0, U->cat6, 512, 256, 3, U->p4)); } else { TRY(conv(I_C42, U->a4_1, 256, 0, U->cat6, 512, 256, 3)); TRY(pool(U->cat6, 512, 256, U->p4, 256, 4)); }   // + pool (Unet.py:63)
         TRY(conv(I_C51, U->p4, 256, 0, U->a5_1, 512, 0, 4));
         TRY(conv(I_C52, U->a5_1, 512, 0, U->a5_2, 512, 0, 4));
         TRY(deconv(I_UP6, U->a5_2, 512, U->cat6, 512, 4));

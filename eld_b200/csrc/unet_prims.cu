@@ -52,6 +52,9 @@ int launch_conv_gemm(eld_ctx* ctx, const GemmOp& op, cudaStream_t st)
     p.bias = op.bias;
     p.aux = static_cast<const __nv_bfloat16*>(op.aux); p.aux_pitch = op.aux_pitch; p.aux_c0 = op.aux_c0;
     p.cout = op.cout;
+    ELD_REQUIRE(op.pool_out == nullptr || (op.epi_mode == EPI_STORE && op.H % 2 == 0 && op.W % 2 == 0),
+                "conv tile: the fused max pool needs a plain store epilogue and even H, W");
+    p.pool_out = static_cast<__nv_bfloat16*>(op.pool_out); p.pool_pitch = op.pool_pitch;
     const int rb = p.kc * 2;
     const int b_tile = p.n_tile * rb;
     const int b_total = op.taps * (op.cin / p.kc) * b_tile;

@@ -42,6 +42,8 @@ struct GemmOp {
     const float* bias;
     const void* aux;
     int aux_pitch, aux_c0;
+    void* pool_out = nullptr;   // optional fused 2x2 max pool of the activated output (EPI_STORE only)
+    int pool_pitch = 0;
 };
 
 struct WgradOp {
