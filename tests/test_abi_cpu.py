@@ -96,3 +96,29 @@ def test_noise_model_ctor_contract():
     p = full._sample_params_full()
     assert set(p) >= {'K', 'g_scale', 'G_scale', 'G_lambda', 'R_scale', 'color_bias', 'ratio', 'q_step'}
     assert 100 <= p['ratio'] <= 300 and 0.1 <= p['K'] <= 30 and len(p['color_bias']) == 4
+
+
+def test_sample_augment_follows_the_reference_rng_order():
+    """Three randint(2) draws per frame in the reference's order (sid_dataset.py:344,347,350) - host logic, no GPU."""
+    from eld_b200.noise import NoiseModel
+    np.random.seed(77)
+    got = NoiseModel.sample_augment(5)
+    np.random.seed(77)
+    want = [sum(b for b in (1, 2, 4) if np.random.randint(2, size=1)[0] == 1) for _ in range(5)]
+    assert got.tolist() == want and got.dtype == np.uint8
+
+
+def test_read_emor_and_load_crf(tmp_path):
+    """util/process.py:147-175 restated: EMoR text blocks and the per-channel CRF table (synthetic files, same format)."""
+    from eld_b200 import process
+    E = np.linspace(0, 1, 1024)
+    with open(tmp_path / 'emor.txt', 'w') as f:
+        for name, arr in (('E', E), ('f0', E ** 0.5), ('h( 1)', np.sin(E))):
+            f.write('%s =\n' % name)
+            for i in range(0, 1024, 4):
+                f.write(' '.join('%.6e' % v for v in arr[i:i + 4]) + '\n')
+    np.savetxt(tmp_path / 'CRF_SonyA7S2_5.txt', np.stack([E ** 0.4, E ** 0.45, E ** 0.5]))
+    e, f0, H = process.read_emor(str(tmp_path / 'emor.txt'))
+    assert e.shape == (1024,) and np.allclose(e, E, atol=1e-6) and np.allclose(f0, E ** 0.5, atol=1e-6) and H.shape == (1, 1024)
+    Erep, fs = process.load_CRF(str(tmp_path))
+    assert Erep.shape == (3, 1024) and fs.shape == (3, 1024) and np.allclose(Erep[2], E, atol=1e-6)

@@ -311,17 +311,6 @@ def test_fused_augmentation_is_an_exact_index_map(torch, model):
         nm.batch_gpu_augmented(c2, aug=np.array([4, 0], dtype=np.uint8), params=SONY, frame_id0=7)
 
 
-@pytest.mark.gpu
-def test_sample_augment_follows_the_reference_rng_order(torch):
-    """Three randint(2) draws per frame in the reference's order (sid_dataset.py:344,347,350)."""
-    from eld_b200.noise import NoiseModel
-    np.random.seed(77)
-    got = NoiseModel.sample_augment(5)
-    np.random.seed(77)
-    want = [sum(b for b in (1, 2, 4) if np.random.randint(2, size=1)[0] == 1) for _ in range(5)]
-    assert got.tolist() == want
-
-
 def test_config3_full_eld_batch32_structure(torch):
     """BASELINE configs[3]: full ELD noise (P + Tukey-lambda read + row + quantisation [+ colour bias]), batch 32 of
     4x512x512, sharded 4 frames per rank over 8 ranks.  Size-independent properties: the frames do not depend on the
