@@ -206,7 +206,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(local) if rank == 0 else None      # one nvidia-smi poller per job, not per rank
     extra = {}
     if a.workload == 'noise':
         # two alternating input/output sets so no step re-reads lines the previous one left in L2
@@ -241,14 +241,15 @@ def main():
         step(i)
     barrier()
     l0 = _lib.launch_count(local)
-    sampler.start()
+    if sampler is not None:
+        sampler.start()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     ev[0].record()
     for i in range(a.steps):
         step(a.warmup + i)
     ev[1].record()
     barrier()
-    clocks = sampler.stop()
+    clocks = sampler.stop() if sampler is not None else None
     ms = ev[0].elapsed_time(ev[1])
     launches = _lib.launch_count(local) - l0
     t = torch.tensor([ms], device=dev)
@@ -289,7 +290,7 @@ def main():
            'gpu_launches': launches, 'roofline': roof}
     out.update(extra)
     if rank == 0:
-        if not a.no_cpu_baseline:
+        if not a.no_cpu_baseline and world == 1:      # the CPU baseline is timed at N = 1 only (the other ranks would idle)
             out['cpu_baseline'] = cpu_baseline(a)
         print(json.dumps(out))
     if world > 1:
