@@ -84,15 +84,22 @@ def launch_count(device=0):
 
 
 def model_mask(model):
-    """Reference semantics (noise.py:158-166): substring tests on the model string; 'P' wins over
-    'p'.  Extra letters G (Tukey-lambda), B (colour bias), R (row), U (quantisation) select the
-    paper-restated terms."""
+    """Reference semantics (noise.py:158-166): substring tests for 'P', 'p', 'g' on the model string; 'P' wins over
+    'p'; every other character is ignored (so the README's names 'G+P', 'G+P*' mean what they mean in the reference).
+    The paper-restated terms - G (Tukey-lambda), B (colour bias), R (row), U (quantisation), NOT in the reference -
+    are an explicit opt-in: the string must start with 'ELD:' (e.g. 'ELD:P+G+B+R+U')."""
+    full = is_full_model(model)
+    body = model[4:] if full else model
     m = 0
-    if 'P' in model:
+    if 'P' in body:
         m |= MODEL_BITS['P']
-    elif 'p' in model:
+    elif 'p' in body:
         m |= MODEL_BITS['p']
-    for ch in 'gGBRU':
-        if ch in model:
+    for ch in ('gGBRU' if full else 'g'):
+        if ch in body:
             m |= MODEL_BITS[ch]
     return m
+
+
+def is_full_model(model):
+    return model.startswith('ELD:')

@@ -28,5 +28,8 @@ def declare_engine(lib):
     lib.eld_unet_forward.argtypes = [vp, vp, vp, vp, vp]
     lib.eld_unet_train_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
     lib.eld_adam_step.argtypes = [vp, vp, vp, vp, vp, sz, f32, f32, f32, f32, f32, i32, f32, vp]
+    lib.eld_unet_grad_buckets.argtypes = [c.POINTER(sz), i32]
+    lib.eld_unet_bucket_events.argtypes = [vp, i32]
+    lib.eld_unet_wait_bucket.argtypes = [vp, i32, vp]
     lib.eld_unet_profile.argtypes = [vp, i32]
     lib.eld_unet_profile_read.argtypes = [vp, i32, c.c_char_p, vp, vp, vp, c.POINTER(i32)]

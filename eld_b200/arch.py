@@ -46,6 +46,7 @@ class UNetSeeInDark(nn.Module):
         self._flat = None
         self._flat_grad = None
         self._engines = {}
+        self._ddp_ready = None
         self._flatten()
 
     # ---- flat parameter storage --------------------------------------------------------------------
@@ -63,7 +64,27 @@ class UNetSeeInDark(nn.Module):
             p.grad = grad[off:off + n].view(p.shape)
             off += n
         self._flat, self._flat_grad = flat, grad
-        self._engines = {}
+        self._drop_engines()
+
+    _MAX_ENGINES = 4      # (n, h, w, train) launch plans kept alive, least recently used evicted (each owns a workspace)
+
+    def _drop_engines(self, keep=0):
+        eng = getattr(self, '_engines', None) or {}
+        while len(eng) > keep:
+            key = next(iter(eng))
+            handle, _ws = eng.pop(key)
+            try:
+                _lib.load().eld_unet_destroy(handle)
+            except Exception:
+                pass
+        self._engines = eng
+        self._ddp_ready = None
+
+    def __del__(self):
+        try:
+            self._drop_engines()
+        except Exception:
+            pass
 
     def _apply(self, fn, *a, **k):
         out = super()._apply(fn, *a, **k)
@@ -85,7 +106,10 @@ class UNetSeeInDark(nn.Module):
     # ---- engine ------------------------------------------------------------------------------------
     def _engine(self, n, h, w, train):
         key = (n, h, w, bool(train))
-        if key not in self._engines:
+        if key in self._engines:
+            self._engines[key] = self._engines.pop(key)          # most recently used last
+        else:
+            self._drop_engines(keep=self._MAX_ENGINES - 1)
             lib = _lib.load()
             dev = self._flat.device
             assert dev.type == 'cuda', 'the B200 engine has no CPU path'
@@ -122,18 +146,46 @@ class UNetSeeInDark(nn.Module):
         return out, loss
 
 
-    def profile(self, x, target, steps=3):
-        """Per-launch CUDA-event timings of `steps` training steps: list of dicts
-        {name, ms (mean), flops, bytes} in launch order (see eld_unet_profile in the C ABI)."""
-        import numpy as np
-        lib = _lib.load()
+    # ---- data parallel: bucketed all-reduce overlapped with backward (SURVEY 8e) ----------------------
+    def grad_buckets(self):
+        """[(offset, count)] of the flat gradient in backward-completion order (decoder, bottleneck, encoder)."""
+        import ctypes as c
+        arr = (c.c_size_t * 6)()
+        k = _lib.load().eld_unet_grad_buckets(arr, 6)
+        return [(int(arr[2 * i]), int(arr[2 * i + 1])) for i in range(k)]
+
+    def train_step_ddp(self, x, target, loss_out=None, group=None):
+        """train_step + SUM all-reduce of the flat gradient, bucket by bucket on a side stream: bucket k's NCCL kernel
+        waits only for the event the engine records when that bucket is final, so the decoder and bottleneck
+        gradients travel while the encoder's backward still runs; the calling stream waits for all buckets at the end
+        (Adam follows).  No host synchronisation."""
+        import torch.distributed as dist
         n, _, h, w = x.shape
         eng = self._engine(n, h, w, True)
-        self.train_step(x, target)
+        lib = _lib.load()
+        if not getattr(self, '_ddp_ready', None) == eng.value:
+            _lib.check(lib.eld_unet_bucket_events(eng, 1), 'eld_unet_bucket_events')
+            self._ddp_ready = eng.value
+            self._ddp_stream = torch.cuda.Stream(device=x.device)
+            self._ddp_buckets = self.grad_buckets()
+        out, loss = self.train_step(x, target, loss_out=loss_out)
+        works = []
+        with torch.cuda.stream(self._ddp_stream):
+            for k, (off, cnt) in enumerate(self._ddp_buckets):
+                _lib.check(lib.eld_unet_wait_bucket(eng, k, ctypes.c_void_p(self._ddp_stream.cuda_stream)), 'eld_unet_wait_bucket')
+                works.append(dist.all_reduce(self._flat_grad[off:off + cnt], group=group, async_op=True))
+        for wk in works:
+            wk.wait()                     # stream-side wait: the current stream waits for the NCCL kernels
+        return out, loss
+
+    def _profile(self, eng, run, steps):
+        import numpy as np
+        lib = _lib.load()
+        run()
         acc = None
         for _ in range(steps):
             lib.eld_unet_profile(eng, 1)
-            self.train_step(x, target)
+            run()
             cap = 512
             names = ctypes.create_string_buffer(32 * cap)
             ms = np.zeros(cap, np.float32)
@@ -154,6 +206,17 @@ class UNetSeeInDark(nn.Module):
         for a in acc:
             a['ms'] /= steps
         return acc
+
+    def profile(self, x, target, steps=3):
+        """Per-launch CUDA-event timings of `steps` training steps: list of dicts
+        {name, ms (mean), flops, bytes} in launch order (see eld_unet_profile in the C ABI)."""
+        n, _, h, w = x.shape
+        return self._profile(self._engine(n, h, w, True), lambda: self.train_step(x, target), steps)
+
+    def profile_forward(self, x, steps=3):
+        """Same for the inference launch sequence."""
+        n, _, h, w = x.shape
+        return self._profile(self._engine(n, h, w, False), lambda: self.forward(x), steps)
 
 
 class FusedAdam(torch.optim.Optimizer):

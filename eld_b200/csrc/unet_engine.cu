@@ -33,6 +33,13 @@ constexpr int kNumLayers = sizeof(kLayers) / sizeof(kLayers[0]);
 enum { I_C11 = 0, I_C12, I_C21, I_C22, I_C31, I_C32, I_C41, I_C42, I_C51, I_C52, I_UP6, I_C61, I_C62, I_UP7,
        I_C71, I_C72, I_UP8, I_C81, I_C82, I_UP9, I_C91, I_C92, I_C10 };
 
+constexpr int kGradBuckets = 3;
+// first table entry (state_dict order without conv1_1 / conv10_1) of each bucket's tile range: upv6.., conv5_1.., conv1_2..
+constexpr int kBucketEntry0[kGradBuckets] = { 9, 7, 0 };
+constexpr int kBucketEntry1[kGradBuckets] = { 21, 9, 7 };
+constexpr int kBucketLayer0[kGradBuckets] = { 10 /*upv6*/, 8 /*conv5_1*/, 0 /*conv1_1*/ };
+constexpr int kBucketLayer1[kGradBuckets] = { 23, 10, 8 };   // one past the last layer
+
 struct PackEntry { unsigned long long src, dst_f, dst_d; int cout, cin, type; int pad; };
 struct PackTable {
     PackEntry e[kNumLayers];
@@ -139,12 +146,16 @@ pack_all_kernel(const float* __restrict__ params, __nv_bfloat16* __restrict__ pa
 
 // staging [tap][ci][co] -> PyTorch OIHW [co][ci][tap]; one block per (32 co x 32 ci) tile of one layer
 __global__ void __launch_bounds__(256)
-wgrad_permute_kernel(const float* __restrict__ gtmp, float* __restrict__ grads, const __grid_constant__ PackTable T)
+wgrad_permute_kernel(const float* __restrict__ gtmp, float* __restrict__ grads, const __grid_constant__ PackTable T,
+                     int tile_begin, int tile_end)
 {
+    // blocks [0, tile_end - tile_begin) move the table tiles [tile_begin, tile_end) (one gradient bucket); any further
+    // blocks (launched with the last bucket only) move conv1_1
     __shared__ float tile[9][32][33];
-    if ((int)blockIdx.x >= T.tile0[T.n]) {   // conv1_1: staging is [9][32 (4 real)][32] behind the regular area; dst [32][4][9] at offset 0
+    const int gtile = (int)blockIdx.x + tile_begin;
+    if (gtile >= tile_end) {   // conv1_1: staging is [9][32 (4 real)][32] behind the regular area; dst [32][4][9] at offset 0
         const float* src = gtmp + T.first_stage;
-        const int b = (int)blockIdx.x - T.tile0[T.n], nb = (int)gridDim.x - T.tile0[T.n];
+        const int b = gtile - tile_end, nb = (int)gridDim.x - (tile_end - tile_begin);
         for (int i = b * 256 + threadIdx.x; i < 32 * 36; i += nb * 256) {
             const int co = i / 36, r = i - co * 36, ci = r / 9, tap = r - ci * 9;
             grads[T.first_dst + i] = src[(tap * 32 + ci) * 32 + co];
@@ -152,7 +163,7 @@ wgrad_permute_kernel(const float* __restrict__ gtmp, float* __restrict__ grads, 
         return;
     }
     int t;
-    const PackEntry& e = T.e[find_entry(T, (int)blockIdx.x, t)];
+    const PackEntry& e = T.e[find_entry(T, gtile, t)];
     if (e.type != L_CONV3) return;
     const int ct = e.cout / 32;
     {
@@ -189,6 +200,8 @@ struct eld_unet {
     __nv_bfloat16* packed;
     float* gtmp = nullptr;
     PackTable table;
+    // gradient buckets in backward-completion order (data-parallel overlap): decoder, bottleneck, encoder
+    cudaEvent_t bucket_ev[kGradBuckets] = { nullptr, nullptr, nullptr };
     // optional per-launch profile (CUDA events on the launch stream)
     bool profile = false;
     struct Rec { char name[32]; double flops, bytes; cudaEvent_t e0, e1; };
@@ -295,6 +308,7 @@ extern "C" int eld_unet_create(eld_ctx* ctx, int n, int h, int w, int train, voi
     ELD_REQUIRE(ctx && out && workspace, "eld_unet_create: NULL argument");
     ELD_REQUIRE(n > 0 && h > 0 && w > 0, "eld_unet_create: bad shape");
     ELD_REQUIRE(h % 16 == 0 && w % 16 == 0, "eld_unet_create: H and W must be multiples of 16 (four 2x2 pools, like the reference); got %dx%d", h, w);
+    ELD_CHECK_CUDA(cudaSetDevice(ctx->device));
     ELD_REQUIRE(!train || (h % 128 == 0 && w % 256 == 0),
                 "eld_unet_create: TRAINING needs H %% 128 == 0 and W %% 256 == 0 (whole 8x16 / 8x8 gradient tiles at 1/16 scale); got %dx%d", h, w);
     eld_unet* u = new (std::nothrow) eld_unet();
@@ -330,7 +344,47 @@ extern "C" int eld_unet_create(eld_ctx* ctx, int n, int h, int w, int train, voi
     return ELD_OK;
 }
 
-extern "C" void eld_unet_destroy(eld_unet* u) { delete u; }
+extern "C" void eld_unet_destroy(eld_unet* u)
+{
+    if (!u) return;
+    for (int k = 0; k < kGradBuckets; ++k) if (u->bucket_ev[k]) cudaEventDestroy(u->bucket_ev[k]);
+    for (auto& r : u->recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    delete u;
+}
+
+extern "C" int eld_unet_grad_buckets(size_t* offsets, int max_offsets)
+{
+    eld_unet tmp{};
+    init_layers(&tmp);
+    if (offsets) {
+        ELD_REQUIRE(max_offsets >= 2 * kGradBuckets, "eld_unet_grad_buckets: need room for %d (offset, count) pairs", kGradBuckets);
+        for (int k = 0; k < kGradBuckets; ++k) {
+            const size_t b = tmp.L[kBucketLayer0[k]].w_off;
+            const size_t e = kBucketLayer1[k] == kNumLayers ? tmp.n_params : tmp.L[kBucketLayer1[k]].w_off;
+            offsets[2 * k] = b; offsets[2 * k + 1] = e - b;
+        }
+    }
+    return kGradBuckets;
+}
+
+extern "C" int eld_unet_bucket_events(eld_unet* u, int enable)
+{
+    ELD_REQUIRE(u, "eld_unet_bucket_events: NULL");
+    ELD_CHECK_CUDA(cudaSetDevice(u->ctx->device));
+    for (int k = 0; k < kGradBuckets; ++k) {
+        if (enable && !u->bucket_ev[k]) ELD_CHECK_CUDA(cudaEventCreateWithFlags(&u->bucket_ev[k], cudaEventDisableTiming));
+        if (!enable && u->bucket_ev[k]) { cudaEventDestroy(u->bucket_ev[k]); u->bucket_ev[k] = nullptr; }
+    }
+    return ELD_OK;
+}
+
+extern "C" int eld_unet_wait_bucket(eld_unet* u, int bucket, void* stream)
+{
+    ELD_REQUIRE(u && bucket >= 0 && bucket < kGradBuckets, "eld_unet_wait_bucket: bad bucket %d", bucket);
+    ELD_REQUIRE(u->bucket_ev[bucket], "eld_unet_wait_bucket: call eld_unet_bucket_events(u, 1) before the step");
+    ELD_CHECK_CUDA(cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), u->bucket_ev[bucket], 0));
+    return ELD_OK;
+}
 
 #define TRY(expr) do { int _rc = (expr); if (_rc != ELD_OK) return _rc; } while (0)
 
@@ -458,6 +512,22 @@ struct Runner {
         return launch_maxpool_bwd(ctx(), A, dskip, pitch, c0, dP, dZ, C, u->n, u->H >> lvl_out, u->W >> lvl_out, st);
     }
 
+    // gradients of bucket k are complete in the staging area: move its conv tiles to the PyTorch layout and mark the
+    // bucket final (a data-parallel caller all-reduces it on a side stream while the rest of backward runs)
+    int finish_bucket(int k, float* g) const
+    {
+        const int t0 = u->table.tile0[kBucketEntry0[k]], t1 = u->table.tile0[kBucketEntry1[k]];
+        const int extra = k == kGradBuckets - 1 ? 2 : 0;         // conv1_1 rides with the last bucket
+        {
+            Scope sc(u, st, "weights", "gperm", 0.0, 0.0);
+            wgrad_permute_kernel<<<t1 - t0 + extra, 256, 0, st>>>(u->gtmp, g, u->table, t0, t1);
+            ELD_CHECK_CUDA(cudaGetLastError());
+            count_launch(ctx());
+        }
+        if (u->bucket_ev[k]) ELD_CHECK_CUDA(cudaEventRecord(u->bucket_ev[k], st));
+        return ELD_OK;
+    }
+
     int pack() const
     {
         Scope sc(u, st, "weights", "pack", 0.0, (double)u->n_params * 8);
@@ -534,11 +604,13 @@ struct Runner {
         TRY(conv_wgrad(I_C61, U->cat6, 512, 0, U->dz6_1, g, 3));
         TRY(conv_dgrad(I_C61, U->dz6_1, U->dcat6, 512, 0, nullptr, 0, 0, 3));
         TRY(deconv_wgrad(I_UP6, U->a5_2, U->dcat6, 512, g, 4));
+        TRY(finish_bucket(0, g));
         TRY(deconv_dgrad(I_UP6, U->dcat6, 512, U->dz5_2, U->a5_2, 4));
         // bottleneck + encoder
         TRY(conv_wgrad(I_C52, U->a5_1, 512, 0, U->dz5_2, g, 4));
         TRY(conv_dgrad(I_C52, U->dz5_2, U->dz5_1, 512, 0, U->a5_1, 512, 0, 4));
         TRY(conv_wgrad(I_C51, U->p4, 256, 0, U->dz5_1, g, 4));
+        TRY(finish_bucket(1, g));
         TRY(conv_dgrad(I_C51, U->dz5_1, U->dp4, 256, 0, nullptr, 0, 0, 4));
         TRY(pool_bwd(U->cat6, U->dcat6, 512, 256, U->dp4, U->dz4_2, 256, 4));
         TRY(conv_wgrad(I_C42, U->a4_1, 256, 0, U->dz4_2, g, 3));
@@ -569,13 +641,7 @@ struct Runner {
             op.db = g + U->L[I_C11].b_off;
             TRY(launch_wgrad(ctx(), op, st));
         }
-        {
-            Scope sc(u, st, "weights", "gperm", 0.0, (double)U->n_params * 8);
-            wgrad_permute_kernel<<<U->table.tile0[U->table.n] + 2, 256, 0, st>>>(U->gtmp, g, U->table);
-            ELD_CHECK_CUDA(cudaGetLastError());
-            count_launch(ctx());
-        }
-        return ELD_OK;
+        return finish_bucket(2, g);
     }
 };
 

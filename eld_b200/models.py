@@ -55,6 +55,15 @@ class BaseModel:
         print(self.optimizers[-1])
 
     def save(self, label=None):
+        # one writer per job: under torch.distributed every replica holds the same state (rank 0 writes, all wait)
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            if dist.get_rank() == 0:
+                self._save(label)
+            dist.barrier()
+            return
+        self._save(label)
+
+    def _save(self, label=None):
         epoch, iterations = self.epoch, self.iterations
         if label is None:
             model_name = os.path.join(self.save_dir, 'model' + '_%03d_%08d.pt' % (epoch, iterations))
@@ -79,7 +88,7 @@ class ELDModel(BaseModel):
         self.device = torch.device('cuda', torch.cuda.current_device()) if torch.cuda.is_available() else None
         self.noise_maker = None
         self.loss_pixel = None
-        self._frame_counter = 0
+        self._frames_seen = 0
 
     def _eval(self):
         self.netG.eval()
@@ -106,6 +115,16 @@ class ELDModel(BaseModel):
             self.load(self, opt.resume_epoch)
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.rank = dist.get_rank() if self.world > 1 else 0
+        self._sync_replicas()
+
+    def _sync_replicas(self):
+        """Data-parallel replicas start from rank 0's weights and Adam moments whatever each rank's torch seed was
+        (the reference is single-GPU; train_syn.py seeds every process alike, an Engine caller may not)."""
+        if self.world > 1:
+            dist.broadcast(self.netG.flat_params, 0)
+            if self.isTrain:
+                dist.broadcast(self.optimizer_G.m, 0)
+                dist.broadcast(self.optimizer_G.v, 0)
 
     # ---- ELDModelBase.set_input (ELD_model.py:173-200) -------------------------------------------------
     def set_input(self, data, mode='train'):
@@ -126,15 +145,24 @@ class ELDModel(BaseModel):
             # on-the-fly synthesis on the training stream (SynDataset semantics, sid_dataset.py:259-280,
             # incl. the [0,1] clip): global frame ids keep the stream invariant to the number of GPUs.
             assert self.noise_maker is not None, 'noise_on_gpu needs a noise_maker (eld_b200.noise.NoiseModel)'
+            # Frame ids count GLOBAL frames: step s of a W-GPU job owns ids [F, F + sum of the ranks' batch sizes), rank r
+            # the r-th slice.  Batches are equal-sized except possibly the last one of an epoch (DataLoader without
+            # drop_last), so F advances by the batch actually seen times W - ids never repeat, and the running count
+            # is part of the checkpoint (a resumed run does not replay the Philox streams from frame 0).
             n = target.shape[0]
-            fid0 = (self._frame_counter * self.world + self.rank) * n
-            self._frame_counter += 1
+            fid0 = self._frames_seen + self.rank * n
+            self._frames_seen += self.world * n
+            # per-frame (K, g_scale, ratio, ...) and flip flags are drawn from a generator keyed by (seed, global frame
+            # id): W ranks draw W*n DIFFERENT tuples (not W copies of the same n), and frame f gets the same tuple at
+            # any GPU count.  The draw itself is noise.py:201-225's call order on that per-frame RandomState.
+            params = self.noise_maker.frame_params(fid0, n)
             if getattr(self.opt, 'augment_on_gpu', False):
                 # ELDTrainDataset's flips / transpose / clip (sid_dataset.py:340-356) fused into the noise kernel:
                 # both the synthesised input and the target come back augmented, one pass over the frames
-                input, target = self.noise_maker.batch_gpu_augmented(target, frame_id0=fid0, clip=True)
+                input, target = self.noise_maker.batch_gpu_augmented(target, aug=self.noise_maker.frame_augment(fid0, n),
+                                                                     params=params, frame_id0=fid0, clip=True)
             else:
-                input = self.noise_maker.batch_gpu(target, frame_id0=fid0, clip=True)
+                input = self.noise_maker.batch_gpu(target, params=params, frame_id0=fid0, clip=True)
         else:
             input = input.to(device=self.device, dtype=torch.float32, non_blocking=True)
         self.input, self.target, self.data_name = input, target, data_name
@@ -183,9 +211,10 @@ class ELDModel(BaseModel):
     def optimize_parameters(self):
         """forward, zero_grad, L1 backward, (all-reduce), Adam - ELD_model.py:469-475."""
         self._train()
-        self.output, self.loss_pixel = self.netG.train_step(self.input, self.target)
         if self.world > 1:
-            dist.all_reduce(self.netG.flat_grads)
+            self.output, self.loss_pixel = self.netG.train_step_ddp(self.input, self.target)
+        else:
+            self.output, self.loss_pixel = self.netG.train_step(self.input, self.target)
         self.optimizer_G.step(grad_scale=1.0 / self.world)
 
     def backward_G(self):
@@ -252,12 +281,14 @@ class ELDModel(BaseModel):
         model.netG.load_state_dict(state_dict['netG'])
         if model.isTrain and 'opt_g' in state_dict:
             model.optimizer_G.load_state_dict(state_dict['opt_g'])
+        model._frames_seen = int(state_dict.get('frames_seen', 0))
         print('Resume from epoch %d, iteration %d' % (model.epoch, model.iterations))
         return state_dict
 
     def state_dict(self):
         return {'netG': {k: v.detach().cpu().clone() for k, v in self.netG.state_dict().items()},
-                'opt_g': self.optimizer_G.state_dict(), 'epoch': self.epoch, 'iterations': self.iterations}
+                'opt_g': self.optimizer_G.state_dict(), 'epoch': self.epoch, 'iterations': self.iterations,
+                'frames_seen': self._frames_seen}
 
 
 def eld_model():

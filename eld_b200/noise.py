@@ -62,6 +62,18 @@ def params_array(params_list):
     return arr
 
 
+def _with_rng(rng, fn):
+    """Run `fn` (written against numpy's global legacy RNG, like the reference) on the RandomState `rng`: the global
+    state is swapped in and restored, so the call order - the contract - lives in one place."""
+    saved = np.random.get_state()
+    np.random.set_state(rng.get_state())
+    try:
+        return fn()
+    finally:
+        rng.set_state(np.random.get_state())
+        np.random.set_state(saved)
+
+
 def _cur_stream(torch):
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -82,10 +94,31 @@ class NoiseModelBase:
         assert len(params) == n
         return list(params)
 
-    def _sample_params_any(self):
-        if any(ch in self.model for ch in 'GBRU'):
-            return self._sample_params_full()
-        return self._sample_params()
+    # ---- per-frame draws keyed by (seed, global frame id): invariant to how frames are sharded over GPUs ----------
+    def _frame_rng(self, fid):
+        return np.random.RandomState(np.random.SeedSequence([int(self.seed) & 0xFFFFFFFF, int(self.seed) >> 32,
+                                                             int(fid) & 0xFFFFFFFF, int(fid) >> 32]).generate_state(4))
+
+    def frame_params(self, fid0, n):
+        """_sample_params (noise.py:201-225, same call order and distributions) for global frames fid0 .. fid0+n-1, each
+        from its own RandomState seeded by (self.seed, frame id) - not from numpy's global stream, which every rank of
+        a data-parallel job would replay identically."""
+        return [self._sample_params_any(rng=self._frame_rng(fid0 + i)) for i in range(n)]
+
+    def frame_augment(self, fid0, n):
+        """ELDTrainDataset's three coin flips (sid_dataset.py:344-350) per global frame id, same order."""
+        flags = np.zeros(n, dtype=np.uint8)
+        for i in range(n):
+            rng = self._frame_rng((fid0 + i) ^ (1 << 62))
+            for bit in (1, 2, 4):
+                if rng.randint(2, size=1)[0] == 1:
+                    flags[i] |= bit
+        return flags
+
+    def _sample_params_any(self, rng=None):
+        if _lib.is_full_model(self.model):
+            return self._sample_params_full(rng)
+        return self._sample_params(rng)
 
     def batch_gpu(self, clean, params=None, frame_id0=None, clip=True, out=None, seed=None):
         """clean: cuda float32 [N,4,h,w] in [0,1] -> noisy, same shape (reference layout)."""
@@ -235,8 +268,11 @@ class NoiseModel(NoiseModelBase):
         self.seed = seed
         self.cfa = cfa
 
-    def _sample_params(self):
-        """Identical numpy-global-RNG call order to noise.py:201-225 (pinned by tests/golden)."""
+    def _sample_params(self, rng=None):
+        """Identical numpy-global-RNG call order to noise.py:201-225 (pinned by tests/golden); `rng` = a RandomState to
+        draw from instead of numpy's global one (frame_params)."""
+        if rng is not None:
+            return _with_rng(rng, self._sample_params)
         camera = np.random.choice(self.cameras)
         saturation_level = 16383 - 800
         profiles = ['Profile-1']
@@ -251,9 +287,11 @@ class NoiseModel(NoiseModelBase):
         ratio = np.random.uniform(low=100, high=300)
         return (K, g_scale, saturation_level, ratio)
 
-    def _sample_params_full(self):
+    def _sample_params_full(self, rng=None):
         """Per-frame scalars of the full (paper-restated) model: the calibrated fields the released
         code never reads.  NOT IN THE REFERENCE - parity unpinned."""
+        if rng is not None:
+            return _with_rng(rng, self._sample_params_full)
         camera = np.random.choice(self.cameras)
         cp = self.camera_params[camera]
         prof = cp['Profile-1']

@@ -72,6 +72,15 @@ int    eld_unet_forward(eld_unet* u, const float* params, const float* x, float*
  * and filled; *loss (device float) receives the mean absolute error.  No optimizer step, no host sync. */
 int    eld_unet_train_step(eld_unet* u, const float* params, const float* x, const float* target,
                            float* out, float* grads, float* loss, void* stream);
+/* Data-parallel overlap (the reference is single-GPU, ELD_model.py:187-190): the flat gradient is final in
+ * eld_unet_grad_buckets() = 3 contiguous ranges in backward-completion order (decoder upv6..conv10_1, bottleneck
+ * conv5_*, encoder conv1_1..conv4_2); offsets[2k], offsets[2k+1] = first element, element count of bucket k.
+ * After eld_unet_bucket_events(u, 1) every eld_unet_train_step records an event on its stream when bucket k is final;
+ * eld_unet_wait_bucket makes `stream` (the caller's communication stream) wait for it - the caller then all-reduces
+ * grads[offset, offset+count) there while the rest of backward runs, and runs Adam after the last bucket. */
+int    eld_unet_grad_buckets(size_t* offsets, int max_offsets);      /* returns the bucket count (3) */
+int    eld_unet_bucket_events(eld_unet* u, int enable);
+int    eld_unet_wait_bucket(eld_unet* u, int bucket, void* stream);
 /* torch.optim.Adam step (ELD_model.py:400-401,475) on the flat buffers; grads are multiplied by
  * grad_scale first (1/world_size after a SUM all-reduce).  step counts from 1. */
 /* Per-launch timing (CUDA events on the launch stream) of the steps issued after eld_unet_profile(u, 1);

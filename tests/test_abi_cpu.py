@@ -61,7 +61,10 @@ def test_model_mask_substring_semantics():
     assert model_mask('P+g') == 0x05 and model_mask('Pg') == 0x05 and model_mask('g+P') == 0x05
     assert model_mask('p+g') == 0x06 and model_mask('g') == 0x04 and model_mask('P') == 0x01
     assert model_mask('Pp') == 0x01
-    assert model_mask('P+G+B+R+U') == 0x79
+    assert model_mask('ELD:P+G+B+R+U') == 0x79
+    # reference strings keep their reference meaning (README.md:46 names the baselines G / G+P / G+P*): without the
+    # explicit 'ELD:' prefix the letters G, B, R, U select nothing, exactly like noise.py:158-166
+    assert model_mask('G+P') == 0x01 and model_mask('G') == 0x00 and model_mask('G+P*') == 0x01
 
 
 def test_noise_model_host_side_matches_reference_golden(golden_dir):
@@ -91,7 +94,7 @@ def test_noise_model_ctor_contract():
     nm = NoiseModel('g', exclude=0, verbose=False)
     assert 'CanonEOS5D4' not in nm.cameras and len(nm.cameras) == 4
     nm.model = 'P+g'                                              # .model is a mutable str attribute
-    full = NoiseModel('P+G+B+R+U', include=4, verbose=False)
+    full = NoiseModel('ELD:P+G+B+R+U', include=4, verbose=False)
     np.random.seed(3)
     p = full._sample_params_full()
     assert set(p) >= {'K', 'g_scale', 'G_scale', 'G_lambda', 'R_scale', 'color_bias', 'ratio', 'q_step'}
@@ -122,3 +125,52 @@ def test_read_emor_and_load_crf(tmp_path):
     assert e.shape == (1024,) and np.allclose(e, E, atol=1e-6) and np.allclose(f0, E ** 0.5, atol=1e-6) and H.shape == (1, 1024)
     Erep, fs = process.load_CRF(str(tmp_path))
     assert Erep.shape == (3, 1024) and fs.shape == (3, 1024) and np.allclose(Erep[2], E, atol=1e-6)
+
+
+def test_frame_params_are_keyed_by_global_frame_id():
+    """per-frame (K, g_scale, ratio) and flip flags used by ELDModel.set_input come from a generator keyed by
+    (seed, global frame id) - W ranks draw W*B different tuples, frame f gets the same tuple at any world size, numpy's
+    global stream is left untouched, and each draw follows noise.py:201-225's distributions."""
+    from eld_b200.noise import NoiseModel
+    nm = NoiseModel('P+g', include=4, verbose=False, seed=2018)
+    np.random.seed(5)
+    before = np.random.get_state()[1].copy()
+    B = 4
+    one = nm.frame_params(0, 2 * B)                                   # world 1: frames 0..7 in one batch
+    two = [nm.frame_params(r * B, B) for r in range(2)]               # world 2: rank r owns [r*B, (r+1)*B)
+    assert np.array_equal(np.random.get_state()[1], before)          # global RNG not consumed
+    assert one == two[0] + two[1]
+    assert len({p[0] for p in one}) == 2 * B                          # 8 distinct K, not 2 copies of 4
+    assert all(0.1 <= p[0] <= 30 and 100 <= p[3] <= 300 and p[2] == 15583 for p in one)
+    assert nm.frame_params(3, 1)[0] == one[3]                         # any sharding
+    a1, a2 = nm.frame_augment(0, 8), np.concatenate([nm.frame_augment(0, 4), nm.frame_augment(4, 4)])
+    assert np.array_equal(a1, a2) and a1.max() <= 7
+    # same call order as the reference on the per-frame RandomState: reproduce frame 3 by hand
+    rng = nm._frame_rng(3)
+    np.random.set_state(rng.get_state())
+    want = nm._sample_params()
+    assert want == one[3]
+    full = NoiseModel('ELD:P+G+B+R+U', include=4, verbose=False, seed=1)
+    f = full.frame_params(10, 2)
+    assert f[0] != f[1] and set(f[0]) >= {'K', 'G_scale', 'R_scale', 'G_lambda', 'color_bias'}
+    assert NoiseModel('G+P', include=4, verbose=False).frame_params(0, 1)[0][2] == 15583   # reference string: 4-tuple
+
+
+def test_grad_buckets_partition_the_flat_gradient():
+    """the data-parallel buckets are contiguous ranges of the state_dict-ordered flat gradient, listed in
+    backward-completion order (decoder first, encoder last), and together cover every parameter exactly once."""
+    import ctypes as c
+    from eld_b200 import _lib
+    lib = _lib.load()
+    arr = (c.c_size_t * 6)()
+    k = lib.eld_unet_grad_buckets(arr, 6)
+    b = [(int(arr[2 * i]), int(arr[2 * i + 1])) for i in range(k)]
+    n = lib.eld_unet_param_count()
+    assert k == 3 and sum(cnt for _, cnt in b) == n == 7760484
+    spans = sorted(b)
+    assert spans[0][0] == 0 and all(spans[i][0] + spans[i][1] == spans[i + 1][0] for i in range(2)) and spans[2][0] + spans[2][1] == n
+    off, cnt = c.c_size_t(), c.c_size_t()
+    lib.eld_unet_param_offset(b'upv6', 0, c.byref(off), c.byref(cnt))
+    assert b[0][0] == off.value                        # decoder bucket starts at upv6.weight ...
+    lib.eld_unet_param_offset(b'conv5_1', 0, c.byref(off), c.byref(cnt))
+    assert b[1][0] == off.value and b[2][0] == 0       # ... bottleneck at conv5_1.weight, encoder at conv1_1.weight

@@ -112,3 +112,40 @@ def test_eval_matches_reference_formulas(torch, tmp_path):
     gain = (p[mask] * tt[mask]).sum() / (p[mask] * p[mask]).sum()
     want = ref_numpy.psnr255(gain * p, tt)
     assert abs(r['PSNR'] - want) < 1e-3, (r['PSNR'], want)
+
+
+def test_set_input_noise_stream_is_invariant_to_the_gpu_count(torch, tmp_path):
+    """drive set_input with params=None (the model draws (K, g_scale, ratio) itself) as ONE rank with batch 4
+    and as ranks 0/1 of a 2-rank job with batch 2 each: the union of the noisy inputs is bit-identical, frame for
+    frame - pixels AND per-frame parameters - and the running frame count survives a checkpoint."""
+    from eld_b200 import models
+    from eld_b200.noise import NoiseModel
+
+    def make(world, rank):
+        m = models.eld_model()
+        m.initialize(models.default_opt(name='w', checkpoints_dir=str(tmp_path), noise='P+g', noise_on_gpu=True),
+                     noise_maker=NoiseModel('P+g', include=4, verbose=False, seed=31))
+        m.world, m.rank = world, rank
+        return m
+    g = torch.Generator().manual_seed(1)
+    frames = torch.rand(8, 4, 128, 256, generator=g)          # 2 steps x global batch 4
+    one = make(1, 0)
+    got1 = []
+    for s in range(2):
+        one.set_input({'target': frames[4 * s:4 * s + 4]}, 'train')
+        got1.append(one.input.cpu())
+    got2 = [[None, None], [None, None]]
+    for r in range(2):
+        m = make(2, r)
+        for s in range(2):
+            m.set_input({'target': frames[4 * s + 2 * r:4 * s + 2 * r + 2]}, 'train')
+            got2[s][r] = m.input.cpu()
+    for s in range(2):
+        assert torch.equal(got1[s], torch.cat(got2[s]))
+    # frames of one batch differ in their noise LEVEL (different K per frame), not only in their Philox stream
+    flat = torch.full((4, 4, 128, 256), 0.3)
+    lv = make(1, 0)
+    lv.set_input({'target': flat}, 'train')
+    sd = (lv.input.cpu() - flat).flatten(1).std(1)
+    assert sd.max() / sd.min() > 1.05, sd
+    assert one._frames_seen == 8 and one.state_dict()['frames_seen'] == 8

@@ -68,7 +68,7 @@ def _compare(gpu, ref, y, p, mask):
 
 
 MODELS = [('g', 0x04), ('p+g', 0x06), ('P+g', 0x05), ('P', 0x01), ('p', 0x02),
-          ('P+G+R+U', 0x69), ('P+G+B+R+U', 0x79), ('g+R', 0x24), ('G', 0x08), ('U', 0x40)]
+          ('ELD:P+G+R+U', 0x69), ('ELD:P+G+B+R+U', 0x79), ('ELD:g+R', 0x24), ('ELD:G', 0x08), ('ELD:U', 0x40)]
 
 
 @pytest.mark.parametrize('model,mask', MODELS)
@@ -194,7 +194,7 @@ def test_mosaic_golden_pack(torch, golden_dir):
     assert np.array_equal(clean.cpu().numpy()[0], np.asarray(g['packed'], np.float32))
 
 
-@pytest.mark.parametrize('model,mask', [('P+g', 5), ('p+g', 6), ('P+G+B+R+U', 0x79)])
+@pytest.mark.parametrize('model,mask', [('P+g', 5), ('p+g', 6), ('ELD:P+G+B+R+U', 0x79)])
 def test_mosaic_noise_parity(torch, oracle, model, mask):
     """uint16 LMDB-style mosaic -> dequantise (x/65535, lmdb_dataset.py:38) -> pack -> noise, vs oracle;
     and mosaic path == packed path on the packed clean frame (same random stream)."""
@@ -317,7 +317,7 @@ def test_config3_full_eld_batch32_structure(torch):
     sharding (global frame ids), row noise is ONE draw per sensor row (planes 0,1 share row 2i; planes 3,2 share row
     2i+1, noise.py:16-19) with the calibrated sigma, quantisation noise stays within half a step."""
     from eld_b200.noise import NoiseModel
-    nm = NoiseModel('P+G+B+R+U', include=4, verbose=False, seed=99)
+    nm = NoiseModel('ELD:P+G+B+R+U', include=4, verbose=False, seed=99)
     y = torch.rand(32, 4, 512, 512, device='cuda')
     whole = nm.batch_gpu(y, params=FULL, frame_id0=640, clip=True)
     for rank in range(8):
@@ -326,13 +326,13 @@ def test_config3_full_eld_batch32_structure(torch):
     assert torch.isfinite(whole).all() and whole.min() >= 0 and whole.max() <= 1
     sat, ratio = FULL['saturation'], FULL['ratio']
     flat = torch.full((2, 4, 512, 512), 0.5, device='cuda')
-    r = (NoiseModel('R', include=4, verbose=False, seed=5).batch_gpu(flat, params=FULL, frame_id0=0, clip=False) - flat) * sat / ratio
+    r = (NoiseModel('ELD:R', include=4, verbose=False, seed=5).batch_gpu(flat, params=FULL, frame_id0=0, clip=False) - flat) * sat / ratio
     assert (r - r[..., :1]).abs().max() < 1e-3                       # constant along a packed row
     assert torch.allclose(r[:, 0], r[:, 1], atol=1e-3) and torch.allclose(r[:, 3], r[:, 2], atol=1e-3)
     assert not torch.allclose(r[:, 0], r[:, 2], atol=1e-3)           # even and odd sensor rows are independent draws
     rows = torch.cat([r[:, 0, :, 0], r[:, 2, :, 0]]).double()       # 2 frames x 512 x 2 independent normals
     assert abs(rows.std().item() / FULL['R_scale'] - 1) < 0.06 and abs(rows.mean().item()) < 0.1
-    u = (NoiseModel('U', include=4, verbose=False, seed=5).batch_gpu(flat, params=FULL, frame_id0=0, clip=False) - flat) * sat / ratio
+    u = (NoiseModel('ELD:U', include=4, verbose=False, seed=5).batch_gpu(flat, params=FULL, frame_id0=0, clip=False) - flat) * sat / ratio
     assert u.abs().max() <= 0.5 * FULL['q_step'] + 1e-3
     assert abs(u.double().var().item() / (FULL['q_step'] ** 2 / 12) - 1) < 0.01
 
