@@ -355,10 +355,18 @@ def main():
     for i in range(a.steps):
         step(a.warmup + i)
     ev[1].record()
+    import ctypes
+    probe = torch.zeros(1, device=dev)
+    _lib.check(_lib.load().eld_clock_probe(_lib.ctx(local), probe.data_ptr(),
+                                           ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), 'eld_clock_probe')
     barrier()
     if sampler is not None:
         sampler.window(False)
     clocks = sampler.stop() if sampler is not None else None
+    if clocks is not None:
+        # the SM clock right behind the last timed kernel, from %clock64 / %globaltimer on the device (nvidia-smi's
+        # 25 ms samples cannot resolve an 80 ms window)
+        clocks['sm_mhz_device_probe'] = float(probe.item())
     ms = ev[0].elapsed_time(ev[1])
     launches = _lib.launch_count(local) - l0
     t = torch.tensor([ms], device=dev)

@@ -31,5 +31,6 @@ def declare_engine(lib):
     lib.eld_unet_grad_buckets.argtypes = [c.POINTER(sz), i32]
     lib.eld_unet_bucket_events.argtypes = [vp, i32]
     lib.eld_unet_wait_bucket.argtypes = [vp, i32, vp]
+    lib.eld_clock_probe.argtypes = [vp, vp, vp]
     lib.eld_unet_profile.argtypes = [vp, i32]
     lib.eld_unet_profile_read.argtypes = [vp, i32, c.c_char_p, vp, vp, vp, c.POINTER(i32)]

@@ -53,6 +53,8 @@ struct ConvGemmParams {
     int cout_shift;       // EPI_SHUFFLE: log2(cout) (cout must be a power of two)
     __nv_bfloat16* pool_out;   // optional fused MaxPool2d(2) of the (activated) output: bf16 NHWC [n][H/2][W/2][pool_pitch]
     int pool_pitch;
+    __nv_bfloat16* out2;  // EPI_STORE split store: GEMM columns >= out_split go to out2[pix * out2_pitch + (col - out_split)]
+    int out2_pitch, out_split;   // (planar halves of a concat gradient); out_split % 32 == 0, 0 = off
     long long* prof;      // PROF instantiation only
     int bias_smem_off;    // byte offset (from the 1024-aligned base) of the per-CTA bias copy
 };
@@ -502,7 +504,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const ConvGemmParams p
                 __nv_bfloat16* dst;
                 int bcol;
                 if (p.epi_mode == EPI_STORE) {
-                    dst = p.out + (size_t)pix * p.out_pitch + (p.out_c0 + col);
+                    dst = (p.out_split && col >= p.out_split) ? p.out2 + (size_t)pix * p.out2_pitch + (col - p.out_split)
+                                                              : p.out + (size_t)pix * p.out_pitch + (p.out_c0 + col);
                     bcol = col;
                 } else {
                     const int sub = col >> p.cout_shift, co = col & (p.cout - 1);   // sub = kh*2 + kw

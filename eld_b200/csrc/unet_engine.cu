@@ -444,7 +444,11 @@ struct Runner {
         return launch_conv_gemm(ctx(), op, st);
     }
     // data gradient of a conv: dz [cout] -> d(input) [cin channels at dxc0], optional lrelu' mask from `act_src`
-    int conv_dgrad(int li, const void* dz, void* dx, int dxp, int dxc0, const void* act_src, int asp, int asc0, int lvl) const
+    // dx2 != nullptr: the gradient of a concat input is stored as two PLANAR halves (dx = [up], dx2 = [skip], pitch cin/2
+    // each) - every consumer reads exactly one half, and an interleaved buffer made each of them move whole 128-byte
+    // lines for 64 useful bytes (ncu r01: level-1 pool.bwd 570 MB for 300, upv9 dgrad/wgrad 336 MB for 200)
+    int conv_dgrad(int li, const void* dz, void* dx, int dxp, int dxc0, const void* act_src, int asp, int asc0, int lvl,
+                   void* dx2 = nullptr) const
     {
         const Layer& l = u->L[li];
         GemmOp op{};
@@ -453,6 +457,7 @@ struct Runner {
         op.b = wd(li); op.n_total = l.cin; op.cout = l.cin;
         op.epi_mode = EPI_STORE; op.act = act_src ? ACT_MASK : ACT_NONE;
         op.out = dx; op.out_pitch = dxp; op.out_c0 = dxc0; op.bias = nullptr;
+        if (dx2) { op.out2 = dx2; op.out2_pitch = dxp; op.out_split = l.cin / 2; }
         op.aux = act_src; op.aux_pitch = asp; op.aux_c0 = asc0;
         const double px = (double)u->n * op.H * op.W;
         Scope sc(u, st, l.name, "dgrad", 2.0 * px * l.cout * 9 * l.cin, px * 2 * (l.cin * (act_src ? 2 : 1) + l.cout) + 18.0 * l.cin * l.cout);
@@ -505,11 +510,17 @@ struct Runner {
         Scope sc(u, st, "pool", "fwd", 0.0, pxo * C * 2 * 5);
         return launch_maxpool(ctx(), in, pitch, c0, out, C, u->n, u->H >> lvl_out, u->W >> lvl_out, st);
     }
-    int pool_bwd(const void* A, const void* dskip, int pitch, int c0, const void* dP, void* dZ, int C, int lvl_out) const
+    // A = the interleaved concat buffer's skip half (pitch 2C, offset C); dskip = the PLANAR skip half of its gradient
+    int pool_bwd(const void* A, int pitch, int c0, const void* dskip, const void* dP, void* dZ, int C, int lvl_out) const
     {
         const double pxo = (double)u->n * (u->H >> lvl_out) * (u->W >> lvl_out);
         Scope sc(u, st, "pool", "bwd", 0.0, pxo * C * 2 * 13);
-        return launch_maxpool_bwd(ctx(), A, dskip, pitch, c0, dP, dZ, C, u->n, u->H >> lvl_out, u->W >> lvl_out, st);
+        return launch_maxpool_bwd(ctx(), A, pitch, c0, dskip, C, 0, dP, dZ, C, u->n, u->H >> lvl_out, u->W >> lvl_out, st);
+    }
+    // second (skip) half of a planar concat gradient: [n][h][w][C] right behind the up half
+    __nv_bfloat16* skip_half(__nv_bfloat16* dcat, int lvl, int C) const
+    {
+        return dcat + (size_t)u->n * (u->H >> lvl) * (u->W >> lvl) * C;
     }
 
     // gradients of bucket k are complete in the staging area: move its conv tiles to the PyTorch layout and mark the
@@ -584,50 +595,50 @@ struct Runner {
         TRY(conv_wgrad(I_C92, U->a9_1, 32, 0, U->dz9_2, g, 0));
         TRY(conv_dgrad(I_C92, U->dz9_2, U->dz9_1, 32, 0, U->a9_1, 32, 0, 0));
         TRY(conv_wgrad(I_C91, U->cat9, 64, 0, U->dz9_1, g, 0));
-        TRY(conv_dgrad(I_C91, U->dz9_1, U->dcat9, 64, 0, nullptr, 0, 0, 0));
-        TRY(deconv_wgrad(I_UP9, U->a8_2, U->dcat9, 64, g, 1));
-        TRY(deconv_dgrad(I_UP9, U->dcat9, 64, U->dz8_2, U->a8_2, 1));
+        TRY(conv_dgrad(I_C91, U->dz9_1, U->dcat9, 32, 0, nullptr, 0, 0, 0, skip_half(U->dcat9, 0, 32)));
+        TRY(deconv_wgrad(I_UP9, U->a8_2, U->dcat9, 32, g, 1));
+        TRY(deconv_dgrad(I_UP9, U->dcat9, 32, U->dz8_2, U->a8_2, 1));
         TRY(conv_wgrad(I_C82, U->a8_1, 64, 0, U->dz8_2, g, 1));
         TRY(conv_dgrad(I_C82, U->dz8_2, U->dz8_1, 64, 0, U->a8_1, 64, 0, 1));
         TRY(conv_wgrad(I_C81, U->cat8, 128, 0, U->dz8_1, g, 1));
-        TRY(conv_dgrad(I_C81, U->dz8_1, U->dcat8, 128, 0, nullptr, 0, 0, 1));
-        TRY(deconv_wgrad(I_UP8, U->a7_2, U->dcat8, 128, g, 2));
-        TRY(deconv_dgrad(I_UP8, U->dcat8, 128, U->dz7_2, U->a7_2, 2));
+        TRY(conv_dgrad(I_C81, U->dz8_1, U->dcat8, 64, 0, nullptr, 0, 0, 1, skip_half(U->dcat8, 1, 64)));
+        TRY(deconv_wgrad(I_UP8, U->a7_2, U->dcat8, 64, g, 2));
+        TRY(deconv_dgrad(I_UP8, U->dcat8, 64, U->dz7_2, U->a7_2, 2));
         TRY(conv_wgrad(I_C72, U->a7_1, 128, 0, U->dz7_2, g, 2));
         TRY(conv_dgrad(I_C72, U->dz7_2, U->dz7_1, 128, 0, U->a7_1, 128, 0, 2));
         TRY(conv_wgrad(I_C71, U->cat7, 256, 0, U->dz7_1, g, 2));
-        TRY(conv_dgrad(I_C71, U->dz7_1, U->dcat7, 256, 0, nullptr, 0, 0, 2));
-        TRY(deconv_wgrad(I_UP7, U->a6_2, U->dcat7, 256, g, 3));
-        TRY(deconv_dgrad(I_UP7, U->dcat7, 256, U->dz6_2, U->a6_2, 3));
+        TRY(conv_dgrad(I_C71, U->dz7_1, U->dcat7, 128, 0, nullptr, 0, 0, 2, skip_half(U->dcat7, 2, 128)));
+        TRY(deconv_wgrad(I_UP7, U->a6_2, U->dcat7, 128, g, 3));
+        TRY(deconv_dgrad(I_UP7, U->dcat7, 128, U->dz6_2, U->a6_2, 3));
         TRY(conv_wgrad(I_C62, U->a6_1, 256, 0, U->dz6_2, g, 3));
         TRY(conv_dgrad(I_C62, U->dz6_2, U->dz6_1, 256, 0, U->a6_1, 256, 0, 3));
         TRY(conv_wgrad(I_C61, U->cat6, 512, 0, U->dz6_1, g, 3));
-        TRY(conv_dgrad(I_C61, U->dz6_1, U->dcat6, 512, 0, nullptr, 0, 0, 3));
-        TRY(deconv_wgrad(I_UP6, U->a5_2, U->dcat6, 512, g, 4));
+        TRY(conv_dgrad(I_C61, U->dz6_1, U->dcat6, 256, 0, nullptr, 0, 0, 3, skip_half(U->dcat6, 3, 256)));
+        TRY(deconv_wgrad(I_UP6, U->a5_2, U->dcat6, 256, g, 4));
         TRY(finish_bucket(0, g));
-        TRY(deconv_dgrad(I_UP6, U->dcat6, 512, U->dz5_2, U->a5_2, 4));
+        TRY(deconv_dgrad(I_UP6, U->dcat6, 256, U->dz5_2, U->a5_2, 4));
         // bottleneck + encoder
         TRY(conv_wgrad(I_C52, U->a5_1, 512, 0, U->dz5_2, g, 4));
         TRY(conv_dgrad(I_C52, U->dz5_2, U->dz5_1, 512, 0, U->a5_1, 512, 0, 4));
         TRY(conv_wgrad(I_C51, U->p4, 256, 0, U->dz5_1, g, 4));
         TRY(finish_bucket(1, g));
         TRY(conv_dgrad(I_C51, U->dz5_1, U->dp4, 256, 0, nullptr, 0, 0, 4));
-        TRY(pool_bwd(U->cat6, U->dcat6, 512, 256, U->dp4, U->dz4_2, 256, 4));
+        TRY(pool_bwd(U->cat6, 512, 256, skip_half(U->dcat6, 3, 256), U->dp4, U->dz4_2, 256, 4));
         TRY(conv_wgrad(I_C42, U->a4_1, 256, 0, U->dz4_2, g, 3));
         TRY(conv_dgrad(I_C42, U->dz4_2, U->dz4_1, 256, 0, U->a4_1, 256, 0, 3));
         TRY(conv_wgrad(I_C41, U->p3, 128, 0, U->dz4_1, g, 3));
         TRY(conv_dgrad(I_C41, U->dz4_1, U->dp3, 128, 0, nullptr, 0, 0, 3));
-        TRY(pool_bwd(U->cat7, U->dcat7, 256, 128, U->dp3, U->dz3_2, 128, 3));
+        TRY(pool_bwd(U->cat7, 256, 128, skip_half(U->dcat7, 2, 128), U->dp3, U->dz3_2, 128, 3));
         TRY(conv_wgrad(I_C32, U->a3_1, 128, 0, U->dz3_2, g, 2));
         TRY(conv_dgrad(I_C32, U->dz3_2, U->dz3_1, 128, 0, U->a3_1, 128, 0, 2));
         TRY(conv_wgrad(I_C31, U->p2, 64, 0, U->dz3_1, g, 2));
         TRY(conv_dgrad(I_C31, U->dz3_1, U->dp2, 64, 0, nullptr, 0, 0, 2));
-        TRY(pool_bwd(U->cat8, U->dcat8, 128, 64, U->dp2, U->dz2_2, 64, 2));
+        TRY(pool_bwd(U->cat8, 128, 64, skip_half(U->dcat8, 1, 64), U->dp2, U->dz2_2, 64, 2));
         TRY(conv_wgrad(I_C22, U->a2_1, 64, 0, U->dz2_2, g, 1));
         TRY(conv_dgrad(I_C22, U->dz2_2, U->dz2_1, 64, 0, U->a2_1, 64, 0, 1));
         TRY(conv_wgrad(I_C21, U->p1, 32, 0, U->dz2_1, g, 1));
         TRY(conv_dgrad(I_C21, U->dz2_1, U->dp1, 32, 0, nullptr, 0, 0, 1));
-        TRY(pool_bwd(U->cat9, U->dcat9, 64, 32, U->dp1, U->dz1_2, 32, 1));
+        TRY(pool_bwd(U->cat9, 64, 32, skip_half(U->dcat9, 0, 32), U->dp1, U->dz1_2, 32, 1));
         TRY(conv_wgrad(I_C12, U->a1_1, 32, 0, U->dz1_2, g, 0));
         TRY(conv_dgrad(I_C12, U->dz1_2, U->dz1_1, 32, 0, U->a1_1, 32, 0, 0));
         const double px = (double)U->n * U->H * U->W;
@@ -688,6 +699,13 @@ extern "C" int eld_adam_step(eld_ctx* ctx, float* params, const float* grads, fl
     ELD_CHECK_CUDA(cudaSetDevice(ctx->device));
     return launch_adam(ctx, params, grads, m, v, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale,
                        static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int eld_clock_probe(eld_ctx* ctx, float* out_mhz_device, void* stream)
+{
+    ELD_REQUIRE(ctx && out_mhz_device, "eld_clock_probe: NULL argument");
+    ELD_CHECK_CUDA(cudaSetDevice(ctx->device));
+    return launch_clock_probe(ctx, out_mhz_device, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int eld_unet_profile(eld_unet* u, int enable)

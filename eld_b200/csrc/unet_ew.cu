@@ -71,7 +71,7 @@ maxpool_kernel(const __nv_bfloat16* __restrict__ in, int in_pitch, int in_c0, __
 // PyTorch's max_pool2d backward routes to the FIRST maximum in window scan order; so do we.
 __global__ void __launch_bounds__(256)
 maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restrict__ dskip, int a_pitch, int a_c0,
-                   const __nv_bfloat16* __restrict__ dP, __nv_bfloat16* __restrict__ dZ, int C, int n_img, int Ho, int Wo)
+                   int s_pitch, int s_c0, const __nv_bfloat16* __restrict__ dP, __nv_bfloat16* __restrict__ dZ, int C, int n_img, int Ho, int Wo)
 {
     const int groups = C / 8;
     const size_t total = (size_t)n_img * Ho * Wo * groups;
@@ -87,7 +87,7 @@ maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __r
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const uint4 av = ld16(A + offs[k] * a_pitch + a_c0 + gch * 8);
-            const uint4 sv = ld16(dskip + offs[k] * a_pitch + a_c0 + gch * 8);
+            const uint4 sv = ld16(dskip + offs[k] * s_pitch + s_c0 + gch * 8);
             a[k][0] = av.x; a[k][1] = av.y; a[k][2] = av.z; a[k][3] = av.w;
             s[k][0] = sv.x; s[k][1] = sv.y; s[k][2] = sv.z; s[k][3] = sv.w;
         }
@@ -173,14 +173,41 @@ colsum_kernel(const __nv_bfloat16* __restrict__ g, int pitch, int c0, int C, siz
 // lanes completes them.  Lane q then plays output channel q (bias, loss, dOut), every lane accumulates its 4 x 8 block
 // of dW and writes its own 8 channels of dZ.  ~80 registers -> three 256-thread blocks per SM, and the next pixel's
 // loads are issued before the current pixel's arithmetic (the kernel is HBM-latency bound: 160 B per pixel).
-constexpr int kHeadThreads = 128;      // 32 pixels per block iteration; 5 blocks per SM at <= 102 registers
+constexpr int kHeadThreads = 128;      // 32 pixels per block iteration; 4 blocks per SM (<= 128 registers, no spills)
+constexpr int kHeadStages = 8;         // cp.async ring: 8 x (2 KB activations + 0.5 KB target) per block in flight
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
+// walks pixel indices pb, pb + stride, ... as (image n, in-plane offset l) without a 64-bit division per step
+struct PixWalk {
+    size_t n, l, plane, stride;
+    __device__ PixWalk(size_t p0, size_t plane_, size_t stride_) : n(p0 / plane_), l(p0 % plane_), plane(plane_), stride(stride_) {}
+    __device__ __forceinline__ void next() { l += stride; while (l >= plane) { l -= plane; ++n; } }
+    __device__ __forceinline__ size_t pix() const { return n * plane + l; }
+};
+
 template <bool TRAIN>
-__global__ void __launch_bounds__(kHeadThreads, 5)
+__global__ void __launch_bounds__(kHeadThreads, 4)
 head_kernel(const __nv_bfloat16* __restrict__ a, const float* __restrict__ w, const float* __restrict__ b,
             float* __restrict__ out, const float* __restrict__ target, __nv_bfloat16* __restrict__ dz,
             float* __restrict__ dw, float* __restrict__ db, float* __restrict__ loss,
             int n_img, size_t plane, float inv_numel)
 {
+    // The kernel is HBM-LATENCY bound (160 B per pixel, ~150 instructions): one register-prefetched pixel per thread
+    // kept only ~13 KB per SM in flight (37 % of the bandwidth-delay product).  Every thread now streams ITS OWN 16 bytes
+    // of the pixel and ITS OWN target value through a private slot of a kHeadStages-deep cp.async ring - 7 pixels ahead,
+    // no registers, and no block barrier because a thread only ever reads what it copied itself.
+    __shared__ uint4 ring_a[kHeadStages][kHeadThreads];
+    __shared__ float ring_t[TRAIN ? kHeadStages : 1][kHeadThreads];
     __shared__ float ws[4][33];
     __shared__ float bs[4];
     __shared__ float red[4 * 32 + 4 + 1];
@@ -207,29 +234,35 @@ head_kernel(const __nv_bfloat16* __restrict__ a, const float* __restrict__ w, co
     const size_t total = (size_t)n_img * plane;
     constexpr int kPix = kHeadThreads / 4;
     const size_t stride = (size_t)gridDim.x * kPix;
-    // block-uniform trip count (the shuffles below need whole warps); a ragged tail only masks the memory ops
-    size_t pbase = (size_t)blockIdx.x * kPix;
-    auto locate = [&](size_t pb, bool& valid, size_t& p, size_t& oidx) {
-        valid = pb + (tid >> 2) < total;
-        p = valid ? pb + (tid >> 2) : total - 1;
-        const size_t n = p / plane, l = p - n * plane;
-        oidx = (n * 4 + q) * plane + l;
-    };
-    bool valid, nvalid = false;
-    size_t p, oidx, np = 0, noidx = 0;
-    uint4 v = make_uint4(0, 0, 0, 0), nv = make_uint4(0, 0, 0, 0);
-    float tg = 0.f, ntg = 0.f;
-    if (pbase < total) {
-        locate(pbase, valid, p, oidx);
-        v = __ldg(reinterpret_cast<const uint4*>(a + p * 32) + q);
-        if (TRAIN) tg = __ldg(target + oidx);
-    }
-    for (; pbase < total; pbase += stride) {
-        if (pbase + stride < total) {                     // prefetch the next pixel of this thread
-            locate(pbase + stride, nvalid, np, noidx);
-            nv = __ldg(reinterpret_cast<const uint4*>(a + np * 32) + q);
-            if (TRAIN) ntg = __ldg(target + noidx);
+    // block-uniform trip count (the shuffles below need whole warps); a ragged tail only masks the memory ops.
+    // `first` = this thread's pixel in the block's first group; a thread past the end clamps to the last pixel.
+    const size_t first = (size_t)blockIdx.x * kPix + (tid >> 2);
+    const size_t iters = (size_t)blockIdx.x * kPix < total ? (total - (size_t)blockIdx.x * kPix + stride - 1) / stride : 0;
+    PixWalk load_w(first < total ? first : total - 1, plane, stride), use_w(first < total ? first : total - 1, plane, stride);
+    size_t load_p = first, use_p = first;
+    auto issue = [&](size_t it) {
+        if (it < iters) {
+            const bool ok = load_p < total;
+            const size_t p = ok ? load_w.pix() : total - 1;
+            const size_t n = ok ? load_w.n : (total - 1) / plane, l = ok ? load_w.l : (total - 1) % plane;
+            cp_async16(&ring_a[it % kHeadStages][tid], reinterpret_cast<const uint4*>(a + p * 32) + q);
+            if (TRAIN) cp_async4(&ring_t[it % kHeadStages][tid], target + (n * 4 + q) * plane + l);
+            if (ok) load_w.next();
+            load_p += stride;
         }
+        cp_async_commit();
+    };
+    for (int st = 0; st < kHeadStages - 1; ++st) issue((size_t)st);
+    for (size_t it = 0; it < iters; ++it) {
+        issue(it + kHeadStages - 1);
+        cp_async_wait<kHeadStages - 1>();
+        const bool valid = use_p < total;
+        const size_t p = valid ? use_w.pix() : total - 1;
+        const size_t oidx = valid ? (use_w.n * 4 + q) * plane + use_w.l : 0;
+        const uint4 v = ring_a[it % kHeadStages][tid];
+        const float tg = TRAIN ? ring_t[it % kHeadStages][tid] : 0.f;
+        if (valid) use_w.next();
+        use_p += stride;
         const uint32_t wv[4] = { v.x, v.y, v.z, v.w };
         float av[8];
 #pragma unroll
@@ -245,7 +278,7 @@ head_kernel(const __nv_bfloat16* __restrict__ a, const float* __restrict__ w, co
             o[co] = acc;
         }
         const float mine = (q == 0 ? o[0] : q == 1 ? o[1] : q == 2 ? o[2] : o[3]) + bq;
-        if (valid) out[oidx] = mine;
+        if (valid) __stcs(out + oidx, mine);
         if (TRAIN) {
             const float e = valid ? mine - tg : 0.f;
             ploss += fabsf(e);
@@ -273,8 +306,8 @@ head_kernel(const __nv_bfloat16* __restrict__ a, const float* __restrict__ w, co
             }
             if (valid) reinterpret_cast<uint4*>(dz + p * 32)[q] = make_uint4(zo[0], zo[1], zo[2], zo[3]);
         }
-        v = nv; tg = ntg; valid = nvalid; p = np; oidx = noidx;
     }
+    cp_async_wait<0>();
     if (TRAIN) {
         // reduce over the 8 lanes of a warp that share `q` (lane ^ 4, 8, 16), then shared atomics, then one global
         // atomic per value per block
@@ -352,12 +385,12 @@ int launch_maxpool(eld_ctx* ctx, const void* in, int in_pitch, int in_c0, void* 
     return ELD_OK;
 }
 
-int launch_maxpool_bwd(eld_ctx* ctx, const void* A, const void* dskip, int a_pitch, int a_c0, const void* dP, void* dZ,
-                       int C, int n, int Ho, int Wo, cudaStream_t st)
+int launch_maxpool_bwd(eld_ctx* ctx, const void* A, int a_pitch, int a_c0, const void* dskip, int s_pitch, int s_c0,
+                       const void* dP, void* dZ, int C, int n, int Ho, int Wo, cudaStream_t st)
 {
     const size_t work = (size_t)n * Ho * Wo * (C / 8);
     maxpool_bwd_kernel<<<grid_for(work, 256, 16 * ctx->num_sms), 256, 0, st>>>(
-        static_cast<const __nv_bfloat16*>(A), static_cast<const __nv_bfloat16*>(dskip), a_pitch, a_c0,
+        static_cast<const __nv_bfloat16*>(A), static_cast<const __nv_bfloat16*>(dskip), a_pitch, a_c0, s_pitch, s_c0,
         static_cast<const __nv_bfloat16*>(dP), static_cast<__nv_bfloat16*>(dZ), C, n, Ho, Wo);
     ELD_CHECK_CUDA(cudaGetLastError());
     count_launch(ctx);
@@ -381,12 +414,33 @@ int launch_head(eld_ctx* ctx, const void* a, const float* w, const float* b, flo
     const size_t total = (size_t)n * plane;
     const float inv = 1.0f / (float)(total * 4);
     if (target) {
-        head_kernel<true><<<grid_for(total, 32 * 16, 5 * ctx->num_sms), kHeadThreads, 0, st>>>(
+        head_kernel<true><<<grid_for(total, 32 * 16, 4 * ctx->num_sms), kHeadThreads, 0, st>>>(
             static_cast<const __nv_bfloat16*>(a), w, b, out, target, static_cast<__nv_bfloat16*>(dz), dw, db, loss, n, plane, inv);
     } else {
-        head_kernel<false><<<grid_for(total, 32, 10 * ctx->num_sms), kHeadThreads, 0, st>>>(
+        head_kernel<false><<<grid_for(total, 32, 8 * ctx->num_sms), kHeadThreads, 0, st>>>(
             static_cast<const __nv_bfloat16*>(a), w, b, out, nullptr, nullptr, nullptr, nullptr, nullptr, n, plane, inv);
     }
+    ELD_CHECK_CUDA(cudaGetLastError());
+    count_launch(ctx);
+    return ELD_OK;
+}
+
+// SM clock actually delivered at this point of the stream: one thread spins for ~`spin_ns` of %globaltimer and reports
+// SM cycles (%clock64) per microsecond.  nvidia-smi samples every ~20 ms and averages; this reads the clock the kernels
+// just before it ran at (DVFS reacts in milliseconds).
+__global__ void clock_probe_kernel(float* out_mhz, unsigned long long spin_ns)
+{
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    const long long c0 = clock64();
+    do { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1)); } while (t1 - t0 < spin_ns);
+    const long long c1 = clock64();
+    *out_mhz = (float)((double)(c1 - c0) * 1000.0 / (double)(t1 - t0));
+}
+
+int launch_clock_probe(eld_ctx* ctx, float* out_mhz, cudaStream_t st)
+{
+    clock_probe_kernel<<<1, 1, 0, st>>>(out_mhz, 20000ull);
     ELD_CHECK_CUDA(cudaGetLastError());
     count_launch(ctx);
     return ELD_OK;

@@ -55,6 +55,9 @@ int launch_conv_gemm(eld_ctx* ctx, const GemmOp& op, cudaStream_t st)
     ELD_REQUIRE(op.pool_out == nullptr || (op.epi_mode == EPI_STORE && op.H % 2 == 0 && op.W % 2 == 0),
                 "conv tile: the fused max pool needs a plain store epilogue and even H, W");
     p.pool_out = static_cast<__nv_bfloat16*>(op.pool_out); p.pool_pitch = op.pool_pitch;
+    ELD_REQUIRE(op.out_split == 0 || (op.epi_mode == EPI_STORE && op.out2 && op.out_split % 32 == 0 && op.out2_pitch % 8 == 0),
+                "conv tile: split store needs a plain store epilogue, a second tensor and a split at a multiple of 32 columns");
+    p.out2 = static_cast<__nv_bfloat16*>(op.out2); p.out2_pitch = op.out2_pitch; p.out_split = op.out_split;
     const int rb = p.kc * 2;
     const int b_tile = p.n_tile * rb;
     const int b_total = op.taps * (op.cin / p.kc) * b_tile;

@@ -87,6 +87,9 @@ int    eld_unet_wait_bucket(eld_unet* u, int bucket, void* stream);
  * eld_unet_profile_read synchronises, returns name[32] / ms / algorithmic FLOPs / algorithmic bytes per
  * launch and clears the log.  Used by bench.py for the live roofline numbers. */
 int    eld_unet_profile(eld_unet* u, int enable);
+/* Measurement aid (no reference counterpart): a one-thread kernel on `stream` that compares %clock64 with %globaltimer
+ * for ~20 us and writes the SM clock in MHz that the preceding kernels were running at to *out_mhz_device. */
+int    eld_clock_probe(eld_ctx* ctx, float* out_mhz_device, void* stream);
 int    eld_unet_profile_read(eld_unet* u, int max, char* names32, float* ms, double* flops, double* bytes, int* count);
 int    eld_adam_step(eld_ctx* ctx, float* params, const float* grads, float* m, float* v, size_t n,
                      float lr, float beta1, float beta2, float eps, float weight_decay, int step,

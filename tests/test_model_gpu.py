@@ -64,7 +64,8 @@ def test_checkpoint_roundtrip_reference_format(torch, tmp_path):
     m.epoch, m.iterations = 3, 17
     m.save(label='latest')
     sd = torch.load(os.path.join(str(tmp_path), 'ck', 'model_latest.pt'), weights_only=False)
-    assert set(sd) == {'netG', 'opt_g', 'epoch', 'iterations'}                 # ELD_model.py:516-523
+    # ELD_model.py:516-523's four keys (the reference's load reads exactly these) + the running global frame count
+    assert set(sd) == {'netG', 'opt_g', 'epoch', 'iterations', 'frames_seen'}
     UNetSeeInDarkRef(4, 4).load_state_dict(sd['netG'])                          # loads into the reference-shaped module
     ref_adam = torch.optim.Adam(UNetSeeInDarkRef(4, 4).parameters())
     ref_adam.load_state_dict(sd['opt_g'])                                       # torch.optim.Adam accepts 'opt_g'

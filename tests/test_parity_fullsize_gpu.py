@@ -8,10 +8,12 @@
 Gates (bf16 operands / activations / stored gradients, fp32 accumulation):
   out        rel-L2 <= 2e-2 vs fp32 oracle, <= 3e-3 vs emulation
   loss       <= 1e-2 relative vs fp32 oracle, <= 2e-3 vs emulation
-  gradients  per tensor rel-L2 <= 1e-2 vs the emulated backward (fp32 atomics reorder sums; a real indexing or
-             masking bug moves a tensor by >= 1e-1), and <= 8e-2 vs the fp32 autograd (the bf16 storage itself)
+  gradients  per tensor rel-L2 <= 2e-3 vs the emulated backward (measured on B200: 9e-6 .. 6.5e-4, fp32 atomics
+             reorder sums; a real indexing or masking bug moves a tensor by >= 1e-1), and <= 5e-2 vs the fp32 autograd
+             (the bf16 storage itself: measured 1e-3 .. 3e-2, largest at the 32 x 32 bottleneck)
   dPSNR      <= 0.05 dB between engine and fp32 oracle on seeded synthetic pairs (input = batch_gpu(clean), target =
              clean) with weights TRAINED for 200 Adam steps - an untrained net vs a random target is insensitive.
+             Measured: 0.003 .. 0.005 dB with the same weights, -0.02 dB between the two training trajectories.
 """
 import numpy as np
 import pytest
@@ -120,7 +122,7 @@ def test_train_step_8x4x512x512_config2(torch):
     assert abs(loss.item() - l32.item()) <= 1e-2 * l32.item(), (loss.item(), l32.item())
     table = [(k, _rel(mine[k], gem[k]), _rel(mine[k], g32[k])) for k in mine]
     print('\n'.join('%-18s emu %.2e   fp32 %.2e' % r for r in table))
-    bad = [r for r in table if not (r[1] <= 1e-2 and r[2] <= 8e-2)]
+    bad = [r for r in table if not (r[1] <= 2e-3 and r[2] <= 5e-2)]
     assert not bad, bad
 
 
@@ -128,7 +130,7 @@ def test_dpsnr_after_200_adam_steps(torch):
     """Train the engine for 200 Adam steps (batch 2 x 4 x 256 x 256 crops of seeded smooth frames, P+g noise made by
     batch_gpu), train the fp32 oracle on the SAME stream, then on held-out 1 x 4 x 512 x 512 pairs:
       (1) engine forward vs oracle forward with the SAME trained weights: |dPSNR| <= 0.05 dB (the north-star gate);
-      (2) engine-trained vs oracle-trained weights (two chaotic bf16 / fp32 trajectories): |dPSNR| <= 0.25 dB, and
+      (2) engine-trained vs oracle-trained weights (two bf16 / fp32 training trajectories): |mean dPSNR| <= 0.05 dB, and
           both must have learnt to denoise (PSNR(out) > PSNR(noisy input) + 1 dB)."""
     from oracle import ref_numpy
     from oracle.unet_ref import l1_train_step
@@ -165,4 +167,4 @@ def test_dpsnr_after_200_adam_steps(torch):
     print('dPSNR same weights', d_same, 'two trajectories', d_traj, 'gain over noisy input (engine, oracle)', gain)
     assert max(abs(d) for d in d_same) <= 0.05, d_same
     assert all(g[0] > 1.0 and g[1] > 1.0 for g in gain), gain
-    assert abs(float(np.mean(d_traj))) <= 0.25, d_traj
+    assert abs(float(np.mean(d_traj))) <= 0.05, d_traj

@@ -1,7 +1,10 @@
 #!/usr/bin/env python
 """Per-launch table from `ncu --csv` (tools/ncu_round.sh step_sol.csv): duration, DRAM bytes, DRAM / L2 / tensor-pipe %,
 joined with the engine's launch order (gpurun_out/.../layers.json) so every row carries its layer name.
-    python tools/ncu_step_table.py step_sol.csv [layers.json]
+    python tools/ncu_step_table.py step_sol.csv [layers.json] [traffic.json]
+With a third argument the DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum per launch) is also written as
+JSON - bench.py reads profiles/ncu_traffic.json for `roofline.traffic` (tensor tiles of a step) and
+`roofline_noise.traffic`.
 """
 import collections
 import csv
@@ -46,3 +49,21 @@ for i, d in enumerate(per.values()):
         i, lay, k, us, f(d, 'dram__bytes_read.sum') / 1e6, f(d, 'dram__bytes_write.sum') / 1e6,
         f(d, 'DRAM Throughput'), f(d, 'L2 Cache Throughput'), f(d, 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed')))
 print('total %.1f us over %d launches (ncu: serialised, cold caches, --clock-control none)' % (tot, len(per)))
+if len(sys.argv) > 3:
+    import os
+    tiles = noise = 0.0
+    rows_out = []
+    for d in per.values():
+        k = d['kernel']
+        by = f(d, 'dram__bytes_read.sum') + f(d, 'dram__bytes_write.sum')
+        rows_out.append({'kernel': k.replace('void ', '').split('(')[0][:60], 'dram_bytes': by, 'us': f(d, 'gpu__time_duration.sum') / 1e3})
+        if 'conv_umma_kernel' in k or 'wgrad_conv_kernel' in k or 'wgrad_umma_kernel' in k:
+            tiles += by
+        if 'noise_packed' in k:
+            noise = by
+    out = {}
+    if os.path.exists(sys.argv[3]):
+        out = json.load(open(sys.argv[3]))
+    out['train'] = {'tensor_tile_bytes_per_step': tiles, 'noise_bytes_per_launch': noise, 'launches': rows_out,
+                    'source': 'ncu --clock-control none, SpeedOfLight + MemoryWorkloadAnalysis sections, one training step (tools/ncu_step.py)'}
+    json.dump(out, open(sys.argv[3], 'w'), indent=0)
