@@ -59,9 +59,6 @@ int eld_ctx_create(int device, eld_ctx** out)
         return ELD_E_CUDA;
     }
     ctx->encode_tiled = (eld::PFN_encodeTiled)fn;
-    if (const char* g = getenv("ELD_L2_FETCH")) {      // experiment: L2 fetch granularity hint (32 / 64 / 128 bytes)
-        ELD_CHECK_CUDA(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g)));
-    }
     { int rc = eld::init_gemm_kernels(ctx); if (rc != ELD_OK) { delete ctx; return rc; } }
     *out = ctx;
     return ELD_OK;

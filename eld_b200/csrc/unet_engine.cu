@@ -87,12 +87,13 @@ __global__ void __launch_bounds__(256)
 pack_all_kernel(const float* __restrict__ params, __nv_bfloat16* __restrict__ packed, const __grid_constant__ PackTable T)
 {
     __shared__ float tile[32][32 * 9 + 1];
-    if ((int)blockIdx.x >= T.tile0[T.n]) {   // conv1_1: w[32][4][9] -> operand [32][9][32] (channels 4..31 stay zero)
-        const float* w1 = params + T.first_dst;
+    if ((int)blockIdx.x >= T.tile0[T.n]) {   // conv1_1: w[32][4][9] -> K-major operand [32 co][64 k], k = tap*4 + c (first_conv.cuh),
+        const float* w1 = params + T.first_dst;   // 128-byte rows with the SW128 swizzle; k >= 36 are zeros (k = 36 meets the ones column)
         const int b = (int)blockIdx.x - T.tile0[T.n], nb = (int)gridDim.x - T.tile0[T.n];
-        for (int i = b * 256 + threadIdx.x; i < 32 * 36; i += nb * 256) {
-            const int co = i / 36, r = i - co * 36, ci = r / 9, t = r - ci * 9;
-            packed[T.first_wf + packed_index(32, 32, 9, co, t, ci)] = __float2bfloat16_rn(w1[i]);
+        for (int i = b * 256 + threadIdx.x; i < 32 * 64; i += nb * 256) {
+            const int co = i >> 6, k = i & 63, tap = k >> 2, c = k & 3;
+            const float v = k < 36 ? w1[(co * 4 + c) * 9 + tap] : 0.0f;
+            packed[T.first_wf + (size_t)co * 64 + ((((k >> 3) ^ (co & 7)) << 3) | (k & 7))] = __float2bfloat16_rn(v);
         }
         return;
     }
@@ -149,19 +150,10 @@ __global__ void __launch_bounds__(256)
 wgrad_permute_kernel(const float* __restrict__ gtmp, float* __restrict__ grads, const __grid_constant__ PackTable T,
                      int tile_begin, int tile_end)
 {
-    // blocks [0, tile_end - tile_begin) move the table tiles [tile_begin, tile_end) (one gradient bucket); any further
-    // blocks (launched with the last bucket only) move conv1_1
+    // blocks [0, tile_end - tile_begin) move the table tiles [tile_begin, tile_end) (one gradient bucket)
     __shared__ float tile[9][32][33];
     const int gtile = (int)blockIdx.x + tile_begin;
-    if (gtile >= tile_end) {   // conv1_1: staging is [9][32 (4 real)][32] behind the regular area; dst [32][4][9] at offset 0
-        const float* src = gtmp + T.first_stage;
-        const int b = gtile - tile_end, nb = (int)gridDim.x - (tile_end - tile_begin);
-        for (int i = b * 256 + threadIdx.x; i < 32 * 36; i += nb * 256) {
-            const int co = i / 36, r = i - co * 36, ci = r / 9, tap = r - ci * 9;
-            grads[T.first_dst + i] = src[(tap * 32 + ci) * 32 + co];
-        }
-        return;
-    }
+    if (gtile >= tile_end) return;
     int t;
     const PackEntry& e = T.e[find_entry(T, gtile, t)];
     if (e.type != L_CONV3) return;
@@ -194,7 +186,7 @@ struct eld_unet {
     size_t ws_bytes;
     // activations / gradients (bf16), offsets in bytes into ws
     __nv_bfloat16 *a1_1, *cat9, *p1, *a2_1, *cat8, *p2, *a3_1, *cat7, *p3, *a4_1, *cat6, *p4, *a5_1, *a5_2,
-        *a6_1, *a6_2, *a7_1, *a7_2, *a8_1, *a8_2, *a9_1, *a9_2, *x32 = nullptr;
+        *a6_1, *a6_2, *a7_1, *a7_2, *a8_1, *a8_2, *a9_1, *a9_2;
     __nv_bfloat16 *dz9_2, *dz9_1, *dcat9, *dz8_2, *dz8_1, *dcat8, *dz7_2, *dz7_1, *dcat7, *dz6_2, *dz6_1, *dcat6,
         *dz5_2, *dz5_1, *dp4, *dz4_2, *dz4_1, *dp3, *dz3_2, *dz3_1, *dp2, *dz2_2, *dz2_1, *dp1, *dz1_2, *dz1_1;
     __nv_bfloat16* packed;
@@ -226,7 +218,6 @@ static size_t layout(eld_unet* u, char* base, bool train)
     take(&u->a5_1, 4, 512); take(&u->a5_2, 4, 512);
     take(&u->a6_1, 3, 256); take(&u->a6_2, 3, 256); take(&u->a7_1, 2, 128); take(&u->a7_2, 2, 128);
     take(&u->a8_1, 1, 64); take(&u->a8_2, 1, 64); take(&u->a9_1, 0, 32); take(&u->a9_2, 0, 32);
-    take(&u->x32, 0, 32);
     if (train) {
         take(&u->dz9_2, 0, 32); take(&u->dz9_1, 0, 32); take(&u->dcat9, 0, 64);
         take(&u->dz8_2, 1, 64); take(&u->dz8_1, 1, 64); take(&u->dcat8, 1, 128);
@@ -252,7 +243,7 @@ static size_t layout(eld_unet* u, char* base, bool train)
     off += (pk * 2 + 1023) & ~(size_t)1023;
     if (train) {   // [tap][ci][co] staging of the conv3x3 weight gradients (same offsets as the fp32 parameters)
         u->gtmp = reinterpret_cast<float*>(base + off);
-        off += ((u->n_params + 9216) * 4 + 1023) & ~(size_t)1023;     // + [9][32][32] staging of conv1_1 (input padded to 32 ch)
+        off += (u->n_params * 4 + 1023) & ~(size_t)1023;
     }
     return off;
 }
@@ -336,7 +327,7 @@ extern "C" int eld_unet_create(eld_ctx* ctx, int n, int h, int w, int train, voi
     u->table.first_stage = u->n_params;
     u->table.first_dst = u->L[I_C11].w_off;
     u->table.first_wf = u->L[I_C11].wf_off;
-    // the padded input channels of conv1_1's operand must be finite zeros (they multiply the zero channels of x32)
+    // conv1_1's operand image: zero once (pack_all rewrites all of it every step anyway)
     ELD_CHECK_CUDA(cudaMemset(u->packed + u->L[I_C11].wf_off, 0, 32 * 9 * 32 * sizeof(__nv_bfloat16)));
     // opt in to large dynamic shared memory once (not inside a captured region)
     { int rc = init_gemm_kernels(ctx); if (rc != ELD_OK) { delete u; return rc; } }
@@ -528,7 +519,7 @@ struct Runner {
     int finish_bucket(int k, float* g) const
     {
         const int t0 = u->table.tile0[kBucketEntry0[k]], t1 = u->table.tile0[kBucketEntry1[k]];
-        const int extra = k == kGradBuckets - 1 ? 2 : 0;         // conv1_1 rides with the last bucket
+        const int extra = 0;                                      // (conv1_1's wgrad tile writes the PyTorch layout itself)
         {
             Scope sc(u, st, "weights", "gperm", 0.0, 0.0);
             wgrad_permute_kernel<<<t1 - t0 + extra, 256, 0, st>>>(u->gtmp, g, u->table, t0, t1);
@@ -554,19 +545,10 @@ struct Runner {
         static const bool fuse_pool = getenv("ELD_NO_FUSED_POOL") == nullptr;   // (A/B: the stand-alone pool kernel)
         TRY(pack());
         {
+            // conv1_1 (4 -> 32): software-im2col tile straight from the fp32 NCHW frame (first_conv.cuh)
             const double px = (double)U->n * U->H * U->W;
-            {
-                Scope sc(u, st, "input", "pack", 0.0, px * (16 + 64));
-                TRY(launch_pack_input(ctx(), x, U->x32, U->n, U->H, U->W, st));
-            }
-            // conv1_1 (4 -> 32) as a 32 -> 32 tcgen05 tile on the zero-padded input
-            GemmOp op{};
-            op.a = U->x32; op.a_pitch = 32; op.a_c0 = 0; op.a_mode = A_CONV; op.taps = 9; op.cin = 32;
-            op.n_img = U->n; op.H = U->H; op.W = U->W;
-            op.b = wf(I_C11); op.n_total = 32; op.cout = 32;
-            op.epi_mode = EPI_STORE; op.act = ACT_LRELU; op.out = U->a1_1; op.out_pitch = 32; op.out_c0 = 0; op.bias = bias(I_C11);
-            Scope sc(u, st, "conv1_1", "fprop", 2.0 * px * 32 * 36, px * (64 + 64));
-            TRY(launch_conv_gemm(ctx(), op, st));
+            Scope sc(u, st, "conv1_1", "fprop", 2.0 * px * 32 * 36, px * (16 + 64));
+            TRY(launch_first_conv(ctx(), x, wf(I_C11), bias(I_C11), U->a1_1, 32, U->n, U->H, U->W, st));
         }
         if (fuse_pool) { TRY(conv(I_C12, U->a1_1, 32, 0, U->cat9, 64, 32, 0, U->p1)); } else { TRY(conv(I_C12, U->a1_1, 32, 0, U->cat9, 64, 32, 0)); TRY(pool(U->cat9, 64, 32, U->p1, 32, 1)); }      // + pool (Unet.py:51)
         TRY(conv(I_C21, U->p1, 32, 0, U->a2_1, 64, 0, 1));
@@ -641,16 +623,10 @@ struct Runner {
         TRY(pool_bwd(U->cat9, 64, 32, skip_half(U->dcat9, 0, 32), U->dp1, U->dz1_2, 32, 1));
         TRY(conv_wgrad(I_C12, U->a1_1, 32, 0, U->dz1_2, g, 0));
         TRY(conv_dgrad(I_C12, U->dz1_2, U->dz1_1, 32, 0, U->a1_1, 32, 0, 0));
-        const double px = (double)U->n * U->H * U->W;
         {
-            // conv1_1: the tcgen05 wgrad tile on the 32-channel padded copy of the input (4 real channels)
-            Scope sc(u, st, "conv1_1", "wgrad", 2.0 * px * 32 * 36, px * (64 + 64));
-            WgradOp op{};
-            op.mode = WG_CONV; op.p = U->x32; op.p_pitch = 32; op.p_c0 = 0; op.p_ch = 32;
-            op.q = U->dz1_1; op.q_pitch = 32; op.q_c0 = 0; op.q_ch = 32;
-            op.n_img = U->n; op.H = U->H; op.W = U->W; op.dw = U->gtmp + U->n_params; op.out_tco = 1;
-            op.db = g + U->L[I_C11].b_off;
-            TRY(launch_wgrad(ctx(), op, st));
+            const double px = (double)U->n * U->H * U->W;
+            Scope sc(u, st, "conv1_1", "wgrad", 2.0 * px * 32 * 36, px * (16 + 64));
+            TRY(launch_first_conv_wgrad(ctx(), x, U->dz1_1, 32, g + U->L[I_C11].w_off, g + U->L[I_C11].b_off, U->n, U->H, U->W, st));
         }
         return finish_bucket(2, g);
     }
@@ -678,7 +654,7 @@ extern "C" int eld_unet_train_step(eld_unet* u, const float* params, const float
     ELD_CHECK_CUDA(cudaSetDevice(u->ctx->device));
     Runner r{ u, params, static_cast<cudaStream_t>(stream) };
     ELD_CHECK_CUDA(cudaMemsetAsync(grads, 0, u->n_params * sizeof(float), r.st));
-    ELD_CHECK_CUDA(cudaMemsetAsync(u->gtmp, 0, (u->n_params + 9216) * sizeof(float), r.st));
+    ELD_CHECK_CUDA(cudaMemsetAsync(u->gtmp, 0, u->n_params * sizeof(float), r.st));
     ELD_CHECK_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), r.st));
     TRY(r.forward(x));
     {

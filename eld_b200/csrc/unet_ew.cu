@@ -1,6 +1,6 @@
 // unet_ew.cu - the non-GEMM kernels of the U-Net step (all HBM-bound, CUDA cores):
-//   first conv (4->32 on the fp32 NCHW noise output), 2x2 max-pool fwd / bwd(+skip add + LeakyReLU'),
-//   1x1 head + L1 loss + its whole backward, bias gradients, first-layer wgrad, fused Adam.
+//   2x2 max-pool fwd / bwd(+skip add + LeakyReLU'), 1x1 head + L1 loss + its whole backward, deconv bias gradients,
+//   fused Adam.
 #include "common.cuh"
 #include "unet_ew.h"
 #include <cuda_bf16.h>
@@ -14,23 +14,6 @@ __device__ __forceinline__ uint32_t pack_bf2(float a, float b)
 {
     const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<const uint32_t*>(&h);
-}
-
-// x f32 NCHW [n][4][H][W] -> x32 bf16 NHWC [n][H][W][32] (channels 4..31 zero): operand of the tcgen05 tiles for
-// conv1_1 (fprop and wgrad).  One pixel per thread: 4 coalesced plane reads, one 64-byte write.
-__global__ void __launch_bounds__(256)
-pack_input_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ x32, size_t plane, size_t total)
-{
-    for (size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x; p < total; p += (size_t)gridDim.x * blockDim.x) {
-        const size_t n = p / plane, l = p - n * plane;
-        const float* src = x + n * 4 * plane + l;
-        const float v0 = __ldg(src), v1 = __ldg(src + plane), v2 = __ldg(src + 2 * plane), v3 = __ldg(src + 3 * plane);
-        uint4* d = reinterpret_cast<uint4*>(x32 + p * 32);
-        d[0] = make_uint4(pack_bf2(v0, v1), pack_bf2(v2, v3), 0u, 0u);
-        d[1] = make_uint4(0u, 0u, 0u, 0u);
-        d[2] = make_uint4(0u, 0u, 0u, 0u);
-        d[3] = make_uint4(0u, 0u, 0u, 0u);
-    }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -364,15 +347,6 @@ static inline int grid_for(size_t work, int per_block, int cap)
     if (b > (size_t)cap) b = cap;
     if (b < 1) b = 1;
     return (int)b;
-}
-
-int launch_pack_input(eld_ctx* ctx, const float* x, void* x32, int n, int H, int W, cudaStream_t st)
-{
-    const size_t plane = (size_t)H * W, total = plane * n;
-    pack_input_kernel<<<grid_for(total, 256, 16 * ctx->num_sms), 256, 0, st>>>(x, static_cast<__nv_bfloat16*>(x32), plane, total);
-    ELD_CHECK_CUDA(cudaGetLastError());
-    count_launch(ctx);
-    return ELD_OK;
 }
 
 int launch_maxpool(eld_ctx* ctx, const void* in, int in_pitch, int in_c0, void* out, int C, int n, int Ho, int Wo, cudaStream_t st)

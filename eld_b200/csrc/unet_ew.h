@@ -3,7 +3,6 @@
 #include "common.cuh"
 
 namespace eld {
-int launch_pack_input(eld_ctx* ctx, const float* x, void* x32, int n, int H, int W, cudaStream_t st);
 int launch_maxpool(eld_ctx* ctx, const void* in, int in_pitch, int in_c0, void* out, int C, int n, int Ho, int Wo, cudaStream_t st);
 int launch_maxpool_bwd(eld_ctx* ctx, const void* A, int a_pitch, int a_c0, const void* dskip, int s_pitch, int s_c0,
                        const void* dP, void* dZ, int C, int n, int Ho, int Wo, cudaStream_t st);

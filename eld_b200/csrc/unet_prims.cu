@@ -7,6 +7,7 @@
 #include "conv_umma.cuh"
 #include "wgrad_umma.cuh"
 #include "wgrad_conv.cuh"
+#include "first_conv.cuh"
 #include "unet_prims.h"
 
 namespace eld {
@@ -145,8 +146,16 @@ int launch_conv_gemm(eld_ctx* ctx, const GemmOp& op, cudaStream_t st)
         ELD_CHECK_CUDA(cudaMalloc(&d, (size_t)grid * 16 * sizeof(long long)));
         ELD_CHECK_CUDA(cudaMemsetAsync(d, 0, (size_t)grid * 16 * sizeof(long long), st));
         p.prof = d;
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        cudaEventRecord(e0, st);
         conv_umma_kernel<true><<<grid, kConvThreads, smem, st>>>(tmA, p);
+        cudaEventRecord(e1, st);
         ELD_CHECK_CUDA(cudaStreamSynchronize(st));
+        float ev_ms = 0.f;
+        cudaEventElapsedTime(&ev_ms, e0, e1);
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        fprintf(stderr, "[conv prof] event time %.1f us | ", ev_ms * 1e3);
         std::vector<long long> h((size_t)grid * 16);
         ELD_CHECK_CUDA(cudaMemcpy(h.data(), d, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
         cudaFree(d);
@@ -164,9 +173,54 @@ int launch_conv_gemm(eld_ctx* ctx, const GemmOp& op, cudaStream_t st)
     return ELD_OK;
 }
 
+// conv1_1 (4 -> 32): software-im2col tcgen05 tiles on the fp32 NCHW frame (first_conv.cuh)
+int launch_first_conv(eld_ctx* ctx, const float* x, const void* w_img, const float* bias, void* out, int out_pitch,
+                      int n, int H, int W, cudaStream_t st)
+{
+    ELD_REQUIRE(H % 8 == 0 && W % 16 == 0, "first conv tile: H=%d must be a multiple of 8 and W=%d of 16", H, W);
+    FirstConvParams p{};
+    p.x = x; p.n_img = n; p.H = H; p.W = W; p.tiles_x = W / 16; p.tiles_y = H / 8;
+    p.w_img = static_cast<const uint8_t*>(w_img); p.bias = bias;
+    p.out = static_cast<__nv_bfloat16*>(out); p.out_pitch = out_pitch;
+    p.stages = 8;
+    const int total = n * p.tiles_x * p.tiles_y;
+    const int grid = total < ctx->num_sms ? total : ctx->num_sms;
+    const size_t smem = 1024 + 4096 + (size_t)p.stages * kFcATile + 1024;
+    ELD_CHECK_CUDA(launch_pdl(first_conv_fprop_kernel, grid, kFcThreads, smem, st, p));
+    ELD_CHECK_CUDA(cudaGetLastError());
+    count_launch(ctx);
+    return ELD_OK;
+}
+
+int launch_first_conv_wgrad(eld_ctx* ctx, const float* x, const void* dz, int dz_pitch, float* dw, float* db,
+                            int n, int H, int W, cudaStream_t st)
+{
+    ELD_REQUIRE(H % 8 == 0 && W % 16 == 0, "first conv wgrad tile: H=%d must be a multiple of 8 and W=%d of 16", H, W);
+    FirstConvParams p{};
+    p.x = x; p.n_img = n; p.H = H; p.W = W; p.tiles_x = W / 16; p.tiles_y = H / 8;
+    p.dw = dw; p.db = db;
+    p.stages = 6;
+    CUtensorMap tmQ;
+    const cuuint64_t eb = 2;
+    cuuint64_t dims[5] = { (cuuint64_t)dz_pitch, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n, 1 };
+    cuuint64_t str[4] = { dz_pitch * eb, (cuuint64_t)W * dz_pitch * eb, (cuuint64_t)H * W * dz_pitch * eb,
+                          (cuuint64_t)n * H * W * dz_pitch * eb };
+    cuuint32_t box[5] = { 32, 16, 8, 1, 1 };
+    { int rc = encode(ctx, &tmQ, dz, 5, dims, str, box, 64); if (rc) return rc; }
+    const int total = n * p.tiles_x * p.tiles_y;
+    const int grid = total < ctx->num_sms ? total : ctx->num_sms;
+    const size_t smem = 1024 + (size_t)p.stages * (kFcATile + kFcQTile) + kFcATile + 1024;
+    ELD_CHECK_CUDA(launch_pdl(first_conv_wgrad_kernel, grid, kFcThreads, smem, st, tmQ, p));
+    ELD_CHECK_CUDA(cudaGetLastError());
+    count_launch(ctx);
+    return ELD_OK;
+}
+
 int init_gemm_kernels(eld_ctx* ctx)
 {
     ELD_CHECK_CUDA(cudaSetDevice(ctx->device));
+    ELD_CHECK_CUDA(cudaFuncSetAttribute(first_conv_fprop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    ELD_CHECK_CUDA(cudaFuncSetAttribute(first_conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     ELD_CHECK_CUDA(cudaFuncSetAttribute(conv_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     ELD_CHECK_CUDA(cudaFuncSetAttribute(conv_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     ELD_CHECK_CUDA(cudaFuncSetAttribute(wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
