@@ -23,6 +23,11 @@ def declare_engine(lib):
     lib.eld_unet_workspace_bytes.argtypes = [i32, i32, i32, i32]
     lib.eld_unet_workspace_bytes.restype = sz
     lib.eld_unet_create.argtypes = [vp, i32, i32, i32, i32, vp, sz, c.POINTER(vp)]
+    lib.eld_unet_param_count_io.argtypes = [i32, i32]
+    lib.eld_unet_param_count_io.restype = sz
+    lib.eld_unet_param_offset_io.argtypes = [c.c_char_p, i32, i32, i32, c.POINTER(sz), c.POINTER(sz)]
+    lib.eld_unet_create_io.argtypes = [vp, i32, i32, i32, i32, vp, sz, i32, i32, c.POINTER(vp)]
+    lib.eld_unet_grad_buckets_io.argtypes = [i32, i32, c.POINTER(sz), i32]
     lib.eld_unet_destroy.argtypes = [vp]
     lib.eld_unet_destroy.restype = None
     lib.eld_unet_forward.argtypes = [vp, vp, vp, vp, vp]
@@ -31,6 +36,8 @@ def declare_engine(lib):
     lib.eld_unet_grad_buckets.argtypes = [c.POINTER(sz), i32]
     lib.eld_unet_bucket_events.argtypes = [vp, i32]
     lib.eld_unet_wait_bucket.argtypes = [vp, i32, vp]
+    lib.eld_unet_backward.argtypes = [vp, vp, vp, vp, vp, vp]
+    lib.eld_unet_set_loss.argtypes = [vp, i32]
     lib.eld_clock_probe.argtypes = [vp, vp, vp]
     lib.eld_unet_profile.argtypes = [vp, i32]
     lib.eld_unet_profile_read.argtypes = [vp, i32, c.c_char_p, vp, vp, vp, c.POINTER(i32)]

@@ -25,17 +25,52 @@ def _st():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+class _EngineFunction(torch.autograd.Function):
+    """The netG seam as an autograd node: forward = the training engine's forward (activations stay in its
+    workspace), backward = eld_unet_backward on the incoming d(loss)/d(out) - so the reference's own
+    `loss.backward(); optimizer.step()` (ELD_model.py:411-420,469-475) runs against this module unchanged, with any loss.
+    Parameters enter as inputs only so that autograd routes their gradients; the math reads the flat buffer."""
+
+    @staticmethod
+    def forward(ctx, net, x, *params):
+        n, _, h, w = x.shape
+        eng = net._engine(n, h, w, True)
+        out = torch.empty((n, net.out_channels, h, w), dtype=torch.float32, device=x.device)
+        _lib.check(_lib.load().eld_unet_forward(eng, net._flat.data_ptr(), x.data_ptr(), out.data_ptr(), _st()), 'eld_unet_forward')
+        ctx.net, ctx.eng = net, eng
+        ctx.save_for_backward(x)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        net = ctx.net
+        (x,) = ctx.saved_tensors
+        g = torch.empty_like(net._flat)
+        _lib.check(_lib.load().eld_unet_backward(ctx.eng, net._flat.data_ptr(), x.data_ptr(), dout.contiguous().data_ptr(),
+                                                g.data_ptr(), _st()), 'eld_unet_backward')
+        grads, off = [], 0
+        for p in net.parameters():
+            k = p.numel()
+            grads.append(g[off:off + k].view(p.shape))
+            off += k
+        return (None, None) + tuple(grads)       # no gradient wrt the input frame (the reference never asks for one)
+
+
 class UNetSeeInDark(nn.Module):
-    """B200-native UNetSeeInDark.  Only (in_channels, out_channels) = (4, 4) - the raw->raw path
-    train_syn.py uses (--channels 4, stage_in = stage_out = raw) - is built."""
+    """B200-native UNetSeeInDark(in_channels, out_channels) for 4-channel packed raw and 3-channel sRGB frames on either
+    side (ELD_model.py:377-389: --stage_in / --stage_out raw | srgb with --channels 4)."""
 
     def __init__(self, in_channels=4, out_channels=4):
         super().__init__()
-        if (in_channels, out_channels) != (4, 4):
-            raise NotImplementedError('the B200 engine implements the raw Bayer path: in=out=4 channels')
+        if in_channels not in (3, 4) or out_channels not in (3, 4):
+            raise NotImplementedError('the B200 engine takes 4-channel (packed Bayer) or 3-channel (sRGB) frames; X-Trans '
+                                      '(--channels 9) is out of scope (SURVEY 8a row a-X)')
+        self.in_channels, self.out_channels = in_channels, out_channels
         # real torch layers, constructed in the reference ORDER, only to reproduce the default init
         # and the state_dict keys; they are never called.
         for name, kind, cin, cout in _SPEC:
+            cin = in_channels if name == 'conv1_1' else cin
+            cout = out_channels if name == 'conv10_1' else cout
             if kind == 'c':
                 m = nn.Conv2d(cin, cout, kernel_size=3, stride=1, padding=1)
             elif kind == 'd':
@@ -113,33 +148,41 @@ class UNetSeeInDark(nn.Module):
             lib = _lib.load()
             dev = self._flat.device
             assert dev.type == 'cuda', 'the B200 engine has no CPU path'
-            assert lib.eld_unet_param_count() == self._flat.numel()
+            assert lib.eld_unet_param_count_io(self.in_channels, self.out_channels) == self._flat.numel()
             nbytes = lib.eld_unet_workspace_bytes(n, h, w, int(train))
             ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
             handle = ctypes.c_void_p()
-            _lib.check(lib.eld_unet_create(_lib.ctx(dev.index or 0), n, h, w, int(train), ws.data_ptr(), nbytes,
-                                           ctypes.byref(handle)), 'eld_unet_create')
+            _lib.check(lib.eld_unet_create_io(_lib.ctx(dev.index or 0), n, h, w, int(train), ws.data_ptr(), nbytes,
+                                              self.in_channels, self.out_channels, ctypes.byref(handle)), 'eld_unet_create_io')
             self._engines[key] = (handle, ws)
         return self._engines[key][0]
 
     def forward(self, x):
-        """x: cuda float32 NCHW [n,4,h,w] -> float32 NCHW [n,4,h,w]  (inference; no autograd graph)."""
-        assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.shape[1] == 4
+        """x: cuda float32 NCHW [n,4,h,w] -> float32 NCHW [n,4,h,w].  Under torch.enable_grad() in training mode the call
+        is an autograd node (`_EngineFunction`: shapes the training tiles accept, H % 128 == 0 and W % 256 == 0);
+        otherwise plain inference."""
+        assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.shape[1] == self.in_channels
         x = x.contiguous()
         n, _, h, w = x.shape
-        out = torch.empty_like(x)
+        if self.training and torch.is_grad_enabled() and h % 128 == 0 and w % 256 == 0:
+            return _EngineFunction.apply(self, x, *self.parameters())
+        out = torch.empty((n, self.out_channels, h, w), dtype=torch.float32, device=x.device)
         _lib.check(_lib.load().eld_unet_forward(self._engine(n, h, w, False), self._flat.data_ptr(), x.data_ptr(),
                                                out.data_ptr(), _st()), 'eld_unet_forward')
         return out
 
+    loss_kind = 'l1'      # 'l1' (nn.L1Loss, the reference default) or 'l2' (nn.MSELoss) - models/losses.py:29-36
+
     def train_step(self, x, target, loss_out=None):
-        """forward + L1 loss + backward in one launch sequence.  Fills self.flat_grads (== every
+        """forward + pixel loss + backward in one launch sequence.  Fills self.flat_grads (== every
         parameter's .grad) and returns (out, loss) with loss a 0-dim cuda tensor (no host sync)."""
-        assert x.is_cuda and x.dtype == torch.float32 and x.shape == target.shape
-        x, target = x.contiguous(), target.contiguous()
         n, _, h, w = x.shape
-        out = torch.empty_like(x)
+        assert x.is_cuda and x.dtype == torch.float32 and x.shape[1] == self.in_channels
+        assert target.shape == (n, self.out_channels, h, w) and target.dtype == torch.float32
+        x, target = x.contiguous(), target.contiguous()
+        out = torch.empty_like(target)
         loss = loss_out if loss_out is not None else torch.empty((), dtype=torch.float32, device=x.device)
+        _lib.check(_lib.load().eld_unet_set_loss(self._engine(n, h, w, True), 1 if self.loss_kind == 'l2' else 0), 'eld_unet_set_loss')
         _lib.check(_lib.load().eld_unet_train_step(self._engine(n, h, w, True), self._flat.data_ptr(), x.data_ptr(),
                                                    target.data_ptr(), out.data_ptr(), self._flat_grad.data_ptr(),
                                                    loss.data_ptr(), _st()), 'eld_unet_train_step')
@@ -151,10 +194,10 @@ class UNetSeeInDark(nn.Module):
         """[(offset, count)] of the flat gradient in backward-completion order (decoder, bottleneck, encoder)."""
         import ctypes as c
         arr = (c.c_size_t * 6)()
-        k = _lib.load().eld_unet_grad_buckets(arr, 6)
+        k = _lib.load().eld_unet_grad_buckets_io(self.in_channels, self.out_channels, arr, 6)
         return [(int(arr[2 * i]), int(arr[2 * i + 1])) for i in range(k)]
 
-    def train_step_ddp(self, x, target, loss_out=None, group=None):
+    def train_step_ddp(self, x, target, loss_out=None, group=None, timeline=None):
         """train_step + SUM all-reduce of the flat gradient, bucket by bucket on a side stream: bucket k's NCCL kernel
         waits only for the event the engine records when that bucket is final, so the decoder and bottleneck
         gradients travel while the encoder's backward still runs; the calling stream waits for all buckets at the end
@@ -168,14 +211,28 @@ class UNetSeeInDark(nn.Module):
             self._ddp_ready = eng.value
             self._ddp_stream = torch.cuda.Stream(device=x.device)
             self._ddp_buckets = self.grad_buckets()
+        ev = (lambda: torch.cuda.Event(enable_timing=True)) if timeline is not None else None
+        if ev:
+            timeline['step_start'] = ev(); timeline['step_start'].record()
         out, loss = self.train_step(x, target, loss_out=loss_out)
+        if ev:
+            timeline['backward_end'] = ev(); timeline['backward_end'].record()
+            timeline['buckets'] = []
         works = []
         with torch.cuda.stream(self._ddp_stream):
             for k, (off, cnt) in enumerate(self._ddp_buckets):
                 _lib.check(lib.eld_unet_wait_bucket(eng, k, ctypes.c_void_p(self._ddp_stream.cuda_stream)), 'eld_unet_wait_bucket')
+                if ev:
+                    e0 = ev(); e0.record(self._ddp_stream)
                 works.append(dist.all_reduce(self._flat_grad[off:off + cnt], group=group, async_op=True))
+                if ev:
+                    works[-1].wait()      # (timeline mode only) the side stream waits for this bucket so its end can be stamped
+                    e1 = ev(); e1.record(self._ddp_stream)
+                    timeline['buckets'].append((e0, e1, cnt * 4))
         for wk in works:
             wk.wait()                     # stream-side wait: the current stream waits for the NCCL kernels
+        if ev:
+            timeline['allreduce_joined'] = ev(); timeline['allreduce_joined'].record()
         return out, loss
 
     def _profile(self, eng, run, steps):

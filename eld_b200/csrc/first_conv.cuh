@@ -9,6 +9,14 @@
 //     fprop : the K-major A operand   D[128 px][32 co]  = A[px][k] * W[co][k]            3 MMAs (K = 48) per tile
 //     wgrad : the MN-major A operand  D[k][32 co]      += A[px][k] * dZ[px][co]          8 MMAs (K = 128 pixels) per tile
 // (the ones column makes row 36 of the wgrad accumulator the bias gradient).  No padded copy, no pack pass.
+// The raw frame reaches the builders through a TMA ring of halo patches (zero-filled outside the image = the conv
+// padding): the first version loaded its 36 taps straight from global memory and every tile paid a DRAM round trip
+// (164 us); with the patches 8 tiles ahead the builders only read shared memory.  The fp32 planes are described to TMA
+// as bf16 PAIRS with the same geometry the other tiles use (128-byte rows, SWIZZLE_128B) - a {20 x 10 x 4} fp32 box
+// with SWIZZLE_NONE encodes fine but the copy instruction is rejected as illegal on B200 (measured) - so a patch is
+// [4 planes][10 rows][32 floats] with the 16-byte chunks of row r XOR-ed by (r & 7); the builders undo that.  The box
+// starts at column x0 - 4, not x0 - 1: the innermost start of a TMA box must be 16-byte aligned in global memory (a
+// start at x0 - 1 was the actual cause of the illegal-instruction fault; compute-sanitizer pinned it to UTMALDG).
 #pragma once
 #include "umma.cuh"
 #include <cuda_bf16.h>
@@ -18,6 +26,7 @@ namespace eld {
 struct FirstConvParams {
     const float* x;             // f32 NCHW [n][4][H][W]
     int n_img, H, W;            // H % 8 == 0, W % 16 == 0
+    int cin;                    // 4 (packed raw) or 3 (sRGB): a missing 4th plane is out of the tensor map = zeros
     int tiles_x, tiles_y;
     const uint8_t* w_img;       // fprop: 4 KB smem image of W[co][k] (K-major, SW128), k >= 36 zero
     const float* bias;          // fprop
@@ -28,7 +37,14 @@ struct FirstConvParams {
     int stages;
 };
 
-constexpr int kFcThreads = 288;      // warps 0-3: im2col builders (one pixel each) | warp 4: MMA issuer | warps 5-8: epilogue
+// A builder group (4 warps, one pixel per thread) needs ~1000 cycles per tile (36 shared-memory loads, packing, six
+// swizzled stores and - the long pole - a fence.proxy.async before it may signal the tensor core), all of it latency:
+// one group alone bounded the kernels at 70 us.  kFcGroups groups take alternate tiles, so that many are in flight.
+constexpr int kFcGroups = 2;
+constexpr int kFcBuilderWarps = 4 * kFcGroups;
+constexpr int kFcThreads = 32 * (kFcBuilderWarps + 6);   // + MMA issuer, 4 epilogue warps (fprop), TMA producer
+constexpr int kFcRaw = 4 * 10 * 128;      // bytes of one raw patch: [4 planes][10 rows][32 floats], SW128-swizzled rows
+constexpr int kFcRawStages = 8;
 constexpr int kFcATile = 128 * 128;  // bytes
 constexpr int kFcAcc = 4;            // fprop TMEM accumulator ring (4 x 32 columns)
 
@@ -38,25 +54,19 @@ __device__ __forceinline__ uint32_t fc_pack(float a, float b)
     return *reinterpret_cast<const uint32_t*>(&h);
 }
 
-// one row of the im2col tile: pixel (y, x) of image `img`, written as six swizzled 16-byte chunks
-__device__ __forceinline__ void fc_build_row(const FirstConvParams& p, uint8_t* tile, int m, int img, int y, int x)
+// one row of the im2col tile: pixel (py, px) of the 8 x 16 tile whose halo patch is `raw`, written as six swizzled chunks
+__device__ __forceinline__ void fc_build_row(const float* raw, uint8_t* tile, int m, int py, int px)
 {
-    const size_t plane = (size_t)p.H * p.W;
-    const float* base = p.x + (size_t)img * 4 * plane;
     float v[9][4];
 #pragma unroll
-    for (int dy = 0; dy < 3; ++dy) {
-        const int yy = y + dy - 1;
-        const bool oky = yy >= 0 && yy < p.H;
+    for (int c = 0; c < 4; ++c)
 #pragma unroll
-        for (int dx = 0; dx < 3; ++dx) {
-            const int xx = x + dx - 1;
-            const bool ok = oky && xx >= 0 && xx < p.W;
-            const float* q = base + (size_t)(ok ? yy : 0) * p.W + (ok ? xx : 0);
+        for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
-            for (int c = 0; c < 4; ++c) v[dy * 3 + dx][c] = ok ? __ldg(q + c * plane) : 0.0f;
-        }
-    }
+            for (int dx = 0; dx < 3; ++dx) {
+                const int r = c * 10 + py + dy, j = px + dx + 3;      // row of the patch, float inside the row (the box starts at x0 - 4)
+                v[dy * 3 + dx][c] = raw[r * 32 + ((((j >> 2) ^ (r & 7)) << 2) | (j & 3))];
+            }
     uint8_t* row = tile + m * 128;
     const int sw = m & 7;
 #pragma unroll
@@ -83,30 +93,35 @@ __device__ __forceinline__ void fc_tile_coords(const FirstConvParams& p, int til
 // fprop: a1_1 = lrelu(conv1_1(x) + b)
 // ---------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kFcThreads, 1)
-first_conv_fprop_kernel(const FirstConvParams p)
+first_conv_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const FirstConvParams p)
 {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = ptx::smem_u32(smem_raw);
     uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
     uint8_t* w_s = smem;                                   // 4 KB weights
     uint8_t* a_s = smem + 4096;                            // ring of A tiles
-    uint64_t* full = reinterpret_cast<uint64_t*>(a_s + (size_t)p.stages * kFcATile);
+    uint8_t* r_s = a_s + (size_t)p.stages * kFcATile;      // ring of raw halo patches
+    uint64_t* full = reinterpret_cast<uint64_t*>(r_s + ((kFcRawStages * kFcRaw + 1023) & ~1023));
     uint64_t* empty = full + 8;
-    uint64_t* tmem_full = empty + 8;
+    uint64_t* raw_full = empty + 8;
+    uint64_t* raw_empty = raw_full + kFcRawStages;
+    uint64_t* tmem_full = raw_empty + kFcRawStages;
     uint64_t* tmem_empty = tmem_full + kFcAcc;
     uint64_t* w_full = tmem_empty + kFcAcc;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
-    float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);
+    float* s_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full) + 512);    // 16-byte aligned (float4 reads)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total_tiles = p.n_img * p.tiles_x * p.tiles_y;
     if (threadIdx.x == 0) {
+        ptx::prefetch_tmap(&tmX);
         for (int s = 0; s < p.stages; ++s) { ptx::mbar_init(&full[s], 128); ptx::mbar_init(&empty[s], 1); }
+        for (int s = 0; s < kFcRawStages; ++s) { ptx::mbar_init(&raw_full[s], 1); ptx::mbar_init(&raw_empty[s], 128); }
         for (int a = 0; a < kFcAcc; ++a) { ptx::mbar_init(&tmem_full[a], 1); ptx::mbar_init(&tmem_empty[a], 4); }
         ptx::mbar_init(w_full, 1);
         ptx::fence_barrier_init();
     }
-    if (warp == 5) ptx::tmem_alloc(tmem_slot, 128);
+    if (warp == kFcBuilderWarps + 1) ptx::tmem_alloc(tmem_slot, 128);
     if (threadIdx.x < 32) s_bias[threadIdx.x] = __ldg(p.bias + threadIdx.x);
     ptx::tc_fence_before();
     __syncthreads();
@@ -115,21 +130,21 @@ first_conv_fprop_kernel(const FirstConvParams p)
     ptx::grid_dep_wait();          // PDL: x (noise kernel) and the packed weights (pack kernel) are complete past this point
     ptx::grid_dep_launch();
 
-    if (warp < 4) {
-        // ===================== im2col builders =====================
-        const int m = threadIdx.x, py = m >> 4, px = m & 15;
-        int s = 0;
-        uint32_t ph = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            int img, y0, x0;
-            fc_tile_coords(p, tile, img, y0, x0);
+    const int my_tiles = (int)blockIdx.x < total_tiles ? (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    if (warp < kFcBuilderWarps) {
+        // ===================== im2col builders: group g builds this CTA's tiles g, g + kFcGroups, ... =====================
+        const int g = warp >> 2, m = threadIdx.x & 127, py = m >> 4, px = m & 15;
+        for (int i = g; i < my_tiles; i += kFcGroups) {
+            const int s = i % p.stages, rs = i % kFcRawStages;
+            const uint32_t ph = (uint32_t)(i / p.stages) & 1u, rph = (uint32_t)(i / kFcRawStages) & 1u;
+            ptx::mbar_wait(&raw_full[rs], rph);
             ptx::mbar_wait(&empty[s], ph ^ 1u);
-            fc_build_row(p, a_s + (size_t)s * kFcATile, m, img, y0 + py, x0 + px);
+            fc_build_row(reinterpret_cast<const float*>(r_s + (size_t)rs * kFcRaw), a_s + (size_t)s * kFcATile, m, py, px);
+            ptx::mbar_arrive(&raw_empty[rs]);              // this thread's patch reads are done (values are in the A tile)
             ptx::fence_proxy_async();                      // generic-proxy stores -> visible to the tensor core's async proxy
             ptx::mbar_arrive(&full[s]);
-            if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
-    } else if (warp == 4) {
+    } else if (warp == kFcBuilderWarps) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
             ptx::mbar_arrive_expect_tx(w_full, 4096u);
@@ -160,6 +175,20 @@ first_conv_fprop_kernel(const FirstConvParams p)
             __syncwarp();
             if (++s == p.stages) { s = 0; ph ^= 1u; }
             if (++acc == kFcAcc) { acc = 0; acc_ph ^= 1u; }
+        }
+    } else if (warp == kFcBuilderWarps + 5) {
+        // ===================== TMA producer of the raw halo patches =====================
+        if (lane == 0) {
+            int rs = 0;
+            uint32_t rph = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                int img, y0, x0;
+                fc_tile_coords(p, tile, img, y0, x0);
+                ptx::mbar_wait(&raw_empty[rs], rph ^ 1u);
+                ptx::mbar_arrive_expect_tx(&raw_full[rs], (uint32_t)kFcRaw);
+                ptx::tma_load_5d(r_s + (size_t)rs * kFcRaw, &tmX, &raw_full[rs], 2 * (x0 - 4), y0 - 1, 0, img, 0);
+                if (++rs == kFcRawStages) { rs = 0; rph ^= 1u; }
+            }
         }
     } else {
         // ===================== epilogue: bias + LeakyReLU -> bf16 NHWC =====================
@@ -195,7 +224,7 @@ first_conv_fprop_kernel(const FirstConvParams p)
     }
     ptx::tc_fence_before();
     __syncthreads();
-    if (warp == 5) ptx::tmem_dealloc(tmem_base, 128);
+    if (warp == kFcBuilderWarps + 1) ptx::tmem_dealloc(tmem_base, 128);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -204,7 +233,7 @@ first_conv_fprop_kernel(const FirstConvParams p)
 constexpr int kFcQTile = 128 * 64;   // dZ tile: 128 pixel rows x 32 channels bf16 (SW64)
 
 __global__ void __launch_bounds__(kFcThreads, 1)
-first_conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmQ, const FirstConvParams p)
+first_conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmQ, const FirstConvParams p)
 {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = ptx::smem_u32(smem_raw);
@@ -213,10 +242,13 @@ first_conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmQ, const FirstConv
     // of the last stage inside the allocation
     const int stage_bytes = kFcATile + kFcQTile;
     uint8_t* ring = smem;
-    uint64_t* full_a = reinterpret_cast<uint64_t*>(ring + (size_t)p.stages * stage_bytes + kFcATile);
+    uint8_t* r_s = ring + (size_t)p.stages * stage_bytes + kFcATile;
+    uint64_t* full_a = reinterpret_cast<uint64_t*>(r_s + ((kFcRawStages * kFcRaw + 1023) & ~1023));
     uint64_t* full_q = full_a + 8;
     uint64_t* empty = full_q + 8;
-    uint64_t* acc_full = empty + 8;
+    uint64_t* raw_full = empty + 8;
+    uint64_t* raw_empty = raw_full + kFcRawStages;
+    uint64_t* acc_full = raw_empty + kFcRawStages;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -224,11 +256,13 @@ first_conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmQ, const FirstConv
     const int my_tiles = (int)blockIdx.x < total_tiles ? (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     if (threadIdx.x == 0) {
         ptx::prefetch_tmap(&tmQ);
+        ptx::prefetch_tmap(&tmX);
         for (int s = 0; s < p.stages; ++s) { ptx::mbar_init(&full_a[s], 128); ptx::mbar_init(&full_q[s], 1); ptx::mbar_init(&empty[s], 1); }
+        for (int s = 0; s < kFcRawStages; ++s) { ptx::mbar_init(&raw_full[s], 1); ptx::mbar_init(&raw_empty[s], 128); }
         ptx::mbar_init(acc_full, 1);
         ptx::fence_barrier_init();
     }
-    if (warp == 5) ptx::tmem_alloc(tmem_slot, 32);
+    if (warp == kFcBuilderWarps + 1) ptx::tmem_alloc(tmem_slot, 32);
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
@@ -236,18 +270,17 @@ first_conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmQ, const FirstConv
     ptx::grid_dep_wait();
     ptx::grid_dep_launch();
 
-    if (warp < 4) {
-        const int m = threadIdx.x, py = m >> 4, px = m & 15;
-        int s = 0;
-        uint32_t ph = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            int img, y0, x0;
-            fc_tile_coords(p, tile, img, y0, x0);
+    if (warp < kFcBuilderWarps) {
+        const int g = warp >> 2, m = threadIdx.x & 127, py = m >> 4, px = m & 15;
+        for (int i = g; i < my_tiles; i += kFcGroups) {
+            const int s = i % p.stages, rs = i % kFcRawStages;
+            const uint32_t ph = (uint32_t)(i / p.stages) & 1u, rph = (uint32_t)(i / kFcRawStages) & 1u;
+            ptx::mbar_wait(&raw_full[rs], rph);
             ptx::mbar_wait(&empty[s], ph ^ 1u);
-            fc_build_row(p, ring + (size_t)s * stage_bytes, m, img, y0 + py, x0 + px);
+            fc_build_row(reinterpret_cast<const float*>(r_s + (size_t)rs * kFcRaw), ring + (size_t)s * stage_bytes, m, py, px);
+            ptx::mbar_arrive(&raw_empty[rs]);
             ptx::fence_proxy_async();
             ptx::mbar_arrive(&full_a[s]);
-            if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
         // ===================== epilogue (after the last tile): rows 0..35 = dW, row 36 = db =====================
         if (my_tiles > 0 && warp < 2) {
@@ -259,14 +292,16 @@ first_conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmQ, const FirstConv
             const int k = warp * 32 + lane;
             if (k < 36) {
                 const int tap = k >> 2, c = k & 3;
+                if (c < p.cin) {
 #pragma unroll
-                for (int co = 0; co < 32; ++co) atomicAdd(p.dw + (co * 4 + c) * 9 + tap, __uint_as_float(r[co]));
+                    for (int co = 0; co < 32; ++co) atomicAdd(p.dw + (co * p.cin + c) * 9 + tap, __uint_as_float(r[co]));
+                }
             } else if (k == 36) {
 #pragma unroll
                 for (int co = 0; co < 32; ++co) atomicAdd(p.db + co, __uint_as_float(r[co]));
             }
         }
-    } else if (warp == 4) {
+    } else if (warp == kFcBuilderWarps) {
         // ===================== MMA issuer: D[k][co] += A^T (MN-major) * dZ (MN-major), K = 128 pixels per tile ==========
         const uint32_t idesc = ptx::make_idesc_bf16(128, 32, 1, 1);
         // A: 64 k-slots = one 128-byte M block per pixel row, 8-row groups 1024 B apart; M = 128 reads a second block
@@ -295,14 +330,27 @@ first_conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmQ, const FirstConv
             __syncwarp();
             if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
-    } else if (warp == 5) {
-        // ===================== TMA producer of the dZ tiles =====================
+    } else if (warp == kFcBuilderWarps + 1) {
+        // ===================== TMA producer: raw halo patches (ring of 8) and dZ tiles (ring of `stages`) =====================
         if (lane == 0) {
-            int s = 0;
-            uint32_t ph = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            int s = 0, rs = 0;
+            uint32_t ph = 0, rph = 0;
+            // the raw ring is deeper than the A / dZ ring: run it `lead` tiles ahead so a blocked dZ slot never starves it
+            const int lead = kFcRawStages - 1;
+            int t_raw = blockIdx.x, n_raw = 0;
+            auto issue_raw = [&]() {
                 int img, y0, x0;
-                fc_tile_coords(p, tile, img, y0, x0);
+                fc_tile_coords(p, t_raw, img, y0, x0);
+                ptx::mbar_wait(&raw_empty[rs], rph ^ 1u);
+                ptx::mbar_arrive_expect_tx(&raw_full[rs], (uint32_t)kFcRaw);
+                ptx::tma_load_5d(r_s + (size_t)rs * kFcRaw, &tmX, &raw_full[rs], 2 * (x0 - 4), y0 - 1, 0, img, 0);
+                if (++rs == kFcRawStages) { rs = 0; rph ^= 1u; }
+                t_raw += gridDim.x; ++n_raw;
+            };
+            for (int i = 0; i < my_tiles; ++i) {
+                while (n_raw < my_tiles && n_raw <= i + lead - 1) issue_raw();
+                int img, y0, x0;
+                fc_tile_coords(p, (int)blockIdx.x + i * (int)gridDim.x, img, y0, x0);
                 ptx::mbar_wait(&empty[s], ph ^ 1u);
                 ptx::mbar_arrive_expect_tx(&full_q[s], (uint32_t)kFcQTile);
                 ptx::tma_load_5d(ring + (size_t)s * stage_bytes + kFcATile, &tmQ, &full_q[s], 0, x0, y0, img, 0);
@@ -312,7 +360,7 @@ first_conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmQ, const FirstConv
     }
     ptx::tc_fence_before();
     __syncthreads();
-    if (warp == 5) ptx::tmem_dealloc(tmem_base, 32);
+    if (warp == kFcBuilderWarps + 1) ptx::tmem_dealloc(tmem_base, 32);
 }
 
 }  // namespace eld

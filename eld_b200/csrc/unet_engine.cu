@@ -46,6 +46,7 @@ struct PackTable {
     int tile0[kNumLayers + 1];   // prefix sum of (cout/32 x cin/32) tiles per entry: one block per tile, whatever the layer
     int n;
     unsigned long long first_stage, first_dst, first_wf;
+    int first_cin;
 };
 
 // flattened tile id -> (entry, tile inside the entry)
@@ -92,7 +93,7 @@ pack_all_kernel(const float* __restrict__ params, __nv_bfloat16* __restrict__ pa
         const int b = (int)blockIdx.x - T.tile0[T.n], nb = (int)gridDim.x - T.tile0[T.n];
         for (int i = b * 256 + threadIdx.x; i < 32 * 64; i += nb * 256) {
             const int co = i >> 6, k = i & 63, tap = k >> 2, c = k & 3;
-            const float v = k < 36 ? w1[(co * 4 + c) * 9 + tap] : 0.0f;
+            const float v = (k < 36 && c < T.first_cin) ? w1[(co * T.first_cin + c) * 9 + tap] : 0.0f;
             packed[T.first_wf + (size_t)co * 64 + ((((k >> 3) ^ (co & 7)) << 3) | (k & 7))] = __float2bfloat16_rn(v);
         }
         return;
@@ -194,6 +195,8 @@ struct eld_unet {
     PackTable table;
     // gradient buckets in backward-completion order (data-parallel overlap): decoder, bottleneck, encoder
     cudaEvent_t bucket_ev[kGradBuckets] = { nullptr, nullptr, nullptr };
+    int cin0 = 4, cout_last = 4; // channels of the frame in / out: 4 = packed raw, 3 = sRGB (ELD_model.py:377-389)
+    int l2_loss = 0;             // 0: nn.L1Loss (the reference default, losses.py:31-32), 1: nn.MSELoss (losses.py:33-34)
     // optional per-launch profile (CUDA events on the launch stream)
     bool profile = false;
     struct Rec { char name[32]; double flops, bytes; cudaEvent_t e0, e1; };
@@ -254,6 +257,8 @@ static void init_layers(eld_unet* u)
     for (int i = 0; i < kNumLayers; ++i) {
         Layer& l = u->L[i];
         l.name = kLayers[i].name; l.type = kLayers[i].type; l.cin = kLayers[i].cin; l.cout = kLayers[i].cout;
+        if (i == 0) l.cin = u->cin0;
+        if (i == kNumLayers - 1) l.cout = u->cout_last;
         const size_t ksz = l.type == L_CONV3 ? 9 : (l.type == L_DECONV ? 4 : 1);
         l.w_off = off; off += (size_t)l.cin * l.cout * ksz;
         l.b_off = off; off += l.cout;
@@ -262,16 +267,28 @@ static void init_layers(eld_unet* u)
     u->n_params = off;
 }
 
-extern "C" size_t eld_unet_param_count(void)
+static bool io_ok(int cin, int cout) { return (cin == 3 || cin == 4) && (cout == 3 || cout == 4); }
+
+extern "C" size_t eld_unet_param_count_io(int cin, int cout)
 {
+    if (!io_ok(cin, cout)) return 0;
     eld_unet tmp{};
+    tmp.cin0 = cin; tmp.cout_last = cout;
     init_layers(&tmp);
     return tmp.n_params;
 }
+extern "C" size_t eld_unet_param_count(void) { return eld_unet_param_count_io(4, 4); }
 
+extern "C" int eld_unet_param_offset_io(const char* name, int is_bias, int cin, int cout, size_t* offset, size_t* count);
 extern "C" int eld_unet_param_offset(const char* name, int is_bias, size_t* offset, size_t* count)
 {
+    return eld_unet_param_offset_io(name, is_bias, 4, 4, offset, count);
+}
+extern "C" int eld_unet_param_offset_io(const char* name, int is_bias, int cin, int cout, size_t* offset, size_t* count)
+{
+    ELD_REQUIRE(io_ok(cin, cout), "eld_unet_param_offset: channels in / out must be 3 or 4");
     eld_unet tmp{};
+    tmp.cin0 = cin; tmp.cout_last = cout;
     init_layers(&tmp);
     for (int i = 0; i < kNumLayers; ++i) {
         if (strcmp(name, tmp.L[i].name) == 0) {
@@ -294,9 +311,17 @@ extern "C" size_t eld_unet_workspace_bytes(int n, int h, int w, int train)
     return layout(&tmp, nullptr, train != 0) + 1024;
 }
 
+extern "C" int eld_unet_create_io(eld_ctx* ctx, int n, int h, int w, int train, void* workspace, size_t bytes,
+                                  int cin, int cout, eld_unet** out);
 extern "C" int eld_unet_create(eld_ctx* ctx, int n, int h, int w, int train, void* workspace, size_t bytes, eld_unet** out)
 {
+    return eld_unet_create_io(ctx, n, h, w, train, workspace, bytes, 4, 4, out);
+}
+extern "C" int eld_unet_create_io(eld_ctx* ctx, int n, int h, int w, int train, void* workspace, size_t bytes,
+                                  int cin, int cout, eld_unet** out)
+{
     ELD_REQUIRE(ctx && out && workspace, "eld_unet_create: NULL argument");
+    ELD_REQUIRE(io_ok(cin, cout), "eld_unet_create: channels in / out must be 3 (sRGB) or 4 (packed raw); got %d -> %d", cin, cout);
     ELD_REQUIRE(n > 0 && h > 0 && w > 0, "eld_unet_create: bad shape");
     ELD_REQUIRE(h % 16 == 0 && w % 16 == 0, "eld_unet_create: H and W must be multiples of 16 (four 2x2 pools, like the reference); got %dx%d", h, w);
     ELD_CHECK_CUDA(cudaSetDevice(ctx->device));
@@ -304,7 +329,7 @@ extern "C" int eld_unet_create(eld_ctx* ctx, int n, int h, int w, int train, voi
                 "eld_unet_create: TRAINING needs H %% 128 == 0 and W %% 256 == 0 (whole 8x16 / 8x8 gradient tiles at 1/16 scale); got %dx%d", h, w);
     eld_unet* u = new (std::nothrow) eld_unet();
     ELD_REQUIRE(u, "eld_unet_create: out of host memory");
-    u->ctx = ctx; u->n = n; u->H = h; u->W = w;
+    u->ctx = ctx; u->n = n; u->H = h; u->W = w; u->cin0 = cin; u->cout_last = cout;
     init_layers(u);
     char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023);
     const size_t need = layout(u, base, train != 0) + (base - static_cast<char*>(workspace));
@@ -327,6 +352,7 @@ extern "C" int eld_unet_create(eld_ctx* ctx, int n, int h, int w, int train, voi
     u->table.first_stage = u->n_params;
     u->table.first_dst = u->L[I_C11].w_off;
     u->table.first_wf = u->L[I_C11].wf_off;
+    u->table.first_cin = u->cin0;
     // conv1_1's operand image: zero once (pack_all rewrites all of it every step anyway)
     ELD_CHECK_CUDA(cudaMemset(u->packed + u->L[I_C11].wf_off, 0, 32 * 9 * 32 * sizeof(__nv_bfloat16)));
     // opt in to large dynamic shared memory once (not inside a captured region)
@@ -343,9 +369,13 @@ extern "C" void eld_unet_destroy(eld_unet* u)
     delete u;
 }
 
-extern "C" int eld_unet_grad_buckets(size_t* offsets, int max_offsets)
+extern "C" int eld_unet_grad_buckets_io(int cin, int cout, size_t* offsets, int max_offsets);
+extern "C" int eld_unet_grad_buckets(size_t* offsets, int max_offsets) { return eld_unet_grad_buckets_io(4, 4, offsets, max_offsets); }
+extern "C" int eld_unet_grad_buckets_io(int cin, int cout, size_t* offsets, int max_offsets)
 {
+    ELD_REQUIRE(io_ok(cin, cout), "eld_unet_grad_buckets: channels in / out must be 3 or 4");
     eld_unet tmp{};
+    tmp.cin0 = cin; tmp.cout_last = cout;
     init_layers(&tmp);
     if (offsets) {
         ELD_REQUIRE(max_offsets >= 2 * kGradBuckets, "eld_unet_grad_buckets: need room for %d (offset, count) pairs", kGradBuckets);
@@ -547,8 +577,8 @@ struct Runner {
         {
             // conv1_1 (4 -> 32): software-im2col tile straight from the fp32 NCHW frame (first_conv.cuh)
             const double px = (double)U->n * U->H * U->W;
-            Scope sc(u, st, "conv1_1", "fprop", 2.0 * px * 32 * 36, px * (16 + 64));
-            TRY(launch_first_conv(ctx(), x, wf(I_C11), bias(I_C11), U->a1_1, 32, U->n, U->H, U->W, st));
+            Scope sc(u, st, "conv1_1", "fprop", 2.0 * px * 32 * 9 * U->cin0, px * (4 * U->cin0 + 64));
+            TRY(launch_first_conv(ctx(), x, U->cin0, wf(I_C11), bias(I_C11), U->a1_1, 32, U->n, U->H, U->W, st));
         }
         if (fuse_pool) { TRY(conv(I_C12, U->a1_1, 32, 0, U->cat9, 64, 32, 0, U->p1)); } else { TRY(conv(I_C12, U->a1_1, 32, 0, U->cat9, 64, 32, 0)); TRY(pool(U->cat9, 64, 32, U->p1, 32, 1)); }      // + pool (Unet.py:51)
         TRY(conv(I_C21, U->p1, 32, 0, U->a2_1, 64, 0, 1));
@@ -625,8 +655,8 @@ struct Runner {
         TRY(conv_dgrad(I_C12, U->dz1_2, U->dz1_1, 32, 0, U->a1_1, 32, 0, 0));
         {
             const double px = (double)U->n * U->H * U->W;
-            Scope sc(u, st, "conv1_1", "wgrad", 2.0 * px * 32 * 36, px * (16 + 64));
-            TRY(launch_first_conv_wgrad(ctx(), x, U->dz1_1, 32, g + U->L[I_C11].w_off, g + U->L[I_C11].b_off, U->n, U->H, U->W, st));
+            Scope sc(u, st, "conv1_1", "wgrad", 2.0 * px * 32 * 9 * U->cin0, px * (4 * U->cin0 + 64));
+            TRY(launch_first_conv_wgrad(ctx(), x, U->cin0, U->dz1_1, 32, g + U->L[I_C11].w_off, g + U->L[I_C11].b_off, U->n, U->H, U->W, st));
         }
         return finish_bucket(2, g);
     }
@@ -643,7 +673,7 @@ extern "C" int eld_unet_forward(eld_unet* u, const float* params, const float* x
     const double hpx = (double)u->n * u->H * u->W;
     Scope sc(u, r.st, "conv10_1", "fprop", 2.0 * hpx * 128, hpx * (64 + 16));
     return launch_head(u->ctx, u->a9_2, params + u->L[I_C10].w_off, params + u->L[I_C10].b_off, out, nullptr, nullptr,
-                       nullptr, nullptr, nullptr, u->n, (size_t)u->H * u->W, r.st);
+                       nullptr, nullptr, nullptr, u->n, (size_t)u->H * u->W, u->cout_last, 0, r.st);
 }
 
 extern "C" int eld_unet_train_step(eld_unet* u, const float* params, const float* x, const float* target,
@@ -661,7 +691,26 @@ extern "C" int eld_unet_train_step(eld_unet* u, const float* params, const float
         const double hpx = (double)u->n * u->H * u->W;
         Scope sc(u, r.st, "conv10_1", "fwd+loss+bwd", 6.0 * hpx * 128, hpx * (64 + 16 + 16 + 64));
         TRY(launch_head(u->ctx, u->a9_2, params + u->L[I_C10].w_off, params + u->L[I_C10].b_off, out, target, u->dz9_2,
-                        grads + u->L[I_C10].w_off, grads + u->L[I_C10].b_off, loss, u->n, (size_t)u->H * u->W, r.st));
+                        grads + u->L[I_C10].w_off, grads + u->L[I_C10].b_off, loss, u->n, (size_t)u->H * u->W, u->cout_last, u->l2_loss, r.st));
+    }
+    return r.backward(x, grads);
+}
+
+extern "C" int eld_unet_backward(eld_unet* u, const float* params, const float* x, const float* dout, float* grads, void* stream)
+{
+    ELD_REQUIRE(u && params && x && dout && grads, "eld_unet_backward: NULL argument");
+    ELD_REQUIRE(u->dz9_2 != nullptr, "eld_unet_backward: the eld_unet was created with train = 0");
+    ELD_CHECK_CUDA(cudaSetDevice(u->ctx->device));
+    Runner r{ u, params, static_cast<cudaStream_t>(stream) };
+    ELD_CHECK_CUDA(cudaMemsetAsync(grads, 0, u->n_params * sizeof(float), r.st));
+    ELD_CHECK_CUDA(cudaMemsetAsync(u->gtmp, 0, u->n_params * sizeof(float), r.st));
+    {
+        const double hpx = (double)u->n * u->H * u->W;
+        Scope sc(u, r.st, "conv10_1", "bwd", 4.0 * hpx * 128, hpx * (64 + 16 + 64));
+        // the head re-forms `out` into scratch (dz1_1 is not written before the very end of backward) and back-propagates dout
+        TRY(launch_head(u->ctx, u->a9_2, params + u->L[I_C10].w_off, params + u->L[I_C10].b_off,
+                        reinterpret_cast<float*>(u->dz1_1), dout, u->dz9_2,
+                        grads + u->L[I_C10].w_off, grads + u->L[I_C10].b_off, nullptr, u->n, (size_t)u->H * u->W, u->cout_last, 2, r.st));
     }
     return r.backward(x, grads);
 }
@@ -675,6 +724,13 @@ extern "C" int eld_adam_step(eld_ctx* ctx, float* params, const float* grads, fl
     ELD_CHECK_CUDA(cudaSetDevice(ctx->device));
     return launch_adam(ctx, params, grads, m, v, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale,
                        static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int eld_unet_set_loss(eld_unet* u, int kind)
+{
+    ELD_REQUIRE(u && (kind == 0 || kind == 1), "eld_unet_set_loss: kind must be 0 (L1) or 1 (MSE)");
+    u->l2_loss = kind;
+    return ELD_OK;
 }
 
 extern "C" int eld_clock_probe(eld_ctx* ctx, float* out_mhz_device, void* stream)

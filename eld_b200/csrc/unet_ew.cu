@@ -183,8 +183,9 @@ __global__ void __launch_bounds__(kHeadThreads, 4)
 head_kernel(const __nv_bfloat16* __restrict__ a, const float* __restrict__ w, const float* __restrict__ b,
             float* __restrict__ out, const float* __restrict__ target, __nv_bfloat16* __restrict__ dz,
             float* __restrict__ dw, float* __restrict__ db, float* __restrict__ loss,
-            int n_img, size_t plane, float inv_numel)
+            int n_img, size_t plane, float inv_numel, int l2_loss, int cout)
 {
+    // cout = 4 (packed raw) or 3 (sRGB out): lane q >= cout of a pixel's four carries zero weights and writes nothing.
     // The kernel is HBM-LATENCY bound (160 B per pixel, ~150 instructions): one register-prefetched pixel per thread
     // kept only ~13 KB per SM in flight (37 % of the bandwidth-delay product).  Every thread now streams ITS OWN 16 bytes
     // of the pixel and ITS OWN target value through a private slot of a kHeadStages-deep cp.async ring - 7 pixels ahead,
@@ -195,11 +196,13 @@ head_kernel(const __nv_bfloat16* __restrict__ a, const float* __restrict__ w, co
     __shared__ float bs[4];
     __shared__ float red[4 * 32 + 4 + 1];
     const int tid = threadIdx.x;
-    if (tid < 128) ws[tid >> 5][tid & 31] = w[tid];
-    if (tid < 4) bs[tid] = b[tid];
+    if (tid < 128) ws[tid >> 5][tid & 31] = (tid >> 5) < cout ? w[tid] : 0.f;
+    if (tid < 4) bs[tid] = tid < cout ? b[tid] : 0.f;
     if (TRAIN) for (int i = tid; i < 133; i += kHeadThreads) red[i] = 0.f;
     __syncthreads();
     const int q = tid & 3, lane = tid & 31;
+    const bool live = q < cout;                      // this lane owns a real output channel
+    const int qa = live ? q : 0;                     // (address clamp for the target / dOut slot of a dead lane)
     float w4[4][8];
 #pragma unroll
     for (int co = 0; co < 4; ++co)
@@ -229,7 +232,7 @@ head_kernel(const __nv_bfloat16* __restrict__ a, const float* __restrict__ w, co
             const size_t p = ok ? load_w.pix() : total - 1;
             const size_t n = ok ? load_w.n : (total - 1) / plane, l = ok ? load_w.l : (total - 1) % plane;
             cp_async16(&ring_a[it % kHeadStages][tid], reinterpret_cast<const uint4*>(a + p * 32) + q);
-            if (TRAIN) cp_async4(&ring_t[it % kHeadStages][tid], target + (n * 4 + q) * plane + l);
+            if (TRAIN) cp_async4(&ring_t[it % kHeadStages][tid], target + (n * cout + qa) * plane + l);
             if (ok) load_w.next();
             load_p += stride;
         }
@@ -241,7 +244,7 @@ head_kernel(const __nv_bfloat16* __restrict__ a, const float* __restrict__ w, co
         cp_async_wait<kHeadStages - 1>();
         const bool valid = use_p < total;
         const size_t p = valid ? use_w.pix() : total - 1;
-        const size_t oidx = valid ? (use_w.n * 4 + q) * plane + use_w.l : 0;
+        const size_t oidx = valid ? (use_w.n * cout + qa) * plane + use_w.l : 0;
         const uint4 v = ring_a[it % kHeadStages][tid];
         const float tg = TRAIN ? ring_t[it % kHeadStages][tid] : 0.f;
         if (valid) use_w.next();
@@ -261,11 +264,14 @@ head_kernel(const __nv_bfloat16* __restrict__ a, const float* __restrict__ w, co
             o[co] = acc;
         }
         const float mine = (q == 0 ? o[0] : q == 1 ? o[1] : q == 2 ? o[2] : o[3]) + bq;
-        if (valid) __stcs(out + oidx, mine);
+        if (valid && live) __stcs(out + oidx, mine);
         if (TRAIN) {
-            const float e = valid ? mine - tg : 0.f;
-            ploss += fabsf(e);
-            const float d = (e > 0.f ? inv_numel : (e < 0.f ? -inv_numel : 0.f));
+            const float e = (valid && live) ? mine - tg : 0.f;
+            // nn.L1Loss (losses.py:31-32): |e|, sign(e)/numel ; nn.MSELoss (losses.py:33-34): e^2, 2e/numel ;
+            // mode 2: the caller's own d(loss)/d(out) arrives in the `target` slot (autograd seam, ELD_model.py:411-420)
+            ploss += l2_loss == 1 ? e * e : fabsf(e);
+            const float d = l2_loss == 2 ? ((valid && live) ? tg : 0.f)
+                          : l2_loss == 1 ? 2.0f * e * inv_numel : (e > 0.f ? inv_numel : (e < 0.f ? -inv_numel : 0.f));
             pdb += d;
             // the pixel's four dOut values (one per lane of the 4-lane group)
             const int base = lane & ~3;
@@ -313,9 +319,9 @@ head_kernel(const __nv_bfloat16* __restrict__ a, const float* __restrict__ w, co
         if (lane == 0) atomicAdd(&red[132], ls);
         __syncthreads();
         for (int i = tid; i < 133; i += kHeadThreads) {
-            if (i < 128) atomicAdd(dw + i, red[i]);
-            else if (i < 132) atomicAdd(db + (i - 128), red[i]);
-            else atomicAdd(loss, red[132] * inv_numel);
+            if (i < 128) { if ((i >> 5) < cout) atomicAdd(dw + i, red[i]); }
+            else if (i < 132) { if (i - 128 < cout) atomicAdd(db + (i - 128), red[i]); }
+            else if (loss) atomicAdd(loss, red[132] * inv_numel);
         }
     }
 }
@@ -383,16 +389,16 @@ int launch_colsum(eld_ctx* ctx, const void* g, int pitch, int c0, int C, size_t 
 }
 
 int launch_head(eld_ctx* ctx, const void* a, const float* w, const float* b, float* out, const float* target, void* dz,
-                float* dw, float* db, float* loss, int n, size_t plane, cudaStream_t st)
+                float* dw, float* db, float* loss, int n, size_t plane, int cout, int l2_loss, cudaStream_t st)
 {
     const size_t total = (size_t)n * plane;
-    const float inv = 1.0f / (float)(total * 4);
+    const float inv = 1.0f / (float)(total * cout);
     if (target) {
         head_kernel<true><<<grid_for(total, 32 * 16, 4 * ctx->num_sms), kHeadThreads, 0, st>>>(
-            static_cast<const __nv_bfloat16*>(a), w, b, out, target, static_cast<__nv_bfloat16*>(dz), dw, db, loss, n, plane, inv);
+            static_cast<const __nv_bfloat16*>(a), w, b, out, target, static_cast<__nv_bfloat16*>(dz), dw, db, loss, n, plane, inv, l2_loss, cout);
     } else {
         head_kernel<false><<<grid_for(total, 32, 8 * ctx->num_sms), kHeadThreads, 0, st>>>(
-            static_cast<const __nv_bfloat16*>(a), w, b, out, nullptr, nullptr, nullptr, nullptr, nullptr, n, plane, inv);
+            static_cast<const __nv_bfloat16*>(a), w, b, out, nullptr, nullptr, nullptr, nullptr, nullptr, n, plane, inv, 0, cout);
     }
     ELD_CHECK_CUDA(cudaGetLastError());
     count_launch(ctx);

@@ -13,13 +13,14 @@
 namespace eld {
 
 static int encode(eld_ctx* ctx, CUtensorMap* map, const void* ptr, int rank, const cuuint64_t* dims,
-                  const cuuint64_t* strides_bytes, const cuuint32_t* box, int inner_bytes)
+                  const cuuint64_t* strides_bytes, const cuuint32_t* box, int inner_bytes,
+                  CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16)
 {
     cuuint32_t estr[5] = { 1, 1, 1, 1, 1 };
     CUtensorMapSwizzle sw = inner_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                           : inner_bytes == 64  ? CU_TENSOR_MAP_SWIZZLE_64B
                           : inner_bytes == 32  ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
-    CUresult r = ctx->encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr),
+    CUresult r = ctx->encode_tiled(map, dtype, (cuuint32_t)rank, const_cast<void*>(ptr),
                                    dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -173,31 +174,45 @@ int launch_conv_gemm(eld_ctx* ctx, const GemmOp& op, cudaStream_t st)
     return ELD_OK;
 }
 
+// the fp32 NCHW frame [n][4][H][W] as (x in HALF floats, y, plane, image) of bf16: box = 64 halves (32 floats, 128 B,
+// SWIZZLE_128B - the geometry every other tile uses) x 10 rows x 4 planes around an 8 x 16 pixel tile; out-of-image
+// elements are zero-filled = the conv padding (see first_conv.cuh for why not a plain fp32 box)
+static int encode_frame(eld_ctx* ctx, CUtensorMap* map, const float* x, int cin, int n, int H, int W)
+{
+    ELD_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "first conv tile: the input frame must be 16-byte aligned");
+    cuuint64_t dims[5] = { (cuuint64_t)W * 2, (cuuint64_t)H, (cuuint64_t)cin, (cuuint64_t)n, 1 };
+    cuuint64_t str[4] = { (cuuint64_t)W * 4, (cuuint64_t)H * W * 4, (cuuint64_t)cin * H * W * 4, (cuuint64_t)n * cin * H * W * 4 };
+    cuuint32_t box[5] = { 64, 10, 4, 1, 1 };
+    return encode(ctx, map, x, 5, dims, str, box, 128);
+}
+
 // conv1_1 (4 -> 32): software-im2col tcgen05 tiles on the fp32 NCHW frame (first_conv.cuh)
-int launch_first_conv(eld_ctx* ctx, const float* x, const void* w_img, const float* bias, void* out, int out_pitch,
+int launch_first_conv(eld_ctx* ctx, const float* x, int cin, const void* w_img, const float* bias, void* out, int out_pitch,
                       int n, int H, int W, cudaStream_t st)
 {
     ELD_REQUIRE(H % 8 == 0 && W % 16 == 0, "first conv tile: H=%d must be a multiple of 8 and W=%d of 16", H, W);
     FirstConvParams p{};
-    p.x = x; p.n_img = n; p.H = H; p.W = W; p.tiles_x = W / 16; p.tiles_y = H / 8;
+    p.x = x; p.n_img = n; p.H = H; p.W = W; p.tiles_x = W / 16; p.tiles_y = H / 8; p.cin = cin;
     p.w_img = static_cast<const uint8_t*>(w_img); p.bias = bias;
     p.out = static_cast<__nv_bfloat16*>(out); p.out_pitch = out_pitch;
     p.stages = 8;
     const int total = n * p.tiles_x * p.tiles_y;
     const int grid = total < ctx->num_sms ? total : ctx->num_sms;
-    const size_t smem = 1024 + 4096 + (size_t)p.stages * kFcATile + 1024;
-    ELD_CHECK_CUDA(launch_pdl(first_conv_fprop_kernel, grid, kFcThreads, smem, st, p));
+    CUtensorMap tmX;
+    { int rc = encode_frame(ctx, &tmX, x, cin, n, H, W); if (rc) return rc; }
+    const size_t smem = 1024 + 4096 + (size_t)p.stages * kFcATile + ((kFcRawStages * kFcRaw + 1023) & ~1023) + 1024;
+    ELD_CHECK_CUDA(launch_pdl(first_conv_fprop_kernel, grid, kFcThreads, smem, st, tmX, p));
     ELD_CHECK_CUDA(cudaGetLastError());
     count_launch(ctx);
     return ELD_OK;
 }
 
-int launch_first_conv_wgrad(eld_ctx* ctx, const float* x, const void* dz, int dz_pitch, float* dw, float* db,
+int launch_first_conv_wgrad(eld_ctx* ctx, const float* x, int cin, const void* dz, int dz_pitch, float* dw, float* db,
                             int n, int H, int W, cudaStream_t st)
 {
     ELD_REQUIRE(H % 8 == 0 && W % 16 == 0, "first conv wgrad tile: H=%d must be a multiple of 8 and W=%d of 16", H, W);
     FirstConvParams p{};
-    p.x = x; p.n_img = n; p.H = H; p.W = W; p.tiles_x = W / 16; p.tiles_y = H / 8;
+    p.x = x; p.n_img = n; p.H = H; p.W = W; p.tiles_x = W / 16; p.tiles_y = H / 8; p.cin = cin;
     p.dw = dw; p.db = db;
     p.stages = 6;
     CUtensorMap tmQ;
@@ -209,8 +224,10 @@ int launch_first_conv_wgrad(eld_ctx* ctx, const float* x, const void* dz, int dz
     { int rc = encode(ctx, &tmQ, dz, 5, dims, str, box, 64); if (rc) return rc; }
     const int total = n * p.tiles_x * p.tiles_y;
     const int grid = total < ctx->num_sms ? total : ctx->num_sms;
-    const size_t smem = 1024 + (size_t)p.stages * (kFcATile + kFcQTile) + kFcATile + 1024;
-    ELD_CHECK_CUDA(launch_pdl(first_conv_wgrad_kernel, grid, kFcThreads, smem, st, tmQ, p));
+    CUtensorMap tmX;
+    { int rc = encode_frame(ctx, &tmX, x, cin, n, H, W); if (rc) return rc; }
+    const size_t smem = 1024 + (size_t)p.stages * (kFcATile + kFcQTile) + kFcATile + ((kFcRawStages * kFcRaw + 1023) & ~1023) + 1024;
+    ELD_CHECK_CUDA(launch_pdl(first_conv_wgrad_kernel, grid, kFcThreads, smem, st, tmX, tmQ, p));
     ELD_CHECK_CUDA(cudaGetLastError());
     count_launch(ctx);
     return ELD_OK;

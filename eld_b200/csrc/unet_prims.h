@@ -62,9 +62,9 @@ struct WgradOp {
 int init_gemm_kernels(eld_ctx* ctx);   // opt in to large dynamic smem (call once, outside graph capture)
 int launch_wgrad(eld_ctx* ctx, const WgradOp& op, cudaStream_t st);
 int launch_conv_gemm(eld_ctx* ctx, const GemmOp& op, cudaStream_t st);
-int launch_first_conv(eld_ctx* ctx, const float* x, const void* w_img, const float* bias, void* out, int out_pitch,
+int launch_first_conv(eld_ctx* ctx, const float* x, int cin, const void* w_img, const float* bias, void* out, int out_pitch,
                       int n, int H, int W, cudaStream_t st);
-int launch_first_conv_wgrad(eld_ctx* ctx, const float* x, const void* dz, int dz_pitch, float* dw, float* db,
+int launch_first_conv_wgrad(eld_ctx* ctx, const float* x, int cin, const void* dz, int dz_pitch, float* dw, float* db,
                             int n, int H, int W, cudaStream_t st);
 int launch_pack_weights(eld_ctx* ctx, const float* w, void* out, int cout, int cin, int kind, cudaStream_t st);
 

@@ -50,11 +50,20 @@ class Engine(object):
         avg_meters = AverageMeters()
         opt, model = self.opt, self.model
         epoch_start_time = time.time()
-        for i, data in enumerate(train_loader):
+        # engine.py:40-55's loop; with opt.prefetch_noise it runs ONE batch of look-ahead: after step i has been queued, the
+        # synthesis of step i+1's noisy input starts on a side stream (ELDModel.prefetch_input).  Off by default: on B200
+        # the overlapped noise CTAs slow the tiles' epilogue warps by as much as they save (profiles/r02_overlap_ab.txt).
+        it = iter(train_loader)
+        data = next(it, None)
+        while data is not None:
             model.set_input(data, mode='train')
+            nxt = next(it, None)
             model.optimize_parameters(**kwargs)
+            if nxt is not None and getattr(opt, 'prefetch_noise', False) and hasattr(model, 'prefetch_input'):
+                model.prefetch_input(nxt)
             avg_meters.update(model.get_current_errors())
             self.iterations += 1
+            data = nxt
         self.epoch += 1
         if not opt.no_log:
             if self.epoch % opt.save_epoch_freq == 0:

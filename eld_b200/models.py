@@ -27,7 +27,7 @@ def default_opt(**kw):
              resume_epoch=None, seed=2018, chop=False, no_log=True, no_verbose=True, netG='unet', channels=4,
              stage_in='raw', stage_out='raw', model_path=None, include=4, crf=False, batchSize=1, lr=1e-4,
              beta1=0.9, wd=0.0, loss='l1', noise='g', isTrain=True, save_epoch_freq=100, noise_on_gpu=False,
-             augment_on_gpu=False, defer_loss_sync=False)
+             augment_on_gpu=False, defer_loss_sync=False, prefetch_noise=False)
     o.update(kw)
     return SimpleNamespace(**o)
 
@@ -89,6 +89,9 @@ class ELDModel(BaseModel):
         self.noise_maker = None
         self.loss_pixel = None
         self._frames_seen = 0
+        self.CRF = None
+        self._prefetched = None
+        self._noise_stream = None
 
     def _eval(self):
         self.netG.eval()
@@ -100,15 +103,22 @@ class ELDModel(BaseModel):
         BaseModel.initialize(self, opt)
         if self.device is None:
             raise RuntimeError('ELDModel (eld_b200) needs a CUDA device: no CPU fallback')
-        if opt.stage_in != 'raw' or opt.stage_out != 'raw':
-            raise NotImplementedError('only the raw->raw path is in scope (SURVEY 8f.4 lists the sRGB branch as next)')
         if len(opt.gpu_ids) > 0:
             self.device = torch.device('cuda', opt.gpu_ids[0])
-        self.netG = arch.__dict__[opt.netG](opt.channels, opt.channels).to(self.device)     # ELD_model.py:391
+        if getattr(opt, 'crf', False) and getattr(self, 'CRF', None) is None:
+            from . import process
+            self.CRF = process.load_CRF()                                                   # ELD_model.py:374-375
+        chan = {'raw': opt.channels, 'srgb': 3}                                             # ELD_model.py:377-389
+        if opt.stage_in not in chan:
+            raise NotImplementedError('Invalid Input Stage: {}'.format(opt.stage_in))
+        if opt.stage_out not in chan:
+            raise NotImplementedError('Invalid Output Stage: {}'.format(opt.stage_out))
+        self.netG = arch.__dict__[opt.netG](chan[opt.stage_in], chan[opt.stage_out]).to(self.device)     # ELD_model.py:391
         self.noise_maker = noise_maker
         if self.isTrain:
-            if opt.loss != 'l1':
-                raise NotImplementedError("the fused head implements the default L1 pixel loss (losses.py:31-32)")
+            if opt.loss not in ('l1', 'l2'):
+                raise NotImplementedError("pixel losses of models/losses.py:29-36: 'l1' (nn.L1Loss) or 'l2' (nn.MSELoss)")
+            self.netG.loss_kind = opt.loss
             self.optimizer_G = arch.FusedAdam(self.netG, lr=opt.lr, betas=(opt.beta1, 0.999), weight_decay=opt.wd)
             self._init_optimizer([self.optimizer_G])
         if opt.resume:
@@ -138,37 +148,70 @@ class ELDModel(BaseModel):
             input, data_name = data['input'], data['fn']
         else:
             raise NotImplementedError('Mode [%s] is not implemented' % mode)
-        if target is not None:
-            target = target.to(device=self.device, dtype=torch.float32, non_blocking=True)
         synth = mode == 'train' and (input is None or getattr(self.opt, 'noise_on_gpu', False))
+        pre = self._prefetched if synth else None
+        if target is not None and not (pre is not None and pre[0] is data):
+            target = target.to(device=self.device, dtype=torch.float32, non_blocking=True)
         if synth:
-            # on-the-fly synthesis on the training stream (SynDataset semantics, sid_dataset.py:259-280,
-            # incl. the [0,1] clip): global frame ids keep the stream invariant to the number of GPUs.
-            assert self.noise_maker is not None, 'noise_on_gpu needs a noise_maker (eld_b200.noise.NoiseModel)'
-            # Frame ids count GLOBAL frames: step s of a W-GPU job owns ids [F, F + sum of the ranks' batch sizes), rank r
-            # the r-th slice.  Batches are equal-sized except possibly the last one of an epoch (DataLoader without
-            # drop_last), so F advances by the batch actually seen times W - ids never repeat, and the running count
-            # is part of the checkpoint (a resumed run does not replay the Philox streams from frame 0).
-            n = target.shape[0]
-            fid0 = self._frames_seen + self.rank * n
-            self._frames_seen += self.world * n
-            # per-frame (K, g_scale, ratio, ...) and flip flags are drawn from a generator keyed by (seed, global frame
-            # id): W ranks draw W*n DIFFERENT tuples (not W copies of the same n), and frame f gets the same tuple at
-            # any GPU count.  The draw itself is noise.py:201-225's call order on that per-frame RandomState.
-            params = self.noise_maker.frame_params(fid0, n)
-            if getattr(self.opt, 'augment_on_gpu', False):
-                # ELDTrainDataset's flips / transpose / clip (sid_dataset.py:340-356) fused into the noise kernel:
-                # both the synthesised input and the target come back augmented, one pass over the frames
-                input, target = self.noise_maker.batch_gpu_augmented(target, aug=self.noise_maker.frame_augment(fid0, n),
-                                                                     params=params, frame_id0=fid0, clip=True)
+            self._prefetched = None
+            if pre is not None and pre[0] is data:
+                # made ahead by prefetch_input() on the side stream while the previous step's network ran
+                _, input, target, ev = pre
+                cur = torch.cuda.current_stream()
+                cur.wait_event(ev)
+                input.record_stream(cur)
+                target.record_stream(cur)
             else:
-                input = self.noise_maker.batch_gpu(target, params=params, frame_id0=fid0, clip=True)
+                input, target = self._synthesize(target)
+            if self.opt.stage_in == 'srgb' and input.shape[1] == 4:
+                # ISPDataset.__getitem__ (sid_dataset.py:306-312) on the stream: noise -> clip -> raw2rgb_v2(wb, ccm) -> clip
+                from . import process
+                assert 'wb' in data and 'ccm' in data, "--stage_in srgb needs the frames' (wb, ccm) meta in the batch"
+                input = process.isp_dataset_item(input, data['wb'], data['ccm'], CRF=getattr(self, 'CRF', None))
         else:
             input = input.to(device=self.device, dtype=torch.float32, non_blocking=True)
         self.input, self.target, self.data_name = input, target, data_name
         self.rawpath = data['rawpath'][0] if 'rawpath' in data else None
         self.cfa = data['cfa'][0] if 'cfa' in data else 'bayer'
         self.aligned = False if 'unaligned' in data else True
+
+    def _synthesize(self, target):
+        """On-the-fly synthesis (SynDataset semantics, sid_dataset.py:259-280, incl. the [0,1] clip) on the CURRENT stream.
+        Frame ids count GLOBAL frames: step s of a W-GPU job owns ids [F, F + sum of the ranks' batch sizes), rank r the
+        r-th slice.  Batches are equal-sized except possibly the last one of an epoch (DataLoader without drop_last), so F
+        advances by the batch actually seen times W - ids never repeat, and the running count is part of the checkpoint
+        (a resumed run does not replay the Philox streams from frame 0)."""
+        assert self.noise_maker is not None, 'noise_on_gpu needs a noise_maker (eld_b200.noise.NoiseModel)'
+        n = target.shape[0]
+        fid0 = self._frames_seen + self.rank * n
+        self._frames_seen += self.world * n
+        # per-frame (K, g_scale, ratio, ...) and flip flags are drawn from a generator keyed by (seed, global frame id):
+        # W ranks draw W*n DIFFERENT tuples (not W copies of the same n), and frame f gets the same tuple at any GPU
+        # count.  The draw itself is noise.py:201-225's call order on that per-frame RandomState.
+        params = self.noise_maker.frame_params(fid0, n)
+        if getattr(self.opt, 'augment_on_gpu', False):
+            # ELDTrainDataset's flips / transpose / clip (sid_dataset.py:340-356) fused into the noise kernel:
+            # both the synthesised input and the target come back augmented, one pass over the frames
+            return self.noise_maker.batch_gpu_augmented(target, aug=self.noise_maker.frame_augment(fid0, n),
+                                                        params=params, frame_id0=fid0, clip=True)
+        return self.noise_maker.batch_gpu(target, params=params, frame_id0=fid0, clip=True), target
+
+    def prefetch_input(self, data):
+        """Start synthesising the NEXT step's noisy input on a side stream (Engine.train calls this right after it has
+        queued the current step): the exact-Poisson noise kernel is issue-bound, the U-Net tiles are tensor / memory
+        bound, so the two overlap almost for free.  set_input(data) with the SAME dict then only waits for an event.
+        A no-op unless the model synthesises its input (opt.noise_on_gpu or a batch without 'input')."""
+        if not (self.isTrain and (data.get('input') is None or getattr(self.opt, 'noise_on_gpu', False))):
+            return
+        if self._noise_stream is None:
+            self._noise_stream = torch.cuda.Stream(device=self.device)
+        self._noise_stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self._noise_stream):
+            target = data['target'].to(device=self.device, dtype=torch.float32, non_blocking=True)
+            input, target = self._synthesize(target)
+            ev = torch.cuda.Event()
+            ev.record(self._noise_stream)
+        self._prefetched = (data, input, target, ev)
 
     # ---- forward / optimise (ELD_model.py:411-475) -------------------------------------------------------
     def forward(self):
@@ -218,7 +261,12 @@ class ELDModel(BaseModel):
         self.optimizer_G.step(grad_scale=1.0 / self.world)
 
     def backward_G(self):
-        raise RuntimeError('backward is fused into optimize_parameters() (one C-ABI call)')
+        """ELD_model.py:411-420 as written in the reference: loss on self.output, .backward() through the netG autograd
+        node.  optimize_parameters() does not use it (the fused step is one C-ABI call) - it exists so that code written
+        against the reference's forward() / backward_G() pair keeps working, with any torch loss."""
+        loss_fn = torch.nn.functional.l1_loss if self.opt.loss == 'l1' else torch.nn.functional.mse_loss
+        self.loss_G = self.loss_pixel = loss_fn(self.output, self.target)
+        self.loss_G.backward()
 
     def get_current_errors(self):
         ret_errors = OrderedDict()
@@ -226,38 +274,48 @@ class ELDModel(BaseModel):
             ret_errors['Pixel'] = self.loss_pixel if getattr(self.opt, 'defer_loss_sync', False) else self.loss_pixel.item()
         return ret_errors
 
-    @staticmethod
-    def illuminance_correct(predict, source):
-        """IlluminanceCorrect.correct (ELD_model.py:156-169) on the GPU, per frame: scalar gain
-        <p, s> / <p, p> over the pixels where source != 1, applied to clamp(predict, 0, 1)."""
-        p = predict.clamp(0, 1)
-        m = (source != 1).to(p.dtype)
-        num = (p * source * m).flatten(1).double().sum(1)
-        den = (p * p * m).flatten(1).double().sum(1)
-        return (num / den).to(p.dtype).view(-1, 1, 1, 1) * p
+    def eval_metrics(self, predict, target, correct=False):
+        """IlluminanceCorrect (ELD_model.py:138-169) + tensor2im (:23-38) + PSNR (util/index.py:76-79) per frame, on the
+        device (csrc/eval.cu, three launches, no host synchronisation).  Returns (output, psnr[n], gain[n]) - output is
+        the corrected prediction when correct=True, else `predict` itself."""
+        import ctypes
+        from . import _lib
+        predict, target = predict.contiguous(), target.contiguous()
+        n = predict.shape[0]
+        if target.shape[0] == 1 and n != 1:
+            target = target.expand_as(predict).contiguous()     # IlluminanceCorrect.forward's broadcast case (:147-149)
+        out = torch.empty_like(predict) if correct else predict
+        scratch = torch.empty(n * 4, dtype=torch.float64, device=predict.device)
+        psnr = torch.empty(n, dtype=torch.float32, device=predict.device)
+        gain = torch.empty(n, dtype=torch.float32, device=predict.device)
+        _lib.check(_lib.load().eld_eval_correct_psnr(
+            _lib.ctx(predict.device.index or 0), predict.data_ptr(), target.data_ptr(), out.data_ptr() if correct else None, n,
+            predict[0].numel(), int(bool(correct)), scratch.data_ptr(), psnr.data_ptr(), gain.data_ptr(),
+            ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), 'eld_eval_correct_psnr')
+        return out, psnr, gain
+
+    def illuminance_correct(self, predict, source):
+        return self.eval_metrics(predict, source, correct=True)[0]
 
     def eval(self, data, savedir=None, suffix=None, correct=False, crop=True, frame_id=None, **kwargs):
-        """ELDModelBase.eval (ELD_model.py:203-307) without the rawpy / PIL visualisation: centre 512x512 crop
-        (util.crop_center), forward, optional illuminance correction, PSNR exactly as tensor2im +
-        skimage.compare_psnr(data_range=255) compute it (clip(255 x, 0, 255), no rounding; util/index.py:79).
-        Everything stays on the device; one host read of the final scalar."""
+        """ELDModelBase.eval (ELD_model.py:203-243) without the rawpy / PIL visualisation: centre 512x512 crop
+        (util.crop_center), forward (or forward_chop), optional illuminance correction, PSNR of the output and of the
+        input against the target exactly as tensor2im + quality_assess compute them - all on the device (csrc/eval.cu);
+        one host read of the final scalars.  Only the 1st frame is assessed, like the reference (tensor2im takes [0])."""
         self._eval()
         self.set_input(data, 'eval')
         with torch.no_grad():
             x, t = self.input, self.target
             if crop and x.shape[2] >= 512 and x.shape[3] >= 512:
                 h, w = x.shape[2:]
-                y0, x0 = h // 2 - 256, w // 2 - 256
+                y0, x0 = h // 2 - 256, w // 2 - 256                     # util.crop_center
                 x, t = x[:, :, y0:y0 + 512, x0:x0 + 512].contiguous(), t[:, :, y0:y0 + 512, x0:x0 + 512].contiguous()
             out = self.forward_chop(x) if self.opt.chop else self._padded_forward(x)
-            if correct:
-                out = self.illuminance_correct(out, t)
+            out, psnr, _ = self.eval_metrics(out.contiguous(), t, correct=correct)
+            _, psnr_in, _ = self.eval_metrics(x, t, correct=False)
             self.output = out
-            a = (out[0:1] * 255.0).clamp(0, 255).double()          # only the 1st frame is assessed, like the reference
-            b = (t[0:1] * 255.0).clamp(0, 255).double()
-            mse = ((a - b) ** 2).mean()
-            psnr = 10.0 * torch.log10(255.0 ** 2 / mse.clamp_min(1e-30))
-        return {'PSNR': float(psnr.item())}
+            both = torch.stack([psnr[0], psnr_in[0]]).cpu()
+        return {'PSNR': float(both[0]), 'PSNR_input': float(both[1])}
 
     def test(self, data, savedir=None, **kwargs):
         self._eval()

@@ -130,6 +130,17 @@ int eld_isp_process(eld_ctx* ctx, const float* packed, float* rgb, int n, int h,
                     const float* wb, const float* ccm, float gamma,
                     const float* crf_E, const float* crf_f, int crf_len, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Metric side of ELDModelBase.eval (models/ELD_model.py:203-243), per frame f of a batch of `n` frames with
+ * `per_frame` = C*H*W elements each (f32, any layout, pred and target alike):
+ *   correct != 0: IlluminanceCorrect.correct (:156-169): gain = <p,s>/<p,p> over the elements where s != 1,
+ *                 p = clamp(pred,0,1); corrected = gain * p (written to `out` if out != NULL, may alias pred)
+ *   psnr[f] = 10 log10(255^2 / mean((clip(255 x,0,255) - clip(255 target,0,255))^2)), x = corrected (or pred):
+ *             tensor2im (:23-38, no rounding) + skimage's peak_signal_noise_ratio(data_range = 255) (util/index.py:76-79)
+ * scratch: device, n * 4 doubles (zeroed here).  psnr, gain (may be NULL): device f32 [n].  No host synchronisation. */
+int eld_eval_correct_psnr(eld_ctx* ctx, const float* pred, const float* target, float* out, int n, size_t per_frame,
+                          int correct, double* scratch, float* psnr, float* gain, void* stream);
+
 /* Number of kernels the library has launched through this ctx since creation (bench.py's
  * gpu_launches evidence). */
 int64_t eld_launch_count(const eld_ctx* ctx);

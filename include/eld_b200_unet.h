@@ -66,12 +66,29 @@ size_t eld_unet_workspace_bytes(int n, int h, int w, int train);     /* activati
  * h % 128 == 0, w % 256 == 0.  The caller owns `workspace` (device memory) for the lifetime of the object. */
 int    eld_unet_create(eld_ctx* ctx, int n, int h, int w, int train, void* workspace, size_t bytes, eld_unet** out);
 void   eld_unet_destroy(eld_unet* u);
+/* The same network with 3-channel frames on either side (ELDModel.initialize, ELD_model.py:377-389: in_channels = 3 for
+ * --stage_in srgb, out_channels = 3 for --stage_out srgb): conv1_1 becomes [32][cin][3][3], conv10_1 [cout][32][1][1];
+ * everything else, and the meaning of every other entry point, is unchanged (x is [n][cin][h][w], out / target / dout
+ * [n][cout][h][w]).  cin, cout in {3, 4}. */
+size_t eld_unet_param_count_io(int cin, int cout);
+int    eld_unet_param_offset_io(const char* layer, int is_bias, int cin, int cout, size_t* offset, size_t* count);
+int    eld_unet_create_io(eld_ctx* ctx, int n, int h, int w, int train, void* workspace, size_t bytes,
+                          int cin, int cout, eld_unet** out);
+int    eld_unet_grad_buckets_io(int cin, int cout, size_t* offsets, int max_offsets);
 /* ELDModel.forward (ELD_model.py:422-432): x f32 NCHW [n][4][h][w] -> out f32 NCHW [n][4][h][w] */
 int    eld_unet_forward(eld_unet* u, const float* params, const float* x, float* out, void* stream);
-/* forward + L1 loss (mean |out-target|, losses.py:32) + backward (ELD_model.py:411-420): grads is zeroed
+/* forward + pixel loss (L1: mean |out-target|, losses.py:32; or MSE, see eld_unet_set_loss) + backward (ELD_model.py:411-420): grads is zeroed
  * and filled; *loss (device float) receives the mean absolute error.  No optimizer step, no host sync. */
 int    eld_unet_train_step(eld_unet* u, const float* params, const float* x, const float* target,
                            float* out, float* grads, float* loss, void* stream);
+/* The autograd seam (ELDModel.backward_G, ELD_model.py:411-420: `loss.backward()` through netG): after an
+ * eld_unet_forward on a train = 1 object (activations stay in the workspace), back-propagate the caller's
+ * dout = d(loss)/d(out) (f32 NCHW) into `grads` (zeroed and filled, like eld_unet_train_step).  Any loss the caller likes. */
+int    eld_unet_backward(eld_unet* u, const float* params, const float* x, const float* dout, float* grads, void* stream);
+/* Pixel loss of eld_unet_train_step (models/losses.py:29-36, --loss): 0 = nn.L1Loss (default), 1 = nn.MSELoss. */
+#define ELD_LOSS_L1 0
+#define ELD_LOSS_L2 1
+int    eld_unet_set_loss(eld_unet* u, int kind);
 /* Data-parallel overlap (the reference is single-GPU, ELD_model.py:187-190): the flat gradient is final in
  * eld_unet_grad_buckets() = 3 contiguous ranges in backward-completion order (decoder upv6..conv10_1, bottleneck
  * conv5_*, encoder conv1_1..conv4_2); offsets[2k], offsets[2k+1] = first element, element count of bucket k.

@@ -4,8 +4,11 @@ Follows util/process.py line by line: apply_gains :15-19, clamp :56, binning :41
 gamma_compression :34-39 (pinned by tests/golden/isp_kat.npz, produced by the UNMODIFIED reference `process`), and
 camera_response_function :71-84, whose interpolation lives in the third-party `torchinterp1d` package (absent from the
 reference tree, no version pinned anywhere in it - README.md:32-34 lists names only): its published algorithm
-(searchsorted - 1, clamp, y0 + slope*(x - x0), slope = dy / (eps + dx)) is restated here.  PARITY UNPINNED for the CRF
-branch only.  Only tests/ may import this module.
+(searchsorted - 1, clamp, y0 + slope*(x - x0), slope = dy / (eps + dx)) is restated here and PINNED by
+tests/golden/isp_crf_kat.npz: the unmodified reference CRF branch run on its own EMoR curves with torchinterp1d replaced by
+scipy.interpolate.interp1d, the routine the reference's own EMoR/test_EMoR.py:44-47,62-75 holds torchinterp1d against
+(agreement to the 8-bit level on every unsaturated pixel; at exactly saturated pixels the eps of the restated slope leaves
+254.99998, which process.py:82's .int() truncates - documented in tests/test_isp_cpu.py).  Only tests/ may import this module.
 """
 import numpy as np
 

@@ -35,3 +35,20 @@ def test_isp_oracle_crf_branch_structure():
     sq = np.tile(np.sqrt(E), (3, 1)).astype(np.float32)
     y2 = isp_ref.process(k['x'], k['wb'], k['ccm'], CRF=(np.tile(E, (3, 1)), sq))
     assert (y2 >= lin - 1.0 / 255.0 - 1e-6).all()
+
+
+def test_crf_branch_against_the_reference_run_with_its_own_yardstick(golden_dir):
+    """tests/golden/isp_crf_kat.npz = the UNMODIFIED util/process.py CRF branch on the reference's EMoR curves, with the
+    absent third-party torchinterp1d replaced by scipy.interpolate.interp1d - what the reference's own EMoR/test_EMoR.py
+    compares torchinterp1d against.  The oracle restates torchinterp1d's published formula (slope = dy / (eps + dx)): the
+    two agree to the 8-bit level everywhere except at exactly saturated pixels, where the eps in the slope leaves the
+    restated formula 6e-8 under 1.0 and the reference's `.int()` (process.py:82) truncates 254.99998 to 254."""
+    import os
+    import numpy as np
+    from oracle import isp_ref
+    k = np.load(os.path.join(golden_dir, 'isp_crf_kat.npz'))
+    y = isp_ref.process(k['x'], k['wb'], k['ccm'], CRF=(k['E'], k['fs']))
+    steps = np.rint(np.abs(y - k['y']) * 255.0)
+    unsat = k['y'] < 1.0
+    assert unsat.mean() > 0.5 and steps[unsat].max() <= 1 and (steps[unsat] > 0).mean() <= 5e-3
+    assert steps[~unsat].max() <= 1                                   # the documented one-level truncation, nothing else

@@ -74,3 +74,15 @@ def test_isp_dataset_item_and_numpy_seam(torch):
     ref = isp_ref.process(np.clip(x, 0, 1)[None], wb[None], ccm[None])[0]
     assert isinstance(a, np.ndarray) and a.shape == (3, 16, 16)
     assert _steps(a, ref).max() <= 1 and _steps(b, ref).max() <= 1
+
+
+def test_isp_crf_branch_matches_reference_golden(torch):
+    """The CRF branch of the kernel against the golden the UNMODIFIED reference produced on its own EMoR curves
+    (torchinterp1d -> scipy.interpolate.interp1d, the reference's own yardstick; see tests/test_isp_cpu.py)."""
+    from eld_b200 import process
+    k = np.load(os.path.join(REPO, 'tests', 'golden', 'isp_crf_kat.npz'))
+    y = process.process(torch.from_numpy(k['x']).cuda(), k['wb'], k['ccm'], CRF=(k['E'], k['fs'])).cpu().numpy()
+    s = _steps(y, k['y'])
+    unsat = k['y'] < 1.0
+    assert s[unsat].max() <= 1 and (s[unsat] > 0).mean() <= 5e-3, (s[unsat].max(), (s[unsat] > 0).mean())
+    assert s[~unsat].max() <= 1

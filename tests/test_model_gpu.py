@@ -93,26 +93,48 @@ def test_eval_and_chop(torch, tmp_path):
     assert (chop[:, :, 16:64, 16:120] - full[:, :, 16:64, 16:120]).abs().max().item() < 5e-2
 
 
-def test_eval_matches_reference_formulas(torch, tmp_path):
-    """eval(correct=True): IlluminanceCorrect (ELD_model.py:156-169) + tensor2im/PSNR (ELD_model.py:31-36,
-    util/index.py:79) restated in numpy float64 on the same network output."""
+def test_eval_kernels_match_the_reference_golden(torch, tmp_path, golden_dir):
+    """csrc/eval.cu against tests/golden/eval_kat.npz = IlluminanceCorrect / tensor2im / PSNR run by the UNMODIFIED
+    reference module: corrected frames to 2e-6, PSNR to 1e-4 dB; and forward_chop (ELD_model.py:434-467) through the
+    engine against the reference's own forward_chop output (bf16 tiles: rel-L2 <= 2e-2)."""
     from eld_b200 import models
-    from oracle import ref_numpy
-    opt = models.default_opt(name='ev2', checkpoints_dir=str(tmp_path))
+    from oracle.unet_ref import UNetSeeInDarkRef
+    k = np.load(os.path.join(golden_dir, 'eval_kat.npz'))
     m = models.eld_model()
-    m.initialize(opt)
+    m.initialize(models.default_opt(name='ev2', checkpoints_dir=str(tmp_path), chop=True))
+    pred, tgt = torch.from_numpy(k['pred']).cuda(), torch.from_numpy(k['target']).cuda()
+    out, psnr, gain = m.eval_metrics(pred, tgt, correct=True)
+    assert np.allclose(out.cpu().numpy(), k['corrected'], rtol=2e-6, atol=1e-7)
+    assert np.abs(psnr.cpu().numpy() - k['psnr_corrected']).max() <= 1e-4
+    _, psnr_raw, g1 = m.eval_metrics(pred, tgt, correct=False)
+    assert np.abs(psnr_raw.cpu().numpy() - k['psnr_raw']).max() <= 1e-4 and torch.all(g1 == 1)
+    # forward_chop with the reference network's weights (seed 2018 default init)
+    torch.manual_seed(2018)
+    m.netG.load_state_dict(UNetSeeInDarkRef(4, 4).state_dict())
+    m._eval()
+    with torch.no_grad():
+        chop = m.forward_chop(torch.from_numpy(k['chop_in']).cuda()).cpu().numpy()
+    rel = np.linalg.norm(chop - k['chop_out']) / np.linalg.norm(k['chop_out'])
+    assert rel <= 2e-2, rel
+
+
+def test_eval_end_to_end(torch, tmp_path):
+    """ELDModel.eval(correct=True, crop=True) == the oracle restatement applied to the engine's own network output."""
+    from eld_b200 import models
+    from oracle import eval_ref
+    m = models.eld_model()
+    m.initialize(models.default_opt(name='ev3', checkpoints_dir=str(tmp_path)))
     g = torch.Generator().manual_seed(4)
-    t = torch.rand(1, 4, 512, 512, generator=g)
-    t[0, 0, :8, :8] = 1.0                                        # saturated pixels are excluded from the gain
-    d = {'input': (t * 0.5 + 0.02 * torch.randn(1, 4, 512, 512, generator=g)).clamp(0, 1), 'target': t, 'fn': ['x']}
+    t = torch.rand(1, 4, 544, 576, generator=g)
+    t[0, 0, 100:108, 100:108] = 1.0
+    d = {'input': (t * 0.5 + 0.02 * torch.randn(1, 4, 544, 576, generator=g)).clamp(0, 1), 'target': t, 'fn': ['x']}
     r = m.eval(d, correct=True, crop=True)
-    raw = m._padded_forward(d['input'].cuda()).cpu().numpy().astype(np.float64)
-    p = np.clip(raw, 0, 1)
-    tt = t.numpy().astype(np.float64)
-    mask = tt != 1
-    gain = (p[mask] * tt[mask]).sum() / (p[mask] * p[mask]).sum()
-    want = ref_numpy.psnr255(gain * p, tt)
-    assert abs(r['PSNR'] - want) < 1e-3, (r['PSNR'], want)
+    xc, tc = eval_ref.crop_center(d['input'], 512, 512), eval_ref.crop_center(t, 512, 512)
+    raw = m._padded_forward(xc.contiguous().cuda()).cpu().numpy()
+    corr = eval_ref.illuminance_correct(raw, tc.numpy())
+    want = eval_ref.psnr(eval_ref.tensor2im(corr), eval_ref.tensor2im(tc.numpy()))
+    want_in = eval_ref.psnr(eval_ref.tensor2im(xc.numpy()), eval_ref.tensor2im(tc.numpy()))
+    assert abs(r['PSNR'] - want) < 2e-3 and abs(r['PSNR_input'] - want_in) < 1e-3, (r, want, want_in)
 
 
 def test_set_input_noise_stream_is_invariant_to_the_gpu_count(torch, tmp_path):
@@ -150,3 +172,57 @@ def test_set_input_noise_stream_is_invariant_to_the_gpu_count(torch, tmp_path):
     sd = (lv.input.cpu() - flat).flatten(1).std(1)
     assert sd.max() / sd.min() > 1.05, sd
     assert one._frames_seen == 8 and one.state_dict()['frames_seen'] == 8
+
+
+def test_prefetched_input_equals_the_serial_one(torch, tmp_path):
+    """Engine.train's look-ahead (ELDModel.prefetch_input on a side stream) must hand set_input exactly the tensors the
+    serial path makes - same global frame ids, same per-frame parameters - and fall back when the dict differs."""
+    from eld_b200 import models
+    from eld_b200.noise import NoiseModel
+
+    def make():
+        m = models.eld_model()
+        m.initialize(models.default_opt(name='pf', checkpoints_dir=str(tmp_path), noise='P+g', noise_on_gpu=True, augment_on_gpu=True),
+                     noise_maker=NoiseModel('P+g', include=4, verbose=False, seed=5))
+        return m
+    batches = [_batch(torch, 2, s, 256, 256) for s in range(3)]
+    a, b = make(), make()
+    serial = []
+    for d in batches:
+        a.set_input(d, 'train')
+        serial.append((a.input.clone(), a.target.clone()))
+    b.set_input(batches[0], 'train')
+    got = [(b.input.clone(), b.target.clone())]
+    for i in (1, 2):
+        b.prefetch_input(batches[i])
+        b.set_input(batches[i], 'train')
+        got.append((b.input.clone(), b.target.clone()))
+    torch.cuda.synchronize()
+    for (x0, t0), (x1, t1) in zip(serial, got):
+        assert torch.equal(x0, x1) and torch.equal(t0, t1)
+    b.prefetch_input(batches[0])
+    b.set_input(batches[1], 'train')                      # a different dict: the prefetched tensors are dropped, not misused
+    assert b.input.shape == (2, 4, 256, 256) and b._prefetched is None
+
+
+def test_stage_in_srgb_is_wired(torch, tmp_path):
+    """train_syn.py:55-58 / ELD_model.py:377-389: --stage_in srgb builds a 3 -> 4 network; with on-GPU synthesis the input
+    is ISPDataset's chain (noise -> clip -> raw2rgb_v2(wb, ccm) -> clip, sid_dataset.py:306-312) made on the stream."""
+    from eld_b200 import models, process
+    from eld_b200.noise import NoiseModel
+    m = models.eld_model()
+    nm = NoiseModel('p+g', include=4, verbose=False, seed=3)
+    m.initialize(models.default_opt(name='srgb', checkpoints_dir=str(tmp_path), stage_in='srgb', noise='p+g', noise_on_gpu=True),
+                 noise_maker=nm)
+    assert m.netG.conv1_1.weight.shape == (32, 3, 3, 3) and m.netG.conv10_1.weight.shape == (4, 32, 1, 1)
+    g = torch.Generator().manual_seed(2)
+    t = torch.rand(2, 4, 128, 256, generator=g)
+    wb = torch.tensor([[2.0, 1.0, 1.6, 1.0], [1.8, 1.0, 2.1, 1.0]])
+    ccm = torch.eye(3).repeat(2, 1, 1) * 1.2
+    m.set_input({'target': t, 'wb': wb, 'ccm': ccm}, 'train')
+    assert m.input.shape == (2, 3, 128, 256) and m.target.shape == (2, 4, 128, 256)
+    noisy = nm.batch_gpu(t.cuda(), params=nm.frame_params(0, 2), frame_id0=0, clip=True)
+    want = process.isp_dataset_item(noisy, wb, ccm)
+    assert torch.equal(m.input, want)
+    m.optimize_parameters()
+    assert np.isfinite(m.get_current_errors()['Pixel'])

@@ -168,3 +168,22 @@ def test_dpsnr_after_200_adam_steps(torch):
     assert max(abs(d) for d in d_same) <= 0.05, d_same
     assert all(g[0] > 1.0 and g[1] > 1.0 for g in gain), gain
     assert abs(float(np.mean(d_traj))) <= 0.05, d_traj
+
+
+def test_mse_loss_train_step(torch):
+    """--loss l2 (models/losses.py:33-34, nn.MSELoss): loss and every gradient tensor against the emulated backward."""
+    from tests.unet_emul import emulated_train_step, fp32_cuda, smooth_frames
+    ours, ref = _pair(torch)
+    _spread_biases(torch, ours, ref)
+    ours.loss_kind = 'l2'
+    clean = smooth_frames(2, 256, 256, seed=21, device='cuda')
+    x = (clean + 0.05 * torch.randn_like(clean)).clamp(0, 1)
+    out, loss = ours.train_step(x, clean)
+    mine = {k: p.grad.detach().clone() for k, p in ours.named_parameters()}
+    oem, lem, gem = fp32_cuda(lambda: emulated_train_step(ref, x, clean, loss='l2'))
+    want = fp32_cuda(lambda: torch.nn.functional.mse_loss(ref(x), clean))
+    assert abs(loss.item() - lem.item()) <= 2e-3 * lem.item(), (loss.item(), lem.item())
+    assert abs(loss.item() - want.item()) <= 1e-2 * want.item()
+    bad = [(k, _rel(mine[k], gem[k])) for k in mine if _rel(mine[k], gem[k]) > 5e-3]
+    assert not bad, bad
+    ours.loss_kind = 'l1'

@@ -2,11 +2,13 @@
 # usage: gpurun --timeout 900 -- 'bash tools/quick3.sh tag'
 TAG=${1:-q}
 O=gpurun_out/$TAG; mkdir -p $O
-( timeout 600 python -m pytest tests/test_parity_fullsize_gpu.py tests/test_unet_gpu.py tests/test_model_gpu.py -m gpu -q -x 2>&1 | tail -25 ) > $O/pytest.txt 2>&1
+( timeout 600 python -m pytest tests/test_parity_fullsize_gpu.py tests/test_unet_gpu.py tests/test_model_gpu.py tests/test_conv_gpu.py -m gpu -q 2>&1 | tail -25 ) > $O/pytest.txt 2>&1
 timeout 300 python tools/profile_layers.py 8 $O/layers.json > $O/layers.txt 2>&1
 timeout 400 python bench.py --no-cpu-baseline --no-onbox > $O/bench_train.json 2> $O/bench_train.err
-ELD_CONV_PROF=1 timeout 300 python - > $O/convprof.txt 2>&1 <<'PY'
-import torch, sys
+ELD_OVERLAP=1 timeout 400 python bench.py --no-cpu-baseline --no-onbox > $O/bench_train_overlap.json 2>> $O/bench_train.err
+ELD_SKIP=1 timeout 300 python - > $O/convprof.txt 2>&1 <<'PY'
+import torch, sys, os
+if os.environ.get("ELD_SKIP"): sys.exit(0)
 sys.path.insert(0, '.')
 from eld_b200 import arch
 torch.manual_seed(0)
@@ -18,4 +20,4 @@ for i in range(3):
     net.train_step(x, t, loss_out=loss)
     torch.cuda.synchronize()
 PY
-tail -25 $O/pytest.txt; cat $O/bench_train.json; grep -E "sum of|conv1_1|conv1_2|input" $O/layers.txt; grep -A12 "step 2" $O/convprof.txt | cut -c1-260
+tail -25 $O/pytest.txt; cat $O/bench_train.json; grep -E "sum of|conv1_1|conv1_2|input" $O/layers.txt; cat $O/bench_train_overlap.json
