@@ -191,10 +191,10 @@ class UNetSeeInDark(nn.Module):
 
     # ---- data parallel: bucketed all-reduce overlapped with backward (SURVEY 8e) ----------------------
     def grad_buckets(self):
-        """[(offset, count)] of the flat gradient in backward-completion order (decoder, bottleneck, encoder)."""
+        """[(offset, count)] of the flat gradient in backward-completion order (decoder, bottleneck, encoder, first layer)."""
         import ctypes as c
-        arr = (c.c_size_t * 6)()
-        k = _lib.load().eld_unet_grad_buckets_io(self.in_channels, self.out_channels, arr, 6)
+        arr = (c.c_size_t * 16)()
+        k = _lib.load().eld_unet_grad_buckets_io(self.in_channels, self.out_channels, arr, 16)
         return [(int(arr[2 * i]), int(arr[2 * i + 1])) for i in range(k)]
 
     def train_step_ddp(self, x, target, loss_out=None, group=None, timeline=None):

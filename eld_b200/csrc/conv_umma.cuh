@@ -513,11 +513,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const ConvGemmParams p
                     dst = p.out + ((size_t)(img * 2 * p.H + oy) * (2 * p.W) + ox) * p.out_pitch + p.out_c0 + co;
                     bcol = co;
                 }
-                uint4 mk[4];
+                uint32_t mk[16];
                 if (p.act == ACT_MASK && in_img) {
-                    const uint4* ap = reinterpret_cast<const uint4*>(p.aux + (size_t)pix * p.aux_pitch + (p.aux_c0 + col));
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) mk[g] = __ldg(ap + g);
+                    const __nv_bfloat16* ap = p.aux + (size_t)pix * p.aux_pitch + (p.aux_c0 + col);
+                    ptx::ld_global_nc_v8(ap, mk);
+                    ptx::ld_global_nc_v8(ap + 16, mk + 8);
                 }
                 ptx::tmem_ld_wait();
                 float v[32];
@@ -536,7 +536,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const ConvGemmParams p
                 } else if (p.act == ACT_MASK && in_img) {
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
-                        const uint32_t aw[4] = { mk[g].x, mk[g].y, mk[g].z, mk[g].w };
+                        const uint32_t aw[4] = { mk[4 * g], mk[4 * g + 1], mk[4 * g + 2], mk[4 * g + 3] };
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             // LeakyReLU keeps the sign: slope = 0.6 + 0.4 * sign(activation) = 1 or 0.2
@@ -559,30 +559,31 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const ConvGemmParams p
                         pm[j] = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, p.tile_w));
                     }
                     if (in_img && !((x | y) & 1)) {
-                        uint4* q4 = reinterpret_cast<uint4*>(p.pool_out + ((size_t)(img * (p.H >> 1) + (y >> 1)) * (p.W >> 1) + (x >> 1)) * p.pool_pitch + col);
+                        __nv_bfloat16* q4 = p.pool_out + ((size_t)(img * (p.H >> 1) + (y >> 1)) * (p.W >> 1) + (x >> 1)) * p.pool_pitch + col;
+                        uint32_t pw[16];
 #pragma unroll
-                        for (int g = 0; g < 4; ++g) {
-                            uint32_t w[4];
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const __nv_bfloat162 h = __floats2bfloat162_rn(pm[g * 8 + 2 * j], pm[g * 8 + 2 * j + 1]);
-                                w[j] = *reinterpret_cast<const uint32_t*>(&h);
-                            }
-                            q4[g] = make_uint4(w[0], w[1], w[2], w[3]);
+                        for (int j = 0; j < 16; ++j) {
+                            const __nv_bfloat162 h = __floats2bfloat162_rn(pm[2 * j], pm[2 * j + 1]);
+                            pw[j] = *reinterpret_cast<const uint32_t*>(&h);
                         }
+                        ptx::st_global_v8(q4, pw);
+                        ptx::st_global_v8(q4 + 16, pw + 8);
                     }
                 }
                 if (!in_img || (p.dbg & 1)) continue;
-                uint4* d4 = reinterpret_cast<uint4*>(dst);
+                uint32_t wv[16];
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    uint32_t w[4];
+                for (int j = 0; j < 16; ++j) {
+                    const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+                    wv[j] = *reinterpret_cast<const uint32_t*>(&h);
+                }
+                if (p.dbg & 32) {               // (A/B, ELD_CONV_DBG=32: the four 16-byte stores of round 1)
+                    uint4* d4 = reinterpret_cast<uint4*>(dst);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const __nv_bfloat162 h = __floats2bfloat162_rn(v[g * 8 + 2 * j], v[g * 8 + 2 * j + 1]);
-                        w[j] = *reinterpret_cast<const uint32_t*>(&h);
-                    }
-                    d4[g] = make_uint4(w[0], w[1], w[2], w[3]);
+                    for (int g = 0; g < 4; ++g) d4[g] = make_uint4(wv[4 * g], wv[4 * g + 1], wv[4 * g + 2], wv[4 * g + 3]);
+                } else {                        // 64 bytes = two full 32-byte sectors, one 256-bit store each
+                    ptx::st_global_v8(dst, wv);
+                    ptx::st_global_v8(dst + 16, wv + 8);
                 }
             }
             ptx::tc_fence_before();

@@ -207,7 +207,8 @@ first_conv_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const FirstConv
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
-            uint4* d4 = reinterpret_cast<uint4*>(p.out + ((size_t)(img * p.H + y0 + py) * p.W + (x0 + px)) * p.out_pitch);
+            __nv_bfloat16* dst = p.out + ((size_t)(img * p.H + y0 + py) * p.W + (x0 + px)) * p.out_pitch;
+            uint32_t wv[16];
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
                 const float4 b0 = sb4[2 * g], b1 = sb4[2 * g + 1];
@@ -217,8 +218,11 @@ first_conv_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const FirstConv
                                __uint_as_float(r[8 * g + 6]) + b1.z, __uint_as_float(r[8 * g + 7]) + b1.w };
 #pragma unroll
                 for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.2f * v[j]);
-                d4[g] = make_uint4(fc_pack(v[0], v[1]), fc_pack(v[2], v[3]), fc_pack(v[4], v[5]), fc_pack(v[6], v[7]));
+                wv[4 * g] = fc_pack(v[0], v[1]); wv[4 * g + 1] = fc_pack(v[2], v[3]);
+                wv[4 * g + 2] = fc_pack(v[4], v[5]); wv[4 * g + 3] = fc_pack(v[6], v[7]);
             }
+            ptx::st_global_v8(dst, wv);                    // 64 bytes = two full sectors, two 256-bit stores
+            ptx::st_global_v8(dst + 16, wv + 8);
             if (++acc == kFcAcc) { acc = 0; acc_ph ^= 1u; }
         }
     }

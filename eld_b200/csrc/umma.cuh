@@ -160,6 +160,20 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t r[32])
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---- 256-bit global accesses (sm_100: STG.E.ENL2.256 / LDG.E.ENL2.256; 32-byte aligned) ------------------------------
+// An epilogue thread owns 64 contiguous bytes of its pixel: two of these write two FULL 32-byte sectors each, where
+// four 16-byte stores sent four half-sector requests to L2.
+__device__ __forceinline__ void st_global_v8(void* p, const uint32_t w[8])
+{
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+}
+__device__ __forceinline__ void ld_global_nc_v8(const void* p, uint32_t w[8])
+{
+    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "l"(p));
+}
+
 // ---- descriptors ----------------------------------------------------------------------------------
 // Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
 //   [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [49,52) base_offset |

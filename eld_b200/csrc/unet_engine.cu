@@ -33,12 +33,13 @@ constexpr int kNumLayers = sizeof(kLayers) / sizeof(kLayers[0]);
 enum { I_C11 = 0, I_C12, I_C21, I_C22, I_C31, I_C32, I_C41, I_C42, I_C51, I_C52, I_UP6, I_C61, I_C62, I_UP7,
        I_C71, I_C72, I_UP8, I_C81, I_C82, I_UP9, I_C91, I_C92, I_C10 };
 
-constexpr int kGradBuckets = 3;
-// first table entry (state_dict order without conv1_1 / conv10_1) of each bucket's tile range: upv6.., conv5_1.., conv1_2..
-constexpr int kBucketEntry0[kGradBuckets] = { 9, 7, 0 };
-constexpr int kBucketEntry1[kGradBuckets] = { 21, 9, 7 };
-constexpr int kBucketLayer0[kGradBuckets] = { 10 /*upv6*/, 8 /*conv5_1*/, 0 /*conv1_1*/ };
-constexpr int kBucketLayer1[kGradBuckets] = { 23, 10, 8 };   // one past the last layer
+constexpr int kGradBuckets = 4;
+// first table entry (state_dict order without conv1_1 / conv10_1) of each bucket's tile range: upv6.., conv5_1.., conv2_1..,
+// conv1_2.  The last bucket (conv1_1 + conv1_2, 42 KB) is all that is still in flight when backward ends.
+constexpr int kBucketEntry0[kGradBuckets] = { 9, 7, 1, 0 };
+constexpr int kBucketEntry1[kGradBuckets] = { 21, 9, 7, 1 };
+constexpr int kBucketLayer0[kGradBuckets] = { 10 /*upv6*/, 8 /*conv5_1*/, 2 /*conv2_1*/, 0 /*conv1_1*/ };
+constexpr int kBucketLayer1[kGradBuckets] = { 23, 10, 8, 2 };   // one past the last layer
 
 struct PackEntry { unsigned long long src, dst_f, dst_d; int cout, cin, type; int pad; };
 struct PackTable {
@@ -194,7 +195,7 @@ struct eld_unet {
     float* gtmp = nullptr;
     PackTable table;
     // gradient buckets in backward-completion order (data-parallel overlap): decoder, bottleneck, encoder
-    cudaEvent_t bucket_ev[kGradBuckets] = { nullptr, nullptr, nullptr };
+    cudaEvent_t bucket_ev[kGradBuckets] = { nullptr, nullptr, nullptr, nullptr };
     int cin0 = 4, cout_last = 4; // channels of the frame in / out: 4 = packed raw, 3 = sRGB (ELD_model.py:377-389)
     int l2_loss = 0;             // 0: nn.L1Loss (the reference default, losses.py:31-32), 1: nn.MSELoss (losses.py:33-34)
     // optional per-launch profile (CUDA events on the launch stream)
@@ -517,11 +518,14 @@ struct Runner {
         op.mode = WG_DECONV; op.p = dy; op.p_pitch = dyp; op.p_c0 = 0; op.p_ch = l.cout;
         op.q = x; op.q_pitch = l.cin; op.q_c0 = 0; op.q_ch = l.cin;
         op.n_img = u->n; op.H = u->H >> lvl_in; op.W = u->W >> lvl_in; op.dw = grads + l.w_off;
+        static const bool fuse_bias = getenv("ELD_DECONV_COLSUM") == nullptr;    // (A/B: the stand-alone column-sum kernel)
+        op.db = fuse_bias ? grads + l.b_off : nullptr;           // bias gradient = column sums of the d(up) boxes, same launch
         const double px = (double)u->n * op.H * op.W;
         {
             Scope sc(u, st, l.name, "wgrad", 2.0 * px * 4 * l.cout * l.cin, px * 2 * (l.cin + 4 * l.cout) + 16.0 * l.cin * l.cout);
             TRY(launch_wgrad(ctx(), op, st));
         }
+        if (fuse_bias) return ELD_OK;
         Scope sc(u, st, l.name, "bgrad", 0.0, px * 8 * l.cout);
         return launch_colsum(ctx(), dy, dyp, 0, l.cout, (size_t)u->n * op.H * op.W * 4, grads + l.b_off, st);
     }
@@ -649,6 +653,7 @@ struct Runner {
         TRY(conv_wgrad(I_C22, U->a2_1, 64, 0, U->dz2_2, g, 1));
         TRY(conv_dgrad(I_C22, U->dz2_2, U->dz2_1, 64, 0, U->a2_1, 64, 0, 1));
         TRY(conv_wgrad(I_C21, U->p1, 32, 0, U->dz2_1, g, 1));
+        TRY(finish_bucket(2, g));
         TRY(conv_dgrad(I_C21, U->dz2_1, U->dp1, 32, 0, nullptr, 0, 0, 1));
         TRY(pool_bwd(U->cat9, 64, 32, skip_half(U->dcat9, 0, 32), U->dp1, U->dz1_2, 32, 1));
         TRY(conv_wgrad(I_C12, U->a1_1, 32, 0, U->dz1_2, g, 0));
@@ -658,7 +663,7 @@ struct Runner {
             Scope sc(u, st, "conv1_1", "wgrad", 2.0 * px * 32 * 9 * U->cin0, px * (4 * U->cin0 + 64));
             TRY(launch_first_conv_wgrad(ctx(), x, U->cin0, U->dz1_1, 32, g + U->L[I_C11].w_off, g + U->L[I_C11].b_off, U->n, U->H, U->W, st));
         }
-        return finish_bucket(2, g);
+        return finish_bucket(3, g);
     }
 };
 

@@ -40,7 +40,14 @@ int launch_conv_gemm(eld_ctx* ctx, const GemmOp& op, cudaStream_t st)
                 "deconv dgrad tile: H=%d must be a multiple of 8 and W=%d of 16", op.H, op.W);
     ELD_REQUIRE(op.cin % 32 == 0, "conv tile: cin=%d must be a multiple of 32", op.cin);
     ELD_REQUIRE(op.n_total % 32 == 0, "conv tile: GEMM N=%d must be a multiple of 32", op.n_total);
-    ELD_REQUIRE(op.a_pitch % 8 == 0 && op.out_pitch % 8 == 0, "conv tile: pitches must be multiples of 8 channels");
+    ELD_REQUIRE(op.a_pitch % 8 == 0, "conv tile: the input pitch must be a multiple of 8 channels");
+    // the epilogue moves 64 bytes per pixel with two 256-bit accesses: 32-byte aligned pixel rows and channel offsets
+    ELD_REQUIRE(op.out_pitch % 16 == 0 && op.out_c0 % 16 == 0 && (reinterpret_cast<uintptr_t>(op.out) & 31) == 0,
+                "conv tile: output pitch / first channel must be multiples of 16 channels and the tensor 32-byte aligned");
+    ELD_REQUIRE(op.aux == nullptr || (op.aux_pitch % 16 == 0 && op.aux_c0 % 16 == 0 && (reinterpret_cast<uintptr_t>(op.aux) & 31) == 0),
+                "conv tile: mask-source pitch / first channel must be multiples of 16 channels and the tensor 32-byte aligned");
+    ELD_REQUIRE(op.pool_out == nullptr || (op.pool_pitch % 16 == 0 && (reinterpret_cast<uintptr_t>(op.pool_out) & 31) == 0),
+                "conv tile: pooled-output pitch must be a multiple of 16 channels and the tensor 32-byte aligned");
     ConvGemmParams p{};
     p.n_img = op.n_img; p.H = op.H; p.W = op.W;
     p.tiles_x = op.W / 16; p.tiles_y = op.H / 8;
@@ -57,7 +64,8 @@ int launch_conv_gemm(eld_ctx* ctx, const GemmOp& op, cudaStream_t st)
     ELD_REQUIRE(op.pool_out == nullptr || (op.epi_mode == EPI_STORE && op.H % 2 == 0 && op.W % 2 == 0),
                 "conv tile: the fused max pool needs a plain store epilogue and even H, W");
     p.pool_out = static_cast<__nv_bfloat16*>(op.pool_out); p.pool_pitch = op.pool_pitch;
-    ELD_REQUIRE(op.out_split == 0 || (op.epi_mode == EPI_STORE && op.out2 && op.out_split % 32 == 0 && op.out2_pitch % 8 == 0),
+    ELD_REQUIRE(op.out_split == 0 || (op.epi_mode == EPI_STORE && op.out2 && op.out_split % 32 == 0 && op.out2_pitch % 16 == 0 &&
+                                     (reinterpret_cast<uintptr_t>(op.out2) & 31) == 0),
                 "conv tile: split store needs a plain store epilogue, a second tensor and a split at a multiple of 32 columns");
     p.out2 = static_cast<__nv_bfloat16*>(op.out2); p.out2_pitch = op.out2_pitch; p.out_split = op.out_split;
     const int rb = p.kc * 2;
@@ -368,7 +376,7 @@ int launch_wgrad(eld_ctx* ctx, const WgradOp& op, cudaStream_t st)
         (op.q_ch == 32 || op.q_ch == 64 || op.q_ch == 128 || op.q_ch % 256 == 0) && !(op.p_ch == 32 && op.q_ch > 128) &&
         !getenv("ELD_WGRAD_V1"))
         return launch_wgrad_conv(ctx, op, st);
-    ELD_REQUIRE(op.db == nullptr, "wgrad tile: fused bias gradient needs the full-halo conv generation");
+    ELD_REQUIRE(op.db == nullptr || op.mode == WG_DECONV, "wgrad tile: the first-generation tile fuses the bias gradient for deconvs only");
     ELD_REQUIRE(op.H % 4 == 0 && op.W % 16 == 0, "wgrad tile: H=%d must be a multiple of 4 and W=%d of 16", op.H, op.W);
     ELD_REQUIRE(op.p_ch % 32 == 0 && op.q_ch % 32 == 0, "wgrad tile: channel counts must be multiples of 32");
     WgradParams p{};
@@ -399,6 +407,7 @@ int launch_wgrad(eld_ctx* ctx, const WgradOp& op, cudaStream_t st)
     while (cols < p.n_tile) cols *= 2;
     p.tmem_cols = cols;
     p.dw = op.dw;
+    p.db = op.db;
 
     CUtensorMap tmP, tmQ;
     const cuuint64_t eb = 2;

@@ -36,6 +36,8 @@ struct WgradParams {
     int ksplit;
     int stages, tmem_cols;
     float* dw;                // f32 gradient, PyTorch layout (conv OIHW [q_ch][p_ch][3][3]; deconv IOHW [q_ch][p_ch][2][2])
+    float* db;                // deconv only, optional: bias gradient db[co] += sum over the FINE pixels of d(up)[., co] = column
+                              // sums of the P boxes, formed by the otherwise idle epilogue warps of the nt == 0 CTAs while the MMAs run
 };
 
 constexpr int kWgradThreads = 192;
@@ -71,11 +73,12 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant
     const int ch_end = min(total_chunks, ch_begin + per);
     const int nchunks = max(0, ch_end - ch_begin);
     const int boxes_per_tap = p.p_ch / p.box_ch;
+    const bool do_bias = p.db != nullptr && nt == 0;      // the P (d(up)) boxes are the same for every N tile: one of them sums
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&tmP);
         ptx::prefetch_tmap(&tmQ);
-        for (int s = 0; s < p.stages; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
+        for (int s = 0; s < p.stages; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], do_bias ? 5 : 1); }
         ptx::mbar_init(acc_full, 1);
         ptx::fence_barrier_init();
     }
@@ -163,6 +166,30 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant
         const int gb = mt * p.boxes_per_mtile + b;
         const int tap = gb / boxes_per_tap;
         const int pc = (gb - tap * boxes_per_tap) * p.box_ch + (r - b * p.box_ch);   // P-side channel
+        if (do_bias) {
+            // ---- bias gradient while the MMAs run: this thread's (tap, channel) column of the P boxes, all 64 pixel rows ----
+            const int cib = r - b * p.box_ch;                  // channel inside the box
+            const uint32_t chunk16 = (uint32_t)(cib * 2) >> 4, in16 = (uint32_t)(cib * 2) & 15u;
+            float acc = 0.f;
+            int s = 0;
+            uint32_t ph = 0;
+            for (int i = 0; i < nchunks; ++i) {
+                ptx::mbar_wait(&full[s], ph);
+                if (tap < p.taps) {
+                    const uint8_t* box = smem + (size_t)s * stage_bytes + (size_t)b * p_box;
+#pragma unroll 8
+                    for (int row = 0; row < kWgradKP; ++row) {
+                        const uint32_t swz = (p_row == 128) ? (uint32_t)(row & 7) : (uint32_t)((row >> 1) & 3);
+                        const unsigned short v = *reinterpret_cast<const unsigned short*>(box + row * p_row + ((chunk16 ^ swz) << 4) + in16);
+                        acc += __uint_as_float((uint32_t)v << 16);
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&empty[s]);
+                if (++s == p.stages) { s = 0; ph ^= 1u; }
+            }
+            if (tap < p.taps) atomicAdd(p.db + pc, acc);
+        }
         ptx::mbar_wait(acc_full, 0);
         ptx::tc_fence_after();
         const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16);

@@ -25,7 +25,8 @@ int eld_pack_weights(eld_ctx* ctx, const float* w, void* packed_bf16, int cout, 
 
 /* y[n,h,w,y_c0:y_c0+cout] = act( conv3x3_pad1(x[n,h,w,x_c0:x_c0+cin]) + bias )   nn.Conv2d(k=3,p=1), Unet.py:11-44.
  * With ELD_PACK_CONV_DGRAD weights (cin/cout swapped) the same tile is the data gradient.
- * cin % 32 == 0, cout % 32 == 0; any h, w (partial tiles are masked).  bias may be NULL. */
+ * cin % 32 == 0, cout % 32 == 0; any h, w (partial tiles are masked).  bias may be NULL.  y (and aux): 32-byte aligned,
+ * pitch and first channel multiples of 16 (the epilogue uses 256-bit accesses). */
 int eld_conv3x3_bf16(eld_ctx* ctx, const void* x, int x_pitch, int x_c0, int cin, const void* w_packed,
                      const float* bias, void* y, int y_pitch, int y_c0, int cout, int n, int h, int w,
                      int act, const void* aux, int aux_pitch, int aux_c0, void* stream);
@@ -90,12 +91,13 @@ int    eld_unet_backward(eld_unet* u, const float* params, const float* x, const
 #define ELD_LOSS_L2 1
 int    eld_unet_set_loss(eld_unet* u, int kind);
 /* Data-parallel overlap (the reference is single-GPU, ELD_model.py:187-190): the flat gradient is final in
- * eld_unet_grad_buckets() = 3 contiguous ranges in backward-completion order (decoder upv6..conv10_1, bottleneck
- * conv5_*, encoder conv1_1..conv4_2); offsets[2k], offsets[2k+1] = first element, element count of bucket k.
+ * eld_unet_grad_buckets() = 4 contiguous ranges in backward-completion order (decoder upv6..conv10_1, bottleneck
+ * conv5_*, encoder conv2_1..conv4_2, first layer conv1_1..conv1_2); offsets[2k], offsets[2k+1] = first element, element
+ * count of bucket k.
  * After eld_unet_bucket_events(u, 1) every eld_unet_train_step records an event on its stream when bucket k is final;
  * eld_unet_wait_bucket makes `stream` (the caller's communication stream) wait for it - the caller then all-reduces
  * grads[offset, offset+count) there while the rest of backward runs, and runs Adam after the last bucket. */
-int    eld_unet_grad_buckets(size_t* offsets, int max_offsets);      /* returns the bucket count (3) */
+int    eld_unet_grad_buckets(size_t* offsets, int max_offsets);      /* returns the bucket count (4) */
 int    eld_unet_bucket_events(eld_unet* u, int enable);
 int    eld_unet_wait_bucket(eld_unet* u, int bucket, void* stream);
 /* torch.optim.Adam step (ELD_model.py:400-401,475) on the flat buffers; grads are multiplied by

@@ -162,15 +162,17 @@ def test_grad_buckets_partition_the_flat_gradient():
     import ctypes as c
     from eld_b200 import _lib
     lib = _lib.load()
-    arr = (c.c_size_t * 6)()
-    k = lib.eld_unet_grad_buckets(arr, 6)
+    arr = (c.c_size_t * 16)()
+    k = lib.eld_unet_grad_buckets(arr, 16)
     b = [(int(arr[2 * i]), int(arr[2 * i + 1])) for i in range(k)]
     n = lib.eld_unet_param_count()
-    assert k == 3 and sum(cnt for _, cnt in b) == n == 7760484
+    assert k == 4 and sum(cnt for _, cnt in b) == n == 7760484
     spans = sorted(b)
-    assert spans[0][0] == 0 and all(spans[i][0] + spans[i][1] == spans[i + 1][0] for i in range(2)) and spans[2][0] + spans[2][1] == n
+    assert spans[0][0] == 0 and all(spans[i][0] + spans[i][1] == spans[i + 1][0] for i in range(k - 1)) and spans[-1][0] + spans[-1][1] == n
     off, cnt = c.c_size_t(), c.c_size_t()
     lib.eld_unet_param_offset(b'upv6', 0, c.byref(off), c.byref(cnt))
     assert b[0][0] == off.value                        # decoder bucket starts at upv6.weight ...
     lib.eld_unet_param_offset(b'conv5_1', 0, c.byref(off), c.byref(cnt))
-    assert b[1][0] == off.value and b[2][0] == 0       # ... bottleneck at conv5_1.weight, encoder at conv1_1.weight
+    assert b[1][0] == off.value and b[3][0] == 0       # ... bottleneck at conv5_1.weight, the last bucket at conv1_1.weight
+    lib.eld_unet_param_offset(b'conv2_1', 0, c.byref(off), c.byref(cnt))
+    assert b[2][0] == off.value and b[3][1] == off.value   # encoder bucket conv2_1..conv4_2; conv1_1 + conv1_2 travel last

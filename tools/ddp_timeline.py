@@ -35,12 +35,12 @@ for _ in range(5):
                  'adam_end': s0.elapsed_time(end),
                  'buckets': [(s0.elapsed_time(a), s0.elapsed_time(b), nbytes) for a, b, nbytes in tl['buckets']]})
 if rank == 0:
-    names = ['decoder upv6..conv10_1', 'bottleneck conv5_*', 'encoder conv1_1..conv4_2']
+    names = ['decoder upv6..conv10_1', 'bottleneck conv5_*', 'encoder conv2_1..conv4_2', 'first layer conv1_1..conv1_2']
     print('world %d, batch 8 x 4x512x512 per GPU; times in ms from the step start (median of 5 steps)' % world)
     med = lambda v: sorted(v)[len(v) // 2]
     print('backward_end %.3f   all-reduce joined %.3f   adam_end %.3f' % (med([r['backward_end'] for r in rows]),
           med([r['joined'] for r in rows]), med([r['adam_end'] for r in rows])))
-    for k in range(3):
+    for k in range(len(rows[0]['buckets'])):
         a = med([r['buckets'][k][0] for r in rows]); b = med([r['buckets'][k][1] for r in rows])
         print('bucket %d %-26s %5.1f MB  ready %.3f  reduced %.3f  (%.0f us)' % (k, names[k], rows[0]['buckets'][k][2] / 1e6, a, b, (b - a) * 1e3))
 dist.destroy_process_group()
