@@ -552,11 +552,15 @@ struct Runner {
     // bucket final (a data-parallel caller all-reduces it on a side stream while the rest of backward runs)
     int finish_bucket(int k, float* g) const
     {
-        const int t0 = u->table.tile0[kBucketEntry0[k]], t1 = u->table.tile0[kBucketEntry1[k]];
-        const int extra = 0;                                      // (conv1_1's wgrad tile writes the PyTorch layout itself)
+        // single-GPU steps (no bucket events) move all conv gradients with ONE launch at the end: a permute launch over a
+        // few dozen tiles is latency-bound (~15 us whatever its size), four of them cost 61 us against 27 us for one
+        const bool per_bucket = u->bucket_ev[0] != nullptr;
+        if (!per_bucket && k != kGradBuckets - 1) return ELD_OK;
+        const int t0 = per_bucket ? u->table.tile0[kBucketEntry0[k]] : 0;
+        const int t1 = per_bucket ? u->table.tile0[kBucketEntry1[k]] : u->table.tile0[u->table.n];
         {
             Scope sc(u, st, "weights", "gperm", 0.0, 0.0);
-            wgrad_permute_kernel<<<t1 - t0 + extra, 256, 0, st>>>(u->gtmp, g, u->table, t0, t1);
+            wgrad_permute_kernel<<<t1 - t0, 256, 0, st>>>(u->gtmp, g, u->table, t0, t1);
             ELD_CHECK_CUDA(cudaGetLastError());
             count_launch(ctx());
         }
