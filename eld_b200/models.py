@@ -27,7 +27,7 @@ def default_opt(**kw):
              resume_epoch=None, seed=2018, chop=False, no_log=True, no_verbose=True, netG='unet', channels=4,
              stage_in='raw', stage_out='raw', model_path=None, include=4, crf=False, batchSize=1, lr=1e-4,
              beta1=0.9, wd=0.0, loss='l1', noise='g', isTrain=True, save_epoch_freq=100, noise_on_gpu=False,
-             augment_on_gpu=False, defer_loss_sync=False, prefetch_noise=False)
+             augment_on_gpu=False, defer_loss_sync=False, prefetch_noise=False, num_burst=1)
     o.update(kw)
     return SimpleNamespace(**o)
 
@@ -188,7 +188,7 @@ class ELDModel(BaseModel):
         # per-frame (K, g_scale, ratio, ...) and flip flags are drawn from a generator keyed by (seed, global frame id):
         # W ranks draw W*n DIFFERENT tuples (not W copies of the same n), and frame f gets the same tuple at any GPU
         # count.  The draw itself is noise.py:201-225's call order on that per-frame RandomState.
-        params = self.noise_maker.frame_params(fid0, n)
+        params = self.noise_maker.frame_params(fid0, n, burst=max(1, int(getattr(self.opt, 'num_burst', 1))))
         if getattr(self.opt, 'augment_on_gpu', False):
             # ELDTrainDataset's flips / transpose / clip (sid_dataset.py:340-356) fused into the noise kernel:
             # both the synthesised input and the target come back augmented, one pass over the frames

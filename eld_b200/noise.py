@@ -99,11 +99,13 @@ class NoiseModelBase:
         return np.random.RandomState(np.random.SeedSequence([int(self.seed) & 0xFFFFFFFF, int(self.seed) >> 32,
                                                              int(fid) & 0xFFFFFFFF, int(fid) >> 32]).generate_state(4))
 
-    def frame_params(self, fid0, n):
+    def frame_params(self, fid0, n, burst=1):
         """_sample_params (noise.py:201-225, same call order and distributions) for global frames fid0 .. fid0+n-1, each
         from its own RandomState seeded by (self.seed, frame id) - not from numpy's global stream, which every rank of
-        a data-parallel job would replay identically."""
-        return [self._sample_params_any(rng=self._frame_rng(fid0 + i)) for i in range(n)]
+        a data-parallel job would replay identically.  burst = k reproduces SynDataset's burst semantics
+        (dataset/sid_dataset.py:269-275: ONE _sample_params() for the k frames of a burst, fresh pixel noise per frame):
+        frames f with the same f // k share their parameter tuple, their Philox streams stay distinct."""
+        return [self._sample_params_any(rng=self._frame_rng((fid0 + i) // burst if burst > 1 else fid0 + i)) for i in range(n)]
 
     def frame_augment(self, fid0, n):
         """ELDTrainDataset's three coin flips (sid_dataset.py:344-350) per global frame id, same order."""

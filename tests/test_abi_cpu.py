@@ -176,3 +176,14 @@ def test_grad_buckets_partition_the_flat_gradient():
     assert b[1][0] == off.value and b[3][0] == 0       # ... bottleneck at conv5_1.weight, the last bucket at conv1_1.weight
     lib.eld_unet_param_offset(b'conv2_1', 0, c.byref(off), c.byref(cnt))
     assert b[2][0] == off.value and b[3][1] == off.value   # encoder bucket conv2_1..conv4_2; conv1_1 + conv1_2 travel last
+
+
+def test_burst_frames_share_parameters():
+    """SynDataset (sid_dataset.py:269-275): one _sample_params() per burst of k frames.  frame_params(burst=k) gives the
+    frames f // k == const the same tuple, at any sharding of the burst over calls."""
+    from eld_b200.noise import NoiseModel
+    nm = NoiseModel('P+g', include=4, verbose=False, seed=7)
+    p = nm.frame_params(0, 8, burst=4)
+    assert p[0] == p[1] == p[2] == p[3] and p[4] == p[7] and p[0] != p[4]
+    assert nm.frame_params(2, 4, burst=4) == p[2:6]
+    assert nm.frame_params(0, 4) != p[:4]                     # burst = 1: every frame its own draw

@@ -30,7 +30,15 @@ def nets(torch):
     ours = arch.unet(4, 4).cuda()
     torch.manual_seed(2018)
     ref = UNetSeeInDarkRef(4, 4)
-    # the default init gives tiny outputs; scale the biases a little so every LeakyReLU branch is exercised
+    # the default init leaves most pre-activations on one side of LeakyReLU's kink: spread the biases (both nets,
+    # identically) so that both branches - and both values of the backward mask - carry real weight
+    g = torch.Generator().manual_seed(5)
+    with torch.no_grad():
+        for (k, p), (_, q) in zip(ref.named_parameters(), ours.named_parameters()):
+            if k.endswith('.bias'):
+                d = (torch.rand(p.shape, generator=g) - 0.5) * 0.2
+                p.add_(d)
+                q.add_(d.to(q.device))
     return ours, ref
 
 

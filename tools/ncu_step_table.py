@@ -40,7 +40,7 @@ i_name = 0
 for i, d in enumerate(per.values()):
     k = d['kernel'].replace('void ', '').replace('eld::', '').split('(')[0][:34]
     lay = ''
-    if names and not k.startswith('noise') and ('conv_umma' in k or 'wgrad' in k or 'maxpool' in k or 'head' in k or 'colsum' in k or 'pack_' in k or 'permute' in k):
+    if names and not k.startswith('noise') and ('conv_umma' in k or 'wgrad' in k or 'maxpool' in k or 'head' in k or 'colsum' in k or 'pack_' in k or 'permute' in k or 'first_conv' in k):
         lay = names[i_name] if i_name < len(names) else ''
         i_name += 1
     us = f(d, 'gpu__time_duration.sum') / 1e3
@@ -57,7 +57,7 @@ if len(sys.argv) > 3:
         k = d['kernel']
         by = f(d, 'dram__bytes_read.sum') + f(d, 'dram__bytes_write.sum')
         rows_out.append({'kernel': k.replace('void ', '').split('(')[0][:60], 'dram_bytes': by, 'us': f(d, 'gpu__time_duration.sum') / 1e3})
-        if 'conv_umma_kernel' in k or 'wgrad_conv_kernel' in k or 'wgrad_umma_kernel' in k:
+        if 'conv_umma_kernel' in k or 'wgrad_conv_kernel' in k or 'wgrad_umma_kernel' in k or 'first_conv' in k:
             tiles += by
         if 'noise_packed' in k:
             noise = by
