@@ -211,6 +211,20 @@ class UNetSeeInDark(nn.Module):
             self._ddp_ready = eng.value
             self._ddp_stream = torch.cuda.Stream(device=x.device)
             self._ddp_buckets = self.grad_buckets()
+            if group is None and getattr(self, '_ddp_group', None) is None:
+                # A communicator of its own for the gradient exchange, limited to a few CTAs: the all-reduce kernels run
+                # UNDER the persistent one-CTA-per-SM tiles, and every SM they occupy delays a tile kernel's slowest CTA.
+                # The exchange is hidden behind backward, so its own speed is worth less than the SMs it leaves alone.
+                import os
+                ctas = int(os.environ.get('ELD_NCCL_MAX_CTAS', '0'))
+                self._ddp_group = False
+                if ctas > 0:
+                    opts = dist.ProcessGroupNCCL.Options()
+                    opts.config.max_ctas = ctas
+                    opts.config.min_ctas = min(ctas, 4)
+                    self._ddp_group = dist.new_group(pg_options=opts)
+        if group is None and getattr(self, '_ddp_group', None):
+            group = self._ddp_group
         ev = (lambda: torch.cuda.Event(enable_timing=True)) if timeline is not None else None
         if ev:
             timeline['step_start'] = ev(); timeline['step_start'].record()
@@ -229,11 +243,21 @@ class UNetSeeInDark(nn.Module):
                     works[-1].wait()      # (timeline mode only) the side stream waits for this bucket so its end can be stamped
                     e1 = ev(); e1.record(self._ddp_stream)
                     timeline['buckets'].append((e0, e1, cnt * 4))
-        for wk in works:
-            wk.wait()                     # stream-side wait: the current stream waits for the NCCL kernels
         if ev:
+            for wk in works:
+                wk.wait()
             timeline['allreduce_joined'] = ev(); timeline['allreduce_joined'].record()
+            works = []
+        # FusedAdam.step joins them bucket by bucket: Adam on the first buckets runs while the last, tiny one (conv1_*:
+        # final only when backward ends, its all-reduce pure latency) is still in flight
+        self._pending_allreduce = [(off, cnt, wk) for (off, cnt), wk in zip(self._ddp_buckets, works)]
         return out, loss
+
+    def join_allreduce(self):
+        """make the current stream wait for every outstanding bucket (callers that read .grad right after train_step_ddp)"""
+        for _, _, wk in getattr(self, '_pending_allreduce', []) or []:
+            wk.wait()
+        self._pending_allreduce = []
 
     def _profile(self, eng, run, steps):
         import numpy as np
@@ -295,10 +319,28 @@ class FusedAdam(torch.optim.Optimizer):
             self.v = torch.zeros_like(self.net.flat_params)
         self.t += 1
         p = self.net.flat_params
-        _lib.check(_lib.load().eld_adam_step(_lib.ctx(p.device.index or 0), p.data_ptr(), self.net.flat_grads.data_ptr(),
-                                             self.m.data_ptr(), self.v.data_ptr(), p.numel(), float(g['lr']),
-                                             float(g['betas'][0]), float(g['betas'][1]), float(g['eps']),
-                                             float(g['weight_decay']), self.t, float(grad_scale), _st()), 'eld_adam_step')
+
+        def adam(off, cnt):
+            _lib.check(_lib.load().eld_adam_step(_lib.ctx(p.device.index or 0), p.data_ptr() + 4 * off,
+                                                 self.net.flat_grads.data_ptr() + 4 * off, self.m.data_ptr() + 4 * off,
+                                                 self.v.data_ptr() + 4 * off, cnt, float(g['lr']),
+                                                 float(g['betas'][0]), float(g['betas'][1]), float(g['eps']),
+                                                 float(g['weight_decay']), self.t, float(grad_scale), _st()), 'eld_adam_step')
+        pend = getattr(self.net, '_pending_allreduce', None)
+        if pend:
+            # data parallel: buckets arrive in backward-completion order and tile the buffer from its end towards its start;
+            # everything but the last bucket in ONE launch, then the last (tiny) bucket when its all-reduce has landed
+            self.net._pending_allreduce = []
+            for _, _, wk in pend[:-1]:
+                wk.wait()
+            lo = min(off for off, _, _ in pend[:-1]) if len(pend) > 1 else p.numel()
+            if lo < p.numel():
+                adam(lo, p.numel() - lo)
+            pend[-1][2].wait()
+            if lo > 0:
+                adam(0, lo)
+        else:
+            adam(0, p.numel())
 
     def zero_grad(self, set_to_none=False):
         self.net.flat_grads.zero_()

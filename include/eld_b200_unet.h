@@ -94,9 +94,10 @@ int    eld_unet_set_loss(eld_unet* u, int kind);
  * eld_unet_grad_buckets() = 4 contiguous ranges in backward-completion order (decoder upv6..conv10_1, bottleneck
  * conv5_*, encoder conv2_1..conv4_2, first layer conv1_1..conv1_2); offsets[2k], offsets[2k+1] = first element, element
  * count of bucket k.
- * After eld_unet_bucket_events(u, 1) every eld_unet_train_step records an event on its stream when bucket k is final;
- * eld_unet_wait_bucket makes `stream` (the caller's communication stream) wait for it - the caller then all-reduces
- * grads[offset, offset+count) there while the rest of backward runs, and runs Adam after the last bucket. */
+ * After eld_unet_bucket_events(u, 1) every eld_unet_train_step records an event on its stream when bucket k of `grads`
+ * is final; eld_unet_wait_bucket makes `stream` (the caller's communication stream) wait for it - the caller then
+ * all-reduces grads[offset, offset+count) there while the rest of backward runs, and runs Adam on a bucket once its
+ * all-reduce has joined the compute stream. */
 int    eld_unet_grad_buckets(size_t* offsets, int max_offsets);      /* returns the bucket count (4) */
 int    eld_unet_bucket_events(eld_unet* u, int enable);
 int    eld_unet_wait_bucket(eld_unet* u, int bucket, void* stream);

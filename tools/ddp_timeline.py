@@ -20,6 +20,24 @@ net = arch.unet(4, 4).cuda()
 opt = arch.FusedAdam(net, lr=1e-4)
 x = torch.rand(8, 4, 512, 512, device='cuda')
 t = torch.rand(8, 4, 512, 512, device='cuda')
+# correctness first: the bucketed, overlapped exchange must equal one blocking all-reduce of the locally computed gradient
+torch.manual_seed(100 + rank)
+xr = torch.rand(8, 4, 512, 512, device='cuda')
+net.train_step(xr, t)
+want = net.flat_grads.clone()
+dist.all_reduce(want)
+net.train_step_ddp(xr, t)
+net.join_allreduce()
+torch.cuda.synchronize()
+got = net.flat_grads.clone()
+rel = ((got - want).norm() / want.norm()).item()
+peers = [torch.empty_like(got) for _ in range(world)]
+dist.all_gather(peers, got)
+same = all(torch.equal(peers[0], q) for q in peers)
+if rank == 0:
+    print('bucketed all-reduce vs blocking all-reduce of the same local gradients: rel-L2 %.2e (fp32 atomics reorder the local sums); '
+          'identical on all %d ranks: %s' % (rel, world, same))
+assert rel < 1e-3 and same
 for _ in range(5):
     net.train_step_ddp(x, t)
     opt.step(grad_scale=1.0 / world)
