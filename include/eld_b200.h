@@ -75,7 +75,8 @@ typedef struct eld_noise_params {
 /* Random stream (identical in the CUDA kernel and in oracle/eld_oracle.c):
  *   Philox4x32-10, key = (seed_lo, seed_hi), counter = (a, (domain<<16)|(c<<8)|d, frame_lo, frame_hi)
  *   with frame = frame_id0 + n the GLOBAL frame id - so the synthetic stream does not depend on
- *   how frames are sharded over GPUs.  See DESIGN.md "random stream".
+ *   how frames are sharded over GPUs.  See DESIGN.md "random stream".  Normals are Box-Muller on 23-bit
+ *   uniforms: |n| <= 5.77 (numpy's polar method is unbounded; the truncated tail has probability 8e-9 per draw).
  *
  * clean/noisy: packed float32 [n][4][h][w] (the layout NoiseModelBase.__call__ receives).
  * params: HOST pointer to n entries (copied into the launch; no device sync).
