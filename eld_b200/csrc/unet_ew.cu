@@ -169,12 +169,16 @@ __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 
-// walks pixel indices pb, pb + stride, ... as (image n, in-plane offset l) without a 64-bit division per step
-struct PixWalk {
-    size_t n, l, plane, stride;
-    __device__ PixWalk(size_t p0, size_t plane_, size_t stride_) : n(p0 / plane_), l(p0 % plane_), plane(plane_), stride(stride_) {}
-    __device__ __forceinline__ void next() { l += stride; while (l >= plane) { l -= plane; ++n; } }
-    __device__ __forceinline__ size_t pix() const { return n * plane + l; }
+// One thread's walk over its pixels p0, p0 + stride, ...: everything the loop needs as 32-bit offsets that advance by
+// additions (ncu r02: the size_t / division-free-but-64-bit version spent ~200 of its 340 instructions per pixel on index
+// arithmetic and the kernel was issue-bound at 68 %).  a_off = p * 32 (+ 8q), t_off = (n * cout + q) * plane + l.
+struct PixWalk32 {
+    uint32_t p, l, a_off, t_off;
+    __device__ __forceinline__ void next(uint32_t stride, uint32_t plane, uint32_t t_wrap)
+    {
+        p += stride; l += stride; a_off += stride * 32u; t_off += stride;
+        while (l >= plane) { l -= plane; t_off += t_wrap; }      // next image: skip the other cout - 1 planes
+    }
 };
 
 template <bool TRAIN>
@@ -216,38 +220,40 @@ head_kernel(const __nv_bfloat16* __restrict__ a, const float* __restrict__ w, co
 #pragma unroll
             for (int j = 0; j < 8; ++j) pdw[co][j] = 0.f;
     }
-    const size_t total = (size_t)n_img * plane;
-    constexpr int kPix = kHeadThreads / 4;
-    const size_t stride = (size_t)gridDim.x * kPix;
+    const uint32_t total = (uint32_t)n_img * (uint32_t)plane, plane32 = (uint32_t)plane;
+    constexpr uint32_t kPix = kHeadThreads / 4;
+    const uint32_t stride = gridDim.x * kPix;
+    const uint32_t t_wrap = (uint32_t)(cout - 1) * plane32;
     // block-uniform trip count (the shuffles below need whole warps); a ragged tail only masks the memory ops.
-    // `first` = this thread's pixel in the block's first group; a thread past the end clamps to the last pixel.
-    const size_t first = (size_t)blockIdx.x * kPix + (tid >> 2);
-    const size_t iters = (size_t)blockIdx.x * kPix < total ? (total - (size_t)blockIdx.x * kPix + stride - 1) / stride : 0;
-    PixWalk load_w(first < total ? first : total - 1, plane, stride), use_w(first < total ? first : total - 1, plane, stride);
-    size_t load_p = first, use_p = first;
-    auto issue = [&](size_t it) {
+    // `first` = this thread's pixel in the block's first group; a thread past the end parks on the last pixel.
+    const uint32_t blk0 = blockIdx.x * kPix;
+    const uint32_t iters = blk0 < total ? (total - blk0 + stride - 1) / stride : 0;
+    const uint32_t first = blk0 + (uint32_t)(tid >> 2);
+    PixWalk32 ld, us;
+    {
+        const uint32_t p0 = first < total ? first : total - 1, n0 = p0 / plane32, l0 = p0 - n0 * plane32;
+        ld.p = first; ld.l = l0; ld.a_off = p0 * 32u + (uint32_t)q * 8u; ld.t_off = (n0 * (uint32_t)cout + (uint32_t)qa) * plane32 + l0;
+        us = ld;
+    }
+    auto issue = [&](uint32_t it) {
         if (it < iters) {
-            const bool ok = load_p < total;
-            const size_t p = ok ? load_w.pix() : total - 1;
-            const size_t n = ok ? load_w.n : (total - 1) / plane, l = ok ? load_w.l : (total - 1) % plane;
-            cp_async16(&ring_a[it % kHeadStages][tid], reinterpret_cast<const uint4*>(a + p * 32) + q);
-            if (TRAIN) cp_async4(&ring_t[it % kHeadStages][tid], target + (n * cout + qa) * plane + l);
-            if (ok) load_w.next();
-            load_p += stride;
+            const bool ok = ld.p < total;                       // (a parked thread keeps re-reading its last valid pixel)
+            cp_async16(&ring_a[it % kHeadStages][tid], a + ld.a_off);
+            if (TRAIN) cp_async4(&ring_t[it % kHeadStages][tid], target + ld.t_off);
+            if (ok && ld.p + stride < total) ld.next(stride, plane32, t_wrap); else ld.p += stride;
         }
         cp_async_commit();
     };
-    for (int st = 0; st < kHeadStages - 1; ++st) issue((size_t)st);
-    for (size_t it = 0; it < iters; ++it) {
+    for (uint32_t st = 0; st < kHeadStages - 1; ++st) issue(st);
+    for (uint32_t it = 0; it < iters; ++it) {
         issue(it + kHeadStages - 1);
         cp_async_wait<kHeadStages - 1>();
-        const bool valid = use_p < total;
-        const size_t p = valid ? use_w.pix() : total - 1;
-        const size_t oidx = valid ? (use_w.n * cout + qa) * plane + use_w.l : 0;
+        const bool valid = us.p < total;
+        const uint32_t p = valid ? us.a_off >> 5 : total - 1;   // a_off = p * 32 + 8q
+        const uint32_t oidx = us.t_off;
         const uint4 v = ring_a[it % kHeadStages][tid];
         const float tg = TRAIN ? ring_t[it % kHeadStages][tid] : 0.f;
-        if (valid) use_w.next();
-        use_p += stride;
+        if (valid && us.p + stride < total) us.next(stride, plane32, t_wrap); else us.p += stride;
         const uint32_t wv[4] = { v.x, v.y, v.z, v.w };
         float av[8];
 #pragma unroll
@@ -292,7 +298,7 @@ head_kernel(const __nv_bfloat16* __restrict__ a, const float* __restrict__ w, co
                 g1 *= (av[j + 1] > 0.f ? 1.0f : 0.2f);
                 zo[j >> 1] = pack_bf2(g0, g1);
             }
-            if (valid) reinterpret_cast<uint4*>(dz + p * 32)[q] = make_uint4(zo[0], zo[1], zo[2], zo[3]);
+            if (valid) reinterpret_cast<uint4*>(dz + (size_t)p * 32)[q] = make_uint4(zo[0], zo[1], zo[2], zo[3]);
         }
     }
     cp_async_wait<0>();
@@ -393,6 +399,7 @@ int launch_head(eld_ctx* ctx, const void* a, const float* w, const float* b, flo
                 float* dw, float* db, float* loss, int n, size_t plane, int cout, int l2_loss, cudaStream_t st)
 {
     const size_t total = (size_t)n * plane;
+    ELD_REQUIRE(total * 32 < (1ull << 31), "head kernel: %zu pixels exceed its 32-bit index range", total);
     const float inv = 1.0f / (float)(total * cout);
     if (target) {
         head_kernel<true><<<grid_for(total, 32 * 16, 4 * ctx->num_sms), kHeadThreads, 0, st>>>(
