@@ -59,14 +59,14 @@ __global__ void __launch_bounds__(256)
 maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restrict__ dskip, int a_pitch, int a_c0,
                    int s_pitch, int s_c0, const __nv_bfloat16* __restrict__ dP, __nv_bfloat16* __restrict__ dZ, int C, int n_img, int Ho, int Wo)
 {
-    const int groups = C / 16;
-    const size_t total = (size_t)n_img * Ho * Wo * groups;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int gch = i % groups;
-        size_t r = i / groups;
-        const int xo = r % Wo; r /= Wo;
-        const int yo = r % Ho;
-        const int n = r / Ho;
+    const uint32_t groups = (uint32_t)C / 16u;
+    const uint32_t total = (uint32_t)n_img * (uint32_t)Ho * (uint32_t)Wo * groups;      // 32-bit index math (launcher checks the range)
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const uint32_t gch = i % groups;
+        uint32_t r = i / groups;
+        const uint32_t xo = r % (uint32_t)Wo; r /= (uint32_t)Wo;
+        const uint32_t yo = r % (uint32_t)Ho;
+        const uint32_t n = r / (uint32_t)Ho;
         const size_t pix00 = ((size_t)n * 2 * Ho + 2 * yo) * (2 * Wo) + 2 * xo;
         const size_t offs[4] = { pix00, pix00 + 1, pix00 + (size_t)2 * Wo, pix00 + (size_t)2 * Wo + 1 };
         uint32_t a[4][8], s[4][8], dp[8];
@@ -376,6 +376,7 @@ int launch_maxpool_bwd(eld_ctx* ctx, const void* A, int a_pitch, int a_c0, const
     ELD_REQUIRE(C % 16 == 0 && a_pitch % 16 == 0 && a_c0 % 16 == 0 && s_pitch % 16 == 0 && s_c0 % 16 == 0,
                 "pool backward: channel counts, pitches and offsets must be multiples of 16 (256-bit accesses)");
     const size_t work = (size_t)n * Ho * Wo * (C / 16);
+    ELD_REQUIRE(work < (1ull << 31), "pool backward: %zu work items exceed the kernel's 32-bit index range", work);
     maxpool_bwd_kernel<<<grid_for(work, 256, 16 * ctx->num_sms), 256, 0, st>>>(
         static_cast<const __nv_bfloat16*>(A), static_cast<const __nv_bfloat16*>(dskip), a_pitch, a_c0, s_pitch, s_c0,
         static_cast<const __nv_bfloat16*>(dP), static_cast<__nv_bfloat16*>(dZ), C, n, Ho, Wo);
