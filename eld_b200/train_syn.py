@@ -22,15 +22,19 @@ from .noise import NoiseModel
 class SyntheticClean(torch.utils.data.Dataset):
     """stands in for LMDBDataset('SID_Sony_Raw.db') (lmdb_dataset.py:8-41): 4x512x512 f32 in [0,1]"""
 
-    def __init__(self, n, seed, h=512, w=512):
-        self.n, self.seed, self.h, self.w = n, seed, h, w
+    def __init__(self, n, seed, h=512, w=512, meta=False):
+        self.n, self.seed, self.h, self.w, self.meta = n, seed, h, w, meta
 
     def __len__(self):
         return self.n
 
     def __getitem__(self, i):
         g = torch.Generator().manual_seed(self.seed * 1000003 + i)
-        return {'target': torch.rand(4, self.h, self.w, generator=g)}
+        item = {'target': torch.rand(4, self.h, self.w, generator=g)}
+        if self.meta:       # LMDBDataset.meta = per-frame (wb, ccm) (lmdb_dataset.py:24-26), read by ISPDataset (sid_dataset.py:303)
+            item['wb'] = torch.tensor([1.8 + 0.4 * torch.rand((), generator=g).item(), 1.0, 1.5 + 0.4 * torch.rand((), generator=g).item(), 1.0])
+            item['ccm'] = torch.eye(3) * 1.5 - 0.25 * (1 - torch.eye(3))
+        return item
 
 
 def main():
@@ -40,6 +44,10 @@ def main():
     ap.add_argument('--epochs', type=int, default=1); ap.add_argument('--iters', type=int, default=20)
     ap.add_argument('--lr', type=float, default=1e-4); ap.add_argument('--name', default='eld_b200_syn')
     ap.add_argument('--no-augment', action='store_true', help='skip ELDTrainDataset flips/transpose (sid_dataset.py:340-352)')
+    ap.add_argument('--loss', default='l1', choices=['l1', 'l2'])             # options/eld/train_options.py: --loss
+    ap.add_argument('--stage_in', default='raw', choices=['raw', 'srgb'])     # train_syn.py:55-58 (ISPDataset branch)
+    ap.add_argument('--stage_out', default='raw', choices=['raw'])            # an sRGB TARGET needs the rendered LMDB
+    ap.add_argument('--num_burst', type=int, default=1)                       # SynDataset(num_burst=...), sid_dataset.py:269-275
     a = ap.parse_args()
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
@@ -49,9 +57,10 @@ def main():
     rank = dist.get_rank() if world > 1 else 0
     torch.manual_seed(a.seed); np.random.seed(a.seed)                        # base_options.py:31-34
     opt = models.default_opt(name=a.name, gpu_ids=[local], noise=a.noise, include=a.include, batchSize=a.batchSize,
-                             lr=a.lr, noise_on_gpu=True, augment_on_gpu=not a.no_augment, defer_loss_sync=True)
+                             lr=a.lr, noise_on_gpu=True, augment_on_gpu=not a.no_augment and a.stage_in == 'raw', defer_loss_sync=True,
+                             loss=a.loss, stage_in=a.stage_in, stage_out=a.stage_out, num_burst=a.num_burst)
     noise_model = NoiseModel(model=opt.noise, include=opt.include, seed=a.seed, verbose=rank == 0)   # train_syn.py:38
-    ds = SyntheticClean(a.iters * a.batchSize * world, a.seed)
+    ds = SyntheticClean(a.iters * a.batchSize * world, a.seed, meta=a.stage_in == 'srgb')
     sampler = torch.utils.data.distributed.DistributedSampler(ds, world, rank, shuffle=True) if world > 1 else None
     loader = torch.utils.data.DataLoader(ds, batch_size=a.batchSize, shuffle=sampler is None, sampler=sampler,
                                          num_workers=2, pin_memory=True)

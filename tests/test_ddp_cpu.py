@@ -53,3 +53,44 @@ def test_two_rank_frame_ids_and_grad_average(tmp_path):
         for step in range(3):
             fid0 = (step * world + rank) * B
             assert np.array_equal(got[step], single[fid0:fid0 + B])           # bit-equal across world sizes
+
+
+def _bucket_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, REPO)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    import ctypes as c
+    from eld_b200 import _lib
+    lib = _lib.load()
+    arr = (c.c_size_t * 16)()
+    k = lib.eld_unet_grad_buckets(arr, 16)
+    buckets = [(int(arr[2 * i]), int(arr[2 * i + 1])) for i in range(k)]
+    n = lib.eld_unet_param_count()
+    g = torch.Generator().manual_seed(1000 + rank)
+    grad = torch.randn(n, generator=g)
+    whole = grad.clone()
+    dist.all_reduce(whole)                                   # one blocking all-reduce of the flat gradient
+    # the product's host logic (UNetSeeInDark.train_step_ddp + FusedAdam.step): one async all-reduce per bucket, in
+    # backward-completion order, then "Adam" on [lo, n) after all but the last bucket and on [0, lo) after the last
+    works = [(off, cnt, dist.all_reduce(grad[off:off + cnt], async_op=True)) for off, cnt in buckets]
+    updated = torch.zeros(n, dtype=torch.bool)
+    for _, _, wk in works[:-1]:
+        wk.wait()
+    lo = min(off for off, _, _ in works[:-1])
+    updated[lo:] = True
+    works[-1][2].wait()
+    assert works[-1][0] == 0 and works[-1][1] == lo          # the last bucket is exactly the untouched head of the buffer
+    updated[:lo] = True
+    if rank == 0:
+        torch.save({'same': torch.equal(grad, whole), 'all': bool(updated.all()), 'k': k}, out)
+    dist.destroy_process_group()
+
+
+def test_bucketed_allreduce_equals_one_allreduce(tmp_path):
+    """SURVEY 8e host logic at world size 2 (gloo): bucket-wise all-reduce of the flat gradient == one all-reduce of the
+    whole buffer, and the two Adam launches of the data-parallel step cover every parameter exactly once."""
+    out = str(tmp_path / 'b.pt')
+    port = 29700 + (os.getpid() % 2000)
+    mp.spawn(_bucket_worker, args=(2, port, out), nprocs=2, join=True)
+    r = torch.load(out, weights_only=False)
+    assert r['same'] and r['all'] and r['k'] == 4
