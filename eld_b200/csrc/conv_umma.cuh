@@ -53,11 +53,20 @@ struct ConvGemmParams {
     int cout_shift;       // EPI_SHUFFLE: log2(cout) (cout must be a power of two)
     __nv_bfloat16* pool_out;   // optional fused MaxPool2d(2) of the (activated) output: bf16 NHWC [n][H/2][W/2][pool_pitch]
     int pool_pitch;
+    uint32_t* pool_code;       // optional (training): 32 bytes per (pooled pixel, 32 channels) = which window element won and the
+                               // four signs, all the pool backward needs of the activation (unet_ew.cu maxpool_bwd_code_kernel)
     __nv_bfloat16* out2;  // EPI_STORE split store: GEMM columns >= out_split go to out2[pix * out2_pitch + (col - out_split)]
     int out2_pitch, out_split;   // (planar halves of a concat gradient); out_split % 32 == 0, 0 = off
     long long* prof;      // PROF instantiation only
     int bias_smem_off;    // byte offset (from the 1024-aligned base) of the per-CTA bias copy
 };
+
+// max of two packed bf16 pairs (HMNMX2.BF16)
+__device__ __forceinline__ uint32_t bf2_max(uint32_t a, uint32_t b)
+{
+    const __nv_bfloat162 m = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+    return *reinterpret_cast<const uint32_t*>(&m);
+}
 
 // Two tiles at once: consecutive MMAs alternate between two accumulators, so an N = 32 tile's chain of
 // 18 dependent accumulates no longer runs at MMA latency (measured: ~100 cycles per dependent N=32 MMA).
@@ -548,33 +557,48 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const ConvGemmParams p
                         }
                     }
                 }
-                if (p.pool_out) {
-                    // MaxPool2d(2) (Unet.py:13,51-63) fused: the 2x2 window of pixel (x, y) lives in lanes ^1 (x) and ^tile_w (y)
-                    // of this warp.  max commutes with the monotone bf16 rounding, so pooling the fp32 values and rounding once
-                    // equals pooling the stored bf16 activations.  H, W and the tile origin are even: a window is wholly in or out.
-                    float pm[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float a = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 1));
-                        pm[j] = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, p.tile_w));
-                    }
-                    if (in_img && !((x | y) & 1)) {
-                        __nv_bfloat16* q4 = p.pool_out + ((size_t)(img * (p.H >> 1) + (y >> 1)) * (p.W >> 1) + (x >> 1)) * p.pool_pitch + col;
-                        uint32_t pw[16];
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const __nv_bfloat162 h = __floats2bfloat162_rn(pm[2 * j], pm[2 * j + 1]);
-                            pw[j] = *reinterpret_cast<const uint32_t*>(&h);
-                        }
-                        ptx::st_global_v8(q4, pw);
-                        ptx::st_global_v8(q4 + 16, pw + 8);
-                    }
-                }
+                // round once; the pool below works on the rounded (= stored) values
                 uint32_t wv[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
                     wv[j] = *reinterpret_cast<const uint32_t*>(&h);
+                }
+                if (p.pool_out) {
+                    // MaxPool2d(2) (Unet.py:13,51-63) fused: the 2x2 window of pixel (x, y) lives in lanes ^1 (x) and ^tile_w (y)
+                    // of this warp; packed bf16x2 max of the stored values.  H, W and the tile origin are even: a window is
+                    // wholly in or out.
+                    uint32_t pw[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const uint32_t a = bf2_max(wv[j], __shfl_xor_sync(0xffffffffu, wv[j], 1));
+                        pw[j] = bf2_max(a, __shfl_xor_sync(0xffffffffu, a, p.tile_w));
+                    }
+                    const bool origin = in_img && !((x | y) & 1);
+                    const size_t ppix = (size_t)(img * (p.H >> 1) + (y >> 1)) * (p.W >> 1) + (x >> 1);
+                    if (origin) {
+                        __nv_bfloat16* q4 = p.pool_out + ppix * p.pool_pitch + col;
+                        ptx::st_global_v8(q4, pw);
+                        ptx::st_global_v8(q4 + 16, pw + 8);
+                    }
+                    if (p.pool_code) {
+                        // per lane two 32-bit masks over its 32 channels: "is not the window's maximum" and "is negative"
+                        // (channel 2j -> bit j, channel 2j+1 -> bit 16+j); the window's origin lane collects the four lanes'
+                        // masks in the order the backward walks the window: (0,0) (0,1) (1,0) (1,1)
+                        uint32_t nm = 0, sg = 0;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const uint32_t d = wv[j] ^ pw[j];
+                            nm = (nm >> 1) | ((((d & 0x7FFF7FFFu) + 0x7FFF7FFFu) | d) & 0x80008000u);
+                            sg = (sg >> 1) | (wv[j] & 0x80008000u);
+                        }
+                        uint32_t code[8];
+                        code[0] = nm; code[4] = sg;
+                        code[1] = __shfl_xor_sync(0xffffffffu, nm, 1);          code[5] = __shfl_xor_sync(0xffffffffu, sg, 1);
+                        code[2] = __shfl_xor_sync(0xffffffffu, nm, p.tile_w);   code[6] = __shfl_xor_sync(0xffffffffu, sg, p.tile_w);
+                        code[3] = __shfl_xor_sync(0xffffffffu, nm, p.tile_w | 1); code[7] = __shfl_xor_sync(0xffffffffu, sg, p.tile_w | 1);
+                        if (origin) ptx::st_global_v8(p.pool_code + (ppix * (size_t)(p.pool_pitch >> 5) + (size_t)(col >> 5)) * 8, code);
+                    }
                 }
                 if (!in_img || (p.dbg & 1)) continue;
                 // 64 bytes per pixel = two full 32-byte sectors, one 256-bit store each (four 16-byte stores sent four

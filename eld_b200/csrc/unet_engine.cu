@@ -191,6 +191,7 @@ struct eld_unet {
         *a6_1, *a6_2, *a7_1, *a7_2, *a8_1, *a8_2, *a9_1, *a9_2;
     __nv_bfloat16 *dz9_2, *dz9_1, *dcat9, *dz8_2, *dz8_1, *dcat8, *dz7_2, *dz7_1, *dcat7, *dz6_2, *dz6_1, *dcat6,
         *dz5_2, *dz5_1, *dp4, *dz4_2, *dz4_1, *dp3, *dz3_2, *dz3_1, *dp2, *dz2_2, *dz2_1, *dp1, *dz1_2, *dz1_1;
+    __nv_bfloat16 *pc1 = nullptr, *pc2 = nullptr, *pc3 = nullptr, *pc4 = nullptr;   // pool codes, 1 byte per pooled element (training)
     __nv_bfloat16* packed;
     float* gtmp = nullptr;
     PackTable table;
@@ -232,6 +233,7 @@ static size_t layout(eld_unet* u, char* base, bool train)
         take(&u->dz3_2, 2, 128); take(&u->dz3_1, 2, 128); take(&u->dp2, 2, 64);
         take(&u->dz2_2, 1, 64); take(&u->dz2_1, 1, 64); take(&u->dp1, 1, 32);
         take(&u->dz1_2, 0, 32); take(&u->dz1_1, 0, 32);
+        take(&u->pc1, 1, 16); take(&u->pc2, 2, 32); take(&u->pc3, 3, 64); take(&u->pc4, 4, 128);
     }
     // packed weights
     size_t pk = 0;
@@ -440,7 +442,7 @@ struct Runner {
     const float* bias(int i) const { return params + u->L[i].b_off; }
 
     // pool_dst != nullptr: MaxPool2d(2) of the output fused into the tile's epilogue (pooled tensor has cout channels)
-    int conv(int li, const void* x, int xp, int xc0, void* y, int yp, int yc0, int lvl, void* pool_dst = nullptr) const
+    int conv(int li, const void* x, int xp, int xc0, void* y, int yp, int yc0, int lvl, void* pool_dst = nullptr, void* pool_code = nullptr) const
     {
         const Layer& l = u->L[li];
         GemmOp op{};
@@ -448,7 +450,7 @@ struct Runner {
         op.n_img = u->n; op.H = u->H >> lvl; op.W = u->W >> lvl;
         op.b = wf(li); op.n_total = l.cout; op.cout = l.cout;
         op.epi_mode = EPI_STORE; op.act = ACT_LRELU; op.out = y; op.out_pitch = yp; op.out_c0 = yc0; op.bias = bias(li);
-        op.pool_out = pool_dst; op.pool_pitch = l.cout;
+        op.pool_out = pool_dst; op.pool_pitch = l.cout; op.pool_code = pool_code;
         const double px = (double)u->n * op.H * op.W;
         Scope sc(u, st, l.name, "fprop", 2.0 * px * l.cout * 9 * l.cin, px * 2 * (l.cin + l.cout) + 18.0 * l.cin * l.cout);
         return launch_conv_gemm(ctx(), op, st);
@@ -536,10 +538,12 @@ struct Runner {
         return launch_maxpool(ctx(), in, pitch, c0, out, C, u->n, u->H >> lvl_out, u->W >> lvl_out, st);
     }
     // A = the interleaved concat buffer's skip half (pitch 2C, offset C); dskip = the PLANAR skip half of its gradient
-    int pool_bwd(const void* A, int pitch, int c0, const void* dskip, const void* dP, void* dZ, int C, int lvl_out) const
+    // code != nullptr: the forward tile left the argmax + sign code, the activation is not read again
+    int pool_bwd(const void* A, int pitch, int c0, const void* dskip, const void* dP, void* dZ, int C, int lvl_out, const void* code) const
     {
         const double pxo = (double)u->n * (u->H >> lvl_out) * (u->W >> lvl_out);
-        Scope sc(u, st, "pool", "bwd", 0.0, pxo * C * 2 * 13);
+        Scope sc(u, st, "pool", "bwd", 0.0, pxo * C * (code ? 2 * 9 + 1 : 2 * 13));
+        if (code) return launch_maxpool_bwd_code(ctx(), code, dskip, C, 0, dP, dZ, C, u->n, u->H >> lvl_out, u->W >> lvl_out, st);
         return launch_maxpool_bwd(ctx(), A, pitch, c0, dskip, C, 0, dP, dZ, C, u->n, u->H >> lvl_out, u->W >> lvl_out, st);
     }
     // second (skip) half of a planar concat gradient: [n][h][w][C] right behind the up half
@@ -592,13 +596,13 @@ struct Runner {
             Scope sc(u, st, "conv1_1", "fprop", 2.0 * px * 32 * 9 * U->cin0, px * (4 * U->cin0 + 64));
             TRY(launch_first_conv(ctx(), x, U->cin0, wf(I_C11), bias(I_C11), U->a1_1, 32, U->n, U->H, U->W, st));
         }
-        if (fuse_pool) { TRY(conv(I_C12, U->a1_1, 32, 0, U->cat9, 64, 32, 0, U->p1)); } else { TRY(conv(I_C12, U->a1_1, 32, 0, U->cat9, 64, 32, 0)); TRY(pool(U->cat9, 64, 32, U->p1, 32, 1)); }      // + pool (Unet.py:51)
+        if (fuse_pool) { TRY(conv(I_C12, U->a1_1, 32, 0, U->cat9, 64, 32, 0, U->p1, U->pc1)); } else { TRY(conv(I_C12, U->a1_1, 32, 0, U->cat9, 64, 32, 0)); TRY(pool(U->cat9, 64, 32, U->p1, 32, 1)); }      // + pool (Unet.py:51)
         TRY(conv(I_C21, U->p1, 32, 0, U->a2_1, 64, 0, 1));
-        if (fuse_pool) { TRY(conv(I_C22, U->a2_1, 64, 0, U->cat8, 128, 64, 1, U->p2)); } else { TRY(conv(I_C22, U->a2_1, 64, 0, U->cat8, 128, 64, 1)); TRY(pool(U->cat8, 128, 64, U->p2, 64, 2)); }     // + pool (Unet.py:55)
+        if (fuse_pool) { TRY(conv(I_C22, U->a2_1, 64, 0, U->cat8, 128, 64, 1, U->p2, U->pc2)); } else { TRY(conv(I_C22, U->a2_1, 64, 0, U->cat8, 128, 64, 1)); TRY(pool(U->cat8, 128, 64, U->p2, 64, 2)); }     // + pool (Unet.py:55)
         TRY(conv(I_C31, U->p2, 64, 0, U->a3_1, 128, 0, 2));
-        if (fuse_pool) { TRY(conv(I_C32, U->a3_1, 128, 0, U->cat7, 256, 128, 2, U->p3)); } else { TRY(conv(I_C32, U->a3_1, 128, 0, U->cat7, 256, 128, 2)); TRY(pool(U->cat7, 256, 128, U->p3, 128, 3)); }   // + pool (Unet.py:59)
+        if (fuse_pool) { TRY(conv(I_C32, U->a3_1, 128, 0, U->cat7, 256, 128, 2, U->p3, U->pc3)); } else { TRY(conv(I_C32, U->a3_1, 128, 0, U->cat7, 256, 128, 2)); TRY(pool(U->cat7, 256, 128, U->p3, 128, 3)); }   // + pool (Unet.py:59)
         TRY(conv(I_C41, U->p3, 128, 0, U->a4_1, 256, 0, 3));
-        if (fuse_pool) { TRY(conv(I_C42, U->a4_1, 256, 0, U->cat6, 512, 256, 3, U->p4)); } else { TRY(conv(I_C42, U->a4_1, 256, 0, U->cat6, 512, 256, 3)); TRY(pool(U->cat6, 512, 256, U->p4, 256, 4)); }   // + pool (Unet.py:63)
+        if (fuse_pool) { TRY(conv(I_C42, U->a4_1, 256, 0, U->cat6, 512, 256, 3, U->p4, U->pc4)); } else { TRY(conv(I_C42, U->a4_1, 256, 0, U->cat6, 512, 256, 3)); TRY(pool(U->cat6, 512, 256, U->p4, 256, 4)); }   // + pool (Unet.py:63)
         TRY(conv(I_C51, U->p4, 256, 0, U->a5_1, 512, 0, 4));
         TRY(conv(I_C52, U->a5_1, 512, 0, U->a5_2, 512, 0, 4));
         TRY(deconv(I_UP6, U->a5_2, 512, U->cat6, 512, 4));
@@ -615,7 +619,8 @@ struct Runner {
     int backward(const float* x, float* g) const
     {
         eld_unet* U = u;
-        // decoder
+        // the fused pools leave their codes; ELD_POOL_BWD_FROM_ACT=1 keeps the backward that re-reads the activations (A/B)
+        static const bool coded = getenv("ELD_NO_FUSED_POOL") == nullptr && getenv("ELD_POOL_BWD_FROM_ACT") == nullptr;
         TRY(conv_wgrad(I_C92, U->a9_1, 32, 0, U->dz9_2, g, 0));
         TRY(conv_dgrad(I_C92, U->dz9_2, U->dz9_1, 32, 0, U->a9_1, 32, 0, 0));
         TRY(conv_wgrad(I_C91, U->cat9, 64, 0, U->dz9_1, g, 0));
@@ -647,23 +652,23 @@ struct Runner {
         TRY(conv_wgrad(I_C51, U->p4, 256, 0, U->dz5_1, g, 4));
         TRY(finish_bucket(1, g));
         TRY(conv_dgrad(I_C51, U->dz5_1, U->dp4, 256, 0, nullptr, 0, 0, 4));
-        TRY(pool_bwd(U->cat6, 512, 256, skip_half(U->dcat6, 3, 256), U->dp4, U->dz4_2, 256, 4));
+        TRY(pool_bwd(U->cat6, 512, 256, skip_half(U->dcat6, 3, 256), U->dp4, U->dz4_2, 256, 4, coded ? U->pc4 : nullptr));
         TRY(conv_wgrad(I_C42, U->a4_1, 256, 0, U->dz4_2, g, 3));
         TRY(conv_dgrad(I_C42, U->dz4_2, U->dz4_1, 256, 0, U->a4_1, 256, 0, 3));
         TRY(conv_wgrad(I_C41, U->p3, 128, 0, U->dz4_1, g, 3));
         TRY(conv_dgrad(I_C41, U->dz4_1, U->dp3, 128, 0, nullptr, 0, 0, 3));
-        TRY(pool_bwd(U->cat7, 256, 128, skip_half(U->dcat7, 2, 128), U->dp3, U->dz3_2, 128, 3));
+        TRY(pool_bwd(U->cat7, 256, 128, skip_half(U->dcat7, 2, 128), U->dp3, U->dz3_2, 128, 3, coded ? U->pc3 : nullptr));
         TRY(conv_wgrad(I_C32, U->a3_1, 128, 0, U->dz3_2, g, 2));
         TRY(conv_dgrad(I_C32, U->dz3_2, U->dz3_1, 128, 0, U->a3_1, 128, 0, 2));
         TRY(conv_wgrad(I_C31, U->p2, 64, 0, U->dz3_1, g, 2));
         TRY(conv_dgrad(I_C31, U->dz3_1, U->dp2, 64, 0, nullptr, 0, 0, 2));
-        TRY(pool_bwd(U->cat8, 128, 64, skip_half(U->dcat8, 1, 64), U->dp2, U->dz2_2, 64, 2));
+        TRY(pool_bwd(U->cat8, 128, 64, skip_half(U->dcat8, 1, 64), U->dp2, U->dz2_2, 64, 2, coded ? U->pc2 : nullptr));
         TRY(conv_wgrad(I_C22, U->a2_1, 64, 0, U->dz2_2, g, 1));
         TRY(conv_dgrad(I_C22, U->dz2_2, U->dz2_1, 64, 0, U->a2_1, 64, 0, 1));
         TRY(conv_wgrad(I_C21, U->p1, 32, 0, U->dz2_1, g, 1));
         TRY(finish_bucket(2, g));
         TRY(conv_dgrad(I_C21, U->dz2_1, U->dp1, 32, 0, nullptr, 0, 0, 1));
-        TRY(pool_bwd(U->cat9, 64, 32, skip_half(U->dcat9, 0, 32), U->dp1, U->dz1_2, 32, 1));
+        TRY(pool_bwd(U->cat9, 64, 32, skip_half(U->dcat9, 0, 32), U->dp1, U->dz1_2, 32, 1, coded ? U->pc1 : nullptr));
         TRY(conv_wgrad(I_C12, U->a1_1, 32, 0, U->dz1_2, g, 0));
         TRY(conv_dgrad(I_C12, U->dz1_2, U->dz1_1, 32, 0, U->a1_1, 32, 0, 0));
         {

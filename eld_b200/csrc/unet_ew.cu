@@ -105,6 +105,54 @@ maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __r
     }
 }
 
+// Same backward from the 1-byte-per-pooled-element code the forward tile's epilogue leaves (conv_umma.cuh): per (pooled
+// pixel, 32 channels) eight words - "not the maximum" masks of the window's four pixels, then their sign masks
+// (channel 2j -> bit j, 2j+1 -> bit 16+j).  Reads 1/16 of what the activation itself costs (and the level-1 skip half
+// of an interleaved concat buffer cost double: 128-byte lines for 64 useful bytes).
+__global__ void __launch_bounds__(256)
+maxpool_bwd_code_kernel(const uint32_t* __restrict__ code, const __nv_bfloat16* __restrict__ dskip, int s_pitch, int s_c0,
+                        const __nv_bfloat16* __restrict__ dP, __nv_bfloat16* __restrict__ dZ, int C, int n_img, int Ho, int Wo)
+{
+    const uint32_t groups = (uint32_t)C / 16u;
+    const uint32_t total = (uint32_t)n_img * (uint32_t)Ho * (uint32_t)Wo * groups;      // 32-bit index math (launcher checks the range)
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const uint32_t gch = i % groups;
+        const uint32_t ppix = i / groups;
+        uint32_t r = ppix;
+        const uint32_t xo = r % (uint32_t)Wo; r /= (uint32_t)Wo;
+        const uint32_t yo = r % (uint32_t)Ho;
+        const uint32_t n = r / (uint32_t)Ho;
+        const size_t pix00 = ((size_t)n * 2 * Ho + 2 * yo) * (2 * Wo) + 2 * xo;
+        const size_t offs[4] = { pix00, pix00 + 1, pix00 + (size_t)2 * Wo, pix00 + (size_t)2 * Wo + 1 };
+        uint32_t cw[8], s[4][8], dp[8];
+        ptx::ld_global_nc_v8(code + ((size_t)ppix * (groups >> 1) + (gch >> 1)) * 8, cw);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) ptx::ld_global_nc_v8(dskip + offs[k] * s_pitch + s_c0 + gch * 16, s[k]);
+        ptx::ld_global_nc_v8(dP + (size_t)ppix * C + gch * 16, dp);
+        // this thread's 16 channels are pairs 8*(gch&1) .. +7 of the chunk: bring their bits to positions 0..7 / 16..23
+        const uint32_t sh = (gch & 1u) * 8u;
+        const uint32_t m0 = cw[0] >> sh, m1 = cw[1] >> sh, m2 = cw[2] >> sh;
+        // one-hot "first maximum in window order" (a NaN window has no maximum: the last pixel takes it)
+        const uint32_t sel[4] = { ~m0, m0 & ~m1, m0 & m1 & ~m2, m0 & m1 & m2 };
+        const uint32_t neg[4] = { cw[4] >> sh, cw[5] >> sh, cw[6] >> sh, cw[7] >> sh };
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            uint32_t o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                // all-ones where this pixel won; slope = 0.6 + 0.4 * (+-1) = 1 or 0.2 from the sign
+                const uint32_t t_lo = (uint32_t)((int32_t)(sel[k] << (31 - j)) >> 31), t_hi = (uint32_t)((int32_t)(sel[k] << (15 - j)) >> 31);
+                const float g_lo = __uint_as_float((dp[j] << 16) & t_lo), g_hi = __uint_as_float((dp[j] & 0xFFFF0000u) & t_hi);
+                const float f_lo = __fmaf_rn(__uint_as_float(((neg[k] << (31 - j)) & 0x80000000u) | 0x3F800000u), 0.4f, 0.6f);
+                const float f_hi = __fmaf_rn(__uint_as_float(((neg[k] << (15 - j)) & 0x80000000u) | 0x3F800000u), 0.4f, 0.6f);
+                const __nv_bfloat162 h = __floats2bfloat162_rn((bf_lo(s[k][j]) + g_lo) * f_lo, (bf_hi(s[k][j]) + g_hi) * f_hi);
+                o[j] = *reinterpret_cast<const uint32_t*>(&h);
+            }
+            ptx::st_global_v8(dZ + offs[k] * C + gch * 16, o);
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // bias gradient: out[c] += sum over pixels of g[p][c0 + c]   (NHWC bf16, C % 8 == 0, C <= 512)
 // thread handles 8 channels of a pixel; block = (C/8) x (256/(C/8)) ; smem reduce; atomics per block.
@@ -379,6 +427,21 @@ int launch_maxpool_bwd(eld_ctx* ctx, const void* A, int a_pitch, int a_c0, const
     ELD_REQUIRE(work < (1ull << 31), "pool backward: %zu work items exceed the kernel's 32-bit index range", work);
     maxpool_bwd_kernel<<<grid_for(work, 256, 16 * ctx->num_sms), 256, 0, st>>>(
         static_cast<const __nv_bfloat16*>(A), static_cast<const __nv_bfloat16*>(dskip), a_pitch, a_c0, s_pitch, s_c0,
+        static_cast<const __nv_bfloat16*>(dP), static_cast<__nv_bfloat16*>(dZ), C, n, Ho, Wo);
+    ELD_CHECK_CUDA(cudaGetLastError());
+    count_launch(ctx);
+    return ELD_OK;
+}
+
+int launch_maxpool_bwd_code(eld_ctx* ctx, const void* code, const void* dskip, int s_pitch, int s_c0,
+                            const void* dP, void* dZ, int C, int n, int Ho, int Wo, cudaStream_t st)
+{
+    ELD_REQUIRE(C % 32 == 0 && s_pitch % 16 == 0 && s_c0 % 16 == 0,
+                "pool backward (coded): C must be a multiple of 32, pitches and offsets multiples of 16 (256-bit accesses)");
+    const size_t work = (size_t)n * Ho * Wo * (C / 16);
+    ELD_REQUIRE(work < (1ull << 31), "pool backward: %zu work items exceed the kernel's 32-bit index range", work);
+    maxpool_bwd_code_kernel<<<grid_for(work, 256, 16 * ctx->num_sms), 256, 0, st>>>(
+        static_cast<const uint32_t*>(code), static_cast<const __nv_bfloat16*>(dskip), s_pitch, s_c0,
         static_cast<const __nv_bfloat16*>(dP), static_cast<__nv_bfloat16*>(dZ), C, n, Ho, Wo);
     ELD_CHECK_CUDA(cudaGetLastError());
     count_launch(ctx);

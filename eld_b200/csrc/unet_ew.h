@@ -4,6 +4,8 @@
 
 namespace eld {
 int launch_maxpool(eld_ctx* ctx, const void* in, int in_pitch, int in_c0, void* out, int C, int n, int Ho, int Wo, cudaStream_t st);
+int launch_maxpool_bwd_code(eld_ctx* ctx, const void* code, const void* dskip, int s_pitch, int s_c0,
+                            const void* dP, void* dZ, int C, int n, int Ho, int Wo, cudaStream_t st);
 int launch_maxpool_bwd(eld_ctx* ctx, const void* A, int a_pitch, int a_c0, const void* dskip, int s_pitch, int s_c0,
                        const void* dP, void* dZ, int C, int n, int Ho, int Wo, cudaStream_t st);
 int launch_colsum(eld_ctx* ctx, const void* g, int pitch, int c0, int C, size_t npix, float* out, cudaStream_t st);

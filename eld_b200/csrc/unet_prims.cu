@@ -64,6 +64,9 @@ int launch_conv_gemm(eld_ctx* ctx, const GemmOp& op, cudaStream_t st)
     ELD_REQUIRE(op.pool_out == nullptr || (op.epi_mode == EPI_STORE && op.H % 2 == 0 && op.W % 2 == 0),
                 "conv tile: the fused max pool needs a plain store epilogue and even H, W");
     p.pool_out = static_cast<__nv_bfloat16*>(op.pool_out); p.pool_pitch = op.pool_pitch;
+    ELD_REQUIRE(op.pool_code == nullptr || (op.pool_out && op.pool_pitch % 32 == 0 && (reinterpret_cast<uintptr_t>(op.pool_code) & 31) == 0),
+                "conv tile: the pool code needs the fused pool, a multiple of 32 channels and a 32-byte aligned buffer");
+    p.pool_code = static_cast<uint32_t*>(op.pool_code);
     ELD_REQUIRE(op.out_split == 0 || (op.epi_mode == EPI_STORE && op.out2 && op.out_split % 32 == 0 && op.out2_pitch % 16 == 0 &&
                                      (reinterpret_cast<uintptr_t>(op.out2) & 31) == 0),
                 "conv tile: split store needs a plain store epilogue, a second tensor and a split at a multiple of 32 columns");

@@ -44,6 +44,7 @@ struct GemmOp {
     int aux_pitch, aux_c0;
     void* pool_out = nullptr;   // optional fused 2x2 max pool of the activated output (EPI_STORE only)
     int pool_pitch = 0;
+    void* pool_code = nullptr;  // optional with pool_out: 1 byte per pooled element (argmax + signs) for the pool backward
     void* out2 = nullptr;       // EPI_STORE split store: columns >= out_split go to out2 (planar halves of a concat gradient)
     int out2_pitch = 0, out_split = 0;
 };
