@@ -36,6 +36,9 @@ struct ConvGemmParams {
     const float* bias;    // per GEMM column (EPI_SHUFFLE: per cout, column % cout)
     const __nv_bfloat16* aux;
     int aux_pitch, aux_c0;
+    const uint32_t* aux_sign;  // ACT_MASK from sign words instead of the activation: uint32 [pixel][n_total / 32], channel 2j -> bit j,
+                               // 2j+1 -> bit 16+j of its 32-channel chunk (what `sign_out` of the producing forward tile wrote)
+    uint32_t* sign_out;        // optional (training): sign words of the activated output, same layout
     int cout;             // EPI_SHUFFLE: channels per sub-pixel
     int stages;
     int tmem_cols;
@@ -504,6 +507,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const ConvGemmParams p
             const int pix = (img * p.H + y) * p.W + x;
             const int col0 = n_t * p.n_tile;
             const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)p.n_tile;
+            // the first chunk's sign word is requested before the wait for the accumulator: its DRAM latency hides there
+            uint32_t sg_first = 0;
+            if (p.aux_sign && in_img) sg_first = __ldg(p.aux_sign + (size_t)pix * (size_t)(p.n_total >> 5) + (size_t)(col0 >> 5));
             ELD_WAIT(&tmem_full[acc], acc_ph, pw0);
             ptx::tc_fence_after();
             for (int c32 = 0; c32 < p.n_tile; c32 += 32) {
@@ -523,10 +529,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const ConvGemmParams p
                     bcol = co;
                 }
                 uint32_t mk[16];
+                uint32_t sgw = sg_first;
                 if (p.act == ACT_MASK && in_img) {
-                    const __nv_bfloat16* ap = p.aux + (size_t)pix * p.aux_pitch + (p.aux_c0 + col);
-                    ptx::ld_global_nc_v8(ap, mk);
-                    ptx::ld_global_nc_v8(ap + 16, mk + 8);
+                    if (p.aux_sign) {
+                        if (c32) sgw = __ldg(p.aux_sign + (size_t)pix * (size_t)(p.n_total >> 5) + (size_t)(col >> 5));
+                    } else {
+                        const __nv_bfloat16* ap = p.aux + (size_t)pix * p.aux_pitch + (p.aux_c0 + col);
+                        ptx::ld_global_nc_v8(ap, mk);
+                        ptx::ld_global_nc_v8(ap + 16, mk + 8);
+                    }
                 }
                 ptx::tmem_ld_wait();
                 float v[32];
@@ -542,6 +553,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const ConvGemmParams p
                 if (p.act == ACT_LRELU) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.2f * v[j]);
+                } else if (p.act == ACT_MASK && in_img && p.aux_sign) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        // slope = 0.6 + 0.4 * (+-1) = 1 or 0.2
+                        const float s_lo = __uint_as_float(((sgw << (31 - j)) & 0x80000000u) | 0x3F800000u);
+                        const float s_hi = __uint_as_float(((sgw << (15 - j)) & 0x80000000u) | 0x3F800000u);
+                        v[2 * j] *= __fmaf_rn(s_lo, 0.4f, 0.6f);
+                        v[2 * j + 1] *= __fmaf_rn(s_hi, 0.4f, 0.6f);
+                    }
                 } else if (p.act == ACT_MASK && in_img) {
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
@@ -563,6 +583,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const ConvGemmParams p
                 for (int j = 0; j < 16; ++j) {
                     const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
                     wv[j] = *reinterpret_cast<const uint32_t*>(&h);
+                }
+                if (p.sign_out && in_img) {
+                    // sign words of the stored activation: all a later LeakyReLU' needs (1/16 of the tensor)
+                    uint32_t sg = 0;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) sg = (sg >> 1) | (wv[j] & 0x80008000u);
+                    p.sign_out[(size_t)pix * (size_t)(p.n_total >> 5) + (size_t)(col >> 5)] = sg;
                 }
                 if (p.pool_out) {
                     // MaxPool2d(2) (Unet.py:13,51-63) fused: the 2x2 window of pixel (x, y) lives in lanes ^1 (x) and ^tile_w (y)

@@ -32,6 +32,8 @@ struct FirstConvParams {
     const float* bias;          // fprop
     __nv_bfloat16* out;         // fprop: NHWC bf16, 32 channels at out_pitch
     int out_pitch;
+    uint32_t* sign_out;         // fprop, optional (training): one sign word per pixel (channel 2j -> bit j, 2j+1 -> bit 16+j), the
+                                // LeakyReLU' mask conv1_2's data gradient needs (conv_umma.cuh aux_sign)
     float* dw;                  // wgrad: f32 OIHW [32][4][3][3], accumulated into
     float* db;                  // wgrad: f32 [32]
     int stages;
@@ -223,6 +225,12 @@ first_conv_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const FirstConv
             }
             ptx::st_global_v8(dst, wv);                    // 64 bytes = two full sectors, two 256-bit stores
             ptx::st_global_v8(dst + 16, wv + 8);
+            if (p.sign_out) {
+                uint32_t sg = 0;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) sg = (sg >> 1) | (wv[j] & 0x80008000u);
+                p.sign_out[(size_t)(img * p.H + y0 + py) * p.W + (x0 + px)] = sg;
+            }
             if (++acc == kFcAcc) { acc = 0; acc_ph ^= 1u; }
         }
     }

@@ -108,22 +108,41 @@ pack_all_kernel(const float* __restrict__ params, __nv_bfloat16* __restrict__ pa
         const int it = e.cin / 32;
         {
             const int co0 = (tl / it) * 32, ci0 = (tl % it) * 32;
-            for (int i = threadIdx.x; i < 32 * 288; i += 256) {
-                const int co = i / 288, r = i - co * 288;              // r = ci*9 + t
-                tile[co][r] = w[((size_t)(co0 + co) * e.cin + ci0) * 9 + r];
+            if ((reinterpret_cast<uintptr_t>(params) & 15) == 0) {     // layer offsets are multiples of 4 floats: 16-byte loads
+                for (int i = threadIdx.x; i < 32 * 72; i += 256) {
+                    const int co = i / 72, r4 = i - co * 72;
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(w + ((size_t)(co0 + co) * e.cin + ci0) * 9) + r4);
+                    float* t4 = &tile[co][4 * r4];
+                    t4[0] = v.x; t4[1] = v.y; t4[2] = v.z; t4[3] = v.w;
+                }
+            } else {
+                for (int i = threadIdx.x; i < 32 * 288; i += 256) {
+                    const int co = i / 288, r = i - co * 288;              // r = ci*9 + t
+                    tile[co][r] = w[((size_t)(co0 + co) * e.cin + ci0) * 9 + r];
+                }
             }
             __syncthreads();
-            // two adjacent K elements per thread: 4-byte stores (pairs never straddle a 16-byte swizzle chunk)
+            // eight adjacent K elements per thread = one 16-byte chunk of the swizzled row (chunks are what the swizzle permutes)
             const PackTileBase bf = pack_tile_base(e.cout, e.cin, 9, co0, ci0), bd = pack_tile_base(e.cin, e.cout, 9, ci0, co0);
-            for (int i = threadIdx.x; i < 32 * 144; i += 256) {       // fprop: [co][t][ci]
-                const int ci = (i & 15) * 2, t = (i >> 4) % 9, co = i / 144;
-                const __nv_bfloat162 v2 = __floats2bfloat162_rn(tile[co][ci * 9 + t], tile[co][(ci + 1) * 9 + t]);
-                *reinterpret_cast<__nv_bfloat162*>(of + pack_tile_index(bf, t, co, ci)) = v2;
+            for (int i = threadIdx.x; i < 32 * 36; i += 256) {        // fprop: [co][t][ci]
+                const int ci = (i & 3) * 8, t = (i >> 2) % 9, co = i / 36;
+                uint32_t q[4];
+#pragma unroll
+                for (int e2 = 0; e2 < 4; ++e2) {
+                    const __nv_bfloat162 v2 = __floats2bfloat162_rn(tile[co][(ci + 2 * e2) * 9 + t], tile[co][(ci + 2 * e2 + 1) * 9 + t]);
+                    q[e2] = *reinterpret_cast<const uint32_t*>(&v2);
+                }
+                *reinterpret_cast<uint4*>(of + pack_tile_index(bf, t, co, ci)) = make_uint4(q[0], q[1], q[2], q[3]);
             }
-            for (int i = threadIdx.x; i < 32 * 144; i += 256) {       // dgrad: [ci][8-t][co]
-                const int co = (i & 15) * 2, t = (i >> 4) % 9, ci = i / 144;
-                const __nv_bfloat162 v2 = __floats2bfloat162_rn(tile[co][ci * 9 + t], tile[co + 1][ci * 9 + t]);
-                *reinterpret_cast<__nv_bfloat162*>(od + pack_tile_index(bd, 8 - t, ci, co)) = v2;
+            for (int i = threadIdx.x; i < 32 * 36; i += 256) {        // dgrad: [ci][8-t][co]
+                const int co = (i & 3) * 8, t = (i >> 2) % 9, ci = i / 36;
+                uint32_t q[4];
+#pragma unroll
+                for (int e2 = 0; e2 < 4; ++e2) {
+                    const __nv_bfloat162 v2 = __floats2bfloat162_rn(tile[co + 2 * e2][ci * 9 + t], tile[co + 2 * e2 + 1][ci * 9 + t]);
+                    q[e2] = *reinterpret_cast<const uint32_t*>(&v2);
+                }
+                *reinterpret_cast<uint4*>(od + pack_tile_index(bd, 8 - t, ci, co)) = make_uint4(q[0], q[1], q[2], q[3]);
             }
         }
     } else {                              // deconv wt[ci][co][s]
@@ -162,15 +181,31 @@ wgrad_permute_kernel(const float* __restrict__ gtmp, float* __restrict__ grads, 
     const int ct = e.cout / 32;
     {
         const int co0 = (t % ct) * 32, ci0 = (t / ct) * 32;
-        for (int i = threadIdx.x; i < 9 * 32 * 32; i += 256) {
-            const int co = i & 31, ci = (i >> 5) & 31, tap = i >> 10;
-            tile[tap][ci][co] = gtmp[e.src + ((size_t)tap * e.cin + ci0 + ci) * e.cout + co0 + co];
+        // 16-byte accesses on both sides (layer offsets are multiples of 4 floats; the staging buffer is 1 KB aligned)
+        for (int i = threadIdx.x; i < 9 * 32 * 8; i += 256) {
+            const int co4 = i & 7, ci = (i >> 3) & 31, tap = i >> 8;
+            const float4 v = __ldg(reinterpret_cast<const float4*>(gtmp + e.src + ((size_t)tap * e.cin + ci0 + ci) * e.cout + co0) + co4);
+            float* t4 = &tile[tap][ci][4 * co4];
+            t4[0] = v.x; t4[1] = v.y; t4[2] = v.z; t4[3] = v.w;
         }
         __syncthreads();
-        for (int i = threadIdx.x; i < 32 * 288; i += 256) {
-            const int co = i / 288, r = i - co * 288;          // r = ci*9 + tap, contiguous in OIHW
-            const int ci = r / 9, tap = r - ci * 9;
-            grads[e.src + ((size_t)(co0 + co) * e.cin + ci0 + ci) * 9 + tap] = tile[tap][ci][co];
+        if ((reinterpret_cast<uintptr_t>(grads) & 15) == 0) {
+            for (int i = threadIdx.x; i < 32 * 72; i += 256) {
+                const int co = i / 72, r4 = i - co * 72;           // r = ci*9 + tap, contiguous in OIHW
+                float q[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int r = 4 * r4 + k, ci = r / 9, tap = r - ci * 9;
+                    q[k] = tile[tap][ci][co];
+                }
+                *(reinterpret_cast<float4*>(grads + e.src + ((size_t)(co0 + co) * e.cin + ci0) * 9) + r4) = make_float4(q[0], q[1], q[2], q[3]);
+            }
+        } else {
+            for (int i = threadIdx.x; i < 32 * 288; i += 256) {
+                const int co = i / 288, r = i - co * 288;
+                const int ci = r / 9, tap = r - ci * 9;
+                grads[e.src + ((size_t)(co0 + co) * e.cin + ci0 + ci) * 9 + tap] = tile[tap][ci][co];
+            }
         }
     }
 }
@@ -192,6 +227,10 @@ struct eld_unet {
     __nv_bfloat16 *dz9_2, *dz9_1, *dcat9, *dz8_2, *dz8_1, *dcat8, *dz7_2, *dz7_1, *dcat7, *dz6_2, *dz6_1, *dcat6,
         *dz5_2, *dz5_1, *dp4, *dz4_2, *dz4_1, *dp3, *dz3_2, *dz3_1, *dp2, *dz2_2, *dz2_1, *dp1, *dz1_2, *dz1_1;
     __nv_bfloat16 *pc1 = nullptr, *pc2 = nullptr, *pc3 = nullptr, *pc4 = nullptr;   // pool codes, 1 byte per pooled element (training)
+    // sign words (1 bit per element) of the activations whose LeakyReLU' a data gradient applies (training): the dgrad
+    // tiles read these instead of the activation itself
+    struct SignBuf { const void* act; uint32_t* words; } signs[16];
+    int n_signs = 0;
     __nv_bfloat16* packed;
     float* gtmp = nullptr;
     PackTable table;
@@ -234,6 +273,16 @@ static size_t layout(eld_unet* u, char* base, bool train)
         take(&u->dz2_2, 1, 64); take(&u->dz2_1, 1, 64); take(&u->dp1, 1, 32);
         take(&u->dz1_2, 0, 32); take(&u->dz1_1, 0, 32);
         take(&u->pc1, 1, 16); take(&u->pc2, 2, 32); take(&u->pc3, 3, 64); take(&u->pc4, 4, 128);
+        u->n_signs = 0;
+        auto take_signs = [&](__nv_bfloat16* act, int lvl, int ch) {      // ch / 32 words per pixel = ch / 16 bf16-sized units
+            __nv_bfloat16* w = nullptr;
+            take(&w, lvl, ch / 16);
+            u->signs[u->n_signs++] = { act, reinterpret_cast<uint32_t*>(w) };
+        };
+        take_signs(u->a1_1, 0, 32); take_signs(u->a2_1, 1, 64); take_signs(u->a3_1, 2, 128); take_signs(u->a4_1, 3, 256);
+        take_signs(u->a5_1, 4, 512); take_signs(u->a5_2, 4, 512); take_signs(u->a6_1, 3, 256); take_signs(u->a6_2, 3, 256);
+        take_signs(u->a7_1, 2, 128); take_signs(u->a7_2, 2, 128); take_signs(u->a8_1, 1, 64); take_signs(u->a8_2, 1, 64);
+        take_signs(u->a9_1, 0, 32);
     }
     // packed weights
     size_t pk = 0;
@@ -441,6 +490,14 @@ struct Runner {
     const __nv_bfloat16* wd(int i) const { return u->packed + u->L[i].wd_off; }
     const float* bias(int i) const { return params + u->L[i].b_off; }
 
+    // sign words of activation `act` (training engines; ELD_MASK_FROM_ACT=1 keeps the masks that re-read the activations: A/B)
+    uint32_t* sign_of(const void* act) const
+    {
+        static const bool off = getenv("ELD_MASK_FROM_ACT") != nullptr;
+        if (off || !u->dz9_2) return nullptr;
+        for (int i = 0; i < u->n_signs; ++i) if (u->signs[i].act == act) return u->signs[i].words;
+        return nullptr;
+    }
     // pool_dst != nullptr: MaxPool2d(2) of the output fused into the tile's epilogue (pooled tensor has cout channels)
     int conv(int li, const void* x, int xp, int xc0, void* y, int yp, int yc0, int lvl, void* pool_dst = nullptr, void* pool_code = nullptr) const
     {
@@ -451,6 +508,7 @@ struct Runner {
         op.b = wf(li); op.n_total = l.cout; op.cout = l.cout;
         op.epi_mode = EPI_STORE; op.act = ACT_LRELU; op.out = y; op.out_pitch = yp; op.out_c0 = yc0; op.bias = bias(li);
         op.pool_out = pool_dst; op.pool_pitch = l.cout; op.pool_code = pool_code;
+        if (yc0 == 0 && yp == l.cout) op.sign_out = sign_of(y);
         const double px = (double)u->n * op.H * op.W;
         Scope sc(u, st, l.name, "fprop", 2.0 * px * l.cout * 9 * l.cin, px * 2 * (l.cin + l.cout) + 18.0 * l.cin * l.cout);
         return launch_conv_gemm(ctx(), op, st);
@@ -483,6 +541,7 @@ struct Runner {
         op.out = dx; op.out_pitch = dxp; op.out_c0 = dxc0; op.bias = nullptr;
         if (dx2) { op.out2 = dx2; op.out2_pitch = dxp; op.out_split = l.cin / 2; }
         op.aux = act_src; op.aux_pitch = asp; op.aux_c0 = asc0;
+        if (act_src && asc0 == 0 && asp == l.cin) op.aux_sign = sign_of(act_src);
         const double px = (double)u->n * op.H * op.W;
         Scope sc(u, st, l.name, "dgrad", 2.0 * px * l.cout * 9 * l.cin, px * 2 * (l.cin * (act_src ? 2 : 1) + l.cout) + 18.0 * l.cin * l.cout);
         return launch_conv_gemm(ctx(), op, st);
@@ -495,7 +554,7 @@ struct Runner {
         op.n_img = u->n; op.H = u->H >> lvl_in; op.W = u->W >> lvl_in;
         op.b = wd(li); op.n_total = l.cin; op.cout = l.cin;
         op.epi_mode = EPI_STORE; op.act = ACT_MASK; op.out = dx; op.out_pitch = l.cin; op.out_c0 = 0;
-        op.aux = act_src; op.aux_pitch = l.cin; op.aux_c0 = 0;
+        op.aux = act_src; op.aux_pitch = l.cin; op.aux_c0 = 0; op.aux_sign = sign_of(act_src);
         const double px = (double)u->n * op.H * op.W;
         Scope sc(u, st, l.name, "dgrad", 2.0 * px * 4 * l.cout * l.cin, px * 2 * (2 * l.cin + 4 * l.cout) + 8.0 * l.cin * l.cout);
         return launch_conv_gemm(ctx(), op, st);
@@ -594,7 +653,7 @@ struct Runner {
             // conv1_1 (4 -> 32): software-im2col tile straight from the fp32 NCHW frame (first_conv.cuh)
             const double px = (double)U->n * U->H * U->W;
             Scope sc(u, st, "conv1_1", "fprop", 2.0 * px * 32 * 9 * U->cin0, px * (4 * U->cin0 + 64));
-            TRY(launch_first_conv(ctx(), x, U->cin0, wf(I_C11), bias(I_C11), U->a1_1, 32, U->n, U->H, U->W, st));
+            TRY(launch_first_conv(ctx(), x, U->cin0, wf(I_C11), bias(I_C11), U->a1_1, 32, U->n, U->H, U->W, st, sign_of(U->a1_1)));
         }
         if (fuse_pool) { TRY(conv(I_C12, U->a1_1, 32, 0, U->cat9, 64, 32, 0, U->p1, U->pc1)); } else { TRY(conv(I_C12, U->a1_1, 32, 0, U->cat9, 64, 32, 0)); TRY(pool(U->cat9, 64, 32, U->p1, 32, 1)); }      // + pool (Unet.py:51)
         TRY(conv(I_C21, U->p1, 32, 0, U->a2_1, 64, 0, 1));

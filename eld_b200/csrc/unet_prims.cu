@@ -60,6 +60,10 @@ int launch_conv_gemm(eld_ctx* ctx, const GemmOp& op, cudaStream_t st)
     p.out = static_cast<__nv_bfloat16*>(op.out); p.out_pitch = op.out_pitch; p.out_c0 = op.out_c0;
     p.bias = op.bias;
     p.aux = static_cast<const __nv_bfloat16*>(op.aux); p.aux_pitch = op.aux_pitch; p.aux_c0 = op.aux_c0;
+    ELD_REQUIRE(op.aux_sign == nullptr || (op.act == ACT_MASK && op.epi_mode == EPI_STORE), "conv tile: sign words are a mask source of a plain store epilogue");
+    ELD_REQUIRE(op.sign_out == nullptr || (op.act == ACT_LRELU && op.epi_mode == EPI_STORE && op.out_split == 0),
+                "conv tile: sign words are written behind LeakyReLU by a plain store epilogue");
+    p.aux_sign = static_cast<const uint32_t*>(op.aux_sign); p.sign_out = static_cast<uint32_t*>(op.sign_out);
     p.cout = op.cout;
     ELD_REQUIRE(op.pool_out == nullptr || (op.epi_mode == EPI_STORE && op.H % 2 == 0 && op.W % 2 == 0),
                 "conv tile: the fused max pool needs a plain store epilogue and even H, W");
@@ -199,13 +203,13 @@ static int encode_frame(eld_ctx* ctx, CUtensorMap* map, const float* x, int cin,
 
 // conv1_1 (4 -> 32): software-im2col tcgen05 tiles on the fp32 NCHW frame (first_conv.cuh)
 int launch_first_conv(eld_ctx* ctx, const float* x, int cin, const void* w_img, const float* bias, void* out, int out_pitch,
-                      int n, int H, int W, cudaStream_t st)
+                      int n, int H, int W, cudaStream_t st, void* sign_out)
 {
     ELD_REQUIRE(H % 8 == 0 && W % 16 == 0, "first conv tile: H=%d must be a multiple of 8 and W=%d of 16", H, W);
     FirstConvParams p{};
     p.x = x; p.n_img = n; p.H = H; p.W = W; p.tiles_x = W / 16; p.tiles_y = H / 8; p.cin = cin;
     p.w_img = static_cast<const uint8_t*>(w_img); p.bias = bias;
-    p.out = static_cast<__nv_bfloat16*>(out); p.out_pitch = out_pitch;
+    p.out = static_cast<__nv_bfloat16*>(out); p.out_pitch = out_pitch; p.sign_out = static_cast<uint32_t*>(sign_out);
     p.stages = 8;
     const int total = n * p.tiles_x * p.tiles_y;
     const int grid = total < ctx->num_sms ? total : ctx->num_sms;

@@ -42,6 +42,8 @@ struct GemmOp {
     const float* bias;
     const void* aux;
     int aux_pitch, aux_c0;
+    const void* aux_sign = nullptr;   // ACT_MASK from sign words (uint32 [pixel][n_total / 32]) instead of `aux`
+    void* sign_out = nullptr;         // EPI_STORE + ACT_LRELU: also write the output's sign words
     void* pool_out = nullptr;   // optional fused 2x2 max pool of the activated output (EPI_STORE only)
     int pool_pitch = 0;
     void* pool_code = nullptr;  // optional with pool_out: 1 byte per pooled element (argmax + signs) for the pool backward
@@ -64,7 +66,7 @@ int init_gemm_kernels(eld_ctx* ctx);   // opt in to large dynamic smem (call onc
 int launch_wgrad(eld_ctx* ctx, const WgradOp& op, cudaStream_t st);
 int launch_conv_gemm(eld_ctx* ctx, const GemmOp& op, cudaStream_t st);
 int launch_first_conv(eld_ctx* ctx, const float* x, int cin, const void* w_img, const float* bias, void* out, int out_pitch,
-                      int n, int H, int W, cudaStream_t st);
+                      int n, int H, int W, cudaStream_t st, void* sign_out = nullptr);
 int launch_first_conv_wgrad(eld_ctx* ctx, const float* x, int cin, const void* dz, int dz_pitch, float* dw, float* db,
                             int n, int H, int W, cudaStream_t st);
 int launch_pack_weights(eld_ctx* ctx, const float* w, void* out, int cout, int cin, int kind, cudaStream_t st);
