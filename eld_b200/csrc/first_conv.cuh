@@ -37,6 +37,7 @@ struct FirstConvParams {
     float* dw;                  // wgrad: f32 OIHW [32][4][3][3], accumulated into
     float* db;                  // wgrad: f32 [32]
     int stages;
+    int epi_groups;             // fprop: 1 or 2 epilogue groups (alternate tiles)
 };
 
 // A builder group (4 warps, one pixel per thread) needs ~1000 cycles per tile (36 shared-memory loads, packing, six
@@ -45,6 +46,10 @@ struct FirstConvParams {
 constexpr int kFcGroups = 2;
 constexpr int kFcBuilderWarps = 4 * kFcGroups;
 constexpr int kFcThreads = 32 * (kFcBuilderWarps + 6);   // + MMA issuer, 4 epilogue warps (fprop), TMA producer
+// fprop only: a second epilogue group (4 more warps) takes the odd tiles.  One warp per scheduler runs a tile's ~200
+// dependent instructions (tcgen05.ld, bias, LeakyReLU, pack, two 256-bit stores, sign word) in ~1000 cycles: with one
+// group that chain, not the builders or the MMAs, set the kernel's pace.
+constexpr int kFcThreadsFprop = kFcThreads + 128;
 constexpr int kFcRaw = 4 * 10 * 128;      // bytes of one raw patch: [4 planes][10 rows][32 floats], SW128-swizzled rows
 constexpr int kFcRawStages = 8;
 constexpr int kFcATile = 128 * 128;  // bytes
@@ -94,7 +99,7 @@ __device__ __forceinline__ void fc_tile_coords(const FirstConvParams& p, int til
 // ---------------------------------------------------------------------------------------------------------------------
 // fprop: a1_1 = lrelu(conv1_1(x) + b)
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kFcThreads, 1)
+__global__ void __launch_bounds__(kFcThreadsFprop, 1)
 first_conv_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const FirstConvParams p)
 {
     extern __shared__ uint8_t smem_raw[];
@@ -197,10 +202,11 @@ first_conv_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const FirstConv
         const int q = warp & 3;                            // TMEM lane quarter of this warp
         const int m = q * 32 + lane, py = m >> 4, px = m & 15;
         const float4* sb4 = reinterpret_cast<const float4*>(s_bias);
-        uint32_t acc = 0, acc_ph = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int eg = warp > kFcBuilderWarps + 5 ? 1 : 0;  // warps +1..+4 = group 0, +6..+9 = group 1
+        for (int i = eg < p.epi_groups ? eg : my_tiles; i < my_tiles; i += p.epi_groups) {
+            const uint32_t acc = (uint32_t)i % kFcAcc, acc_ph = ((uint32_t)i / kFcAcc) & 1u;
             int img, y0, x0;
-            fc_tile_coords(p, tile, img, y0, x0);
+            fc_tile_coords(p, (int)blockIdx.x + i * (int)gridDim.x, img, y0, x0);
             ptx::mbar_wait(&tmem_full[acc], acc_ph);
             ptx::tc_fence_after();
             uint32_t r[32];
@@ -231,7 +237,6 @@ first_conv_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const FirstConv
                 for (int j = 0; j < 16; ++j) sg = (sg >> 1) | (wv[j] & 0x80008000u);
                 p.sign_out[(size_t)(img * p.H + y0 + py) * p.W + (x0 + px)] = sg;
             }
-            if (++acc == kFcAcc) { acc = 0; acc_ph ^= 1u; }
         }
     }
     ptx::tc_fence_before();

@@ -211,12 +211,14 @@ int launch_first_conv(eld_ctx* ctx, const float* x, int cin, const void* w_img, 
     p.w_img = static_cast<const uint8_t*>(w_img); p.bias = bias;
     p.out = static_cast<__nv_bfloat16*>(out); p.out_pitch = out_pitch; p.sign_out = static_cast<uint32_t*>(sign_out);
     p.stages = 8;
+    static const int epi_groups = getenv("ELD_FC_ONE_EPI") ? 1 : 2;      // (A/B: one epilogue group)
+    p.epi_groups = epi_groups;
     const int total = n * p.tiles_x * p.tiles_y;
     const int grid = total < ctx->num_sms ? total : ctx->num_sms;
     CUtensorMap tmX;
     { int rc = encode_frame(ctx, &tmX, x, cin, n, H, W); if (rc) return rc; }
     const size_t smem = 1024 + 4096 + (size_t)p.stages * kFcATile + ((kFcRawStages * kFcRaw + 1023) & ~1023) + 1024;
-    ELD_CHECK_CUDA(launch_pdl(first_conv_fprop_kernel, grid, kFcThreads, smem, st, tmX, p));
+    ELD_CHECK_CUDA(launch_pdl(first_conv_fprop_kernel, grid, kFcThreadsFprop, smem, st, tmX, p));
     ELD_CHECK_CUDA(cudaGetLastError());
     count_launch(ctx);
     return ELD_OK;
