@@ -586,9 +586,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const ConvGemmParams p
                 }
                 if (p.sign_out && in_img) {
                     // sign words of the stored activation: all a later LeakyReLU' needs (1/16 of the tensor)
-                    uint32_t sg = 0;
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) sg = (sg >> 1) | (wv[j] & 0x80008000u);
+                    const uint32_t sg = ptx::gather_msb16(wv);
                     p.sign_out[(size_t)pix * (size_t)(p.n_total >> 5) + (size_t)(col >> 5)] = sg;
                 }
                 if (p.pool_out) {
@@ -612,13 +610,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const ConvGemmParams p
                         // per lane two 32-bit masks over its 32 channels: "is not the window's maximum" and "is negative"
                         // (channel 2j -> bit j, channel 2j+1 -> bit 16+j); the window's origin lane collects the four lanes'
                         // masks in the order the backward walks the window: (0,0) (0,1) (1,0) (1,1)
-                        uint32_t nm = 0, sg = 0;
+                        uint32_t ne[16];
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const uint32_t d = wv[j] ^ pw[j];
-                            nm = (nm >> 1) | ((((d & 0x7FFF7FFFu) + 0x7FFF7FFFu) | d) & 0x80008000u);
-                            sg = (sg >> 1) | (wv[j] & 0x80008000u);
-                        }
+                        for (int j = 0; j < 16; ++j)
+                            ne[j] = __hne2_mask(*reinterpret_cast<const __nv_bfloat162*>(&wv[j]), *reinterpret_cast<const __nv_bfloat162*>(&pw[j]));
+                        const uint32_t nm = ptx::gather_msb16(ne), sg = ptx::gather_msb16(wv);
                         uint32_t code[8];
                         code[0] = nm; code[4] = sg;
                         code[1] = __shfl_xor_sync(0xffffffffu, nm, 1);          code[5] = __shfl_xor_sync(0xffffffffu, sg, 1);

@@ -232,9 +232,7 @@ first_conv_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const FirstConv
             ptx::st_global_v8(dst, wv);                    // 64 bytes = two full sectors, two 256-bit stores
             ptx::st_global_v8(dst + 16, wv + 8);
             if (p.sign_out) {
-                uint32_t sg = 0;
-#pragma unroll
-                for (int j = 0; j < 16; ++j) sg = (sg >> 1) | (wv[j] & 0x80008000u);
+                const uint32_t sg = ptx::gather_msb16(wv);
                 p.sign_out[(size_t)(img * p.H + y0 + py) * p.W + (x0 + px)] = sg;
             }
         }

@@ -198,5 +198,15 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t M, uint32_t N, u
     return (1u << 4) | (1u << 7) | (1u << 10) | (a_mn_major << 15) | (b_mn_major << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
+// bits 15 / 31 of 16 packed bf16x2 words gathered into one word: word j's low half -> bit j, high half -> bit 16 + j
+// (the layout of the sign words and pool codes).  Four independent accumulators instead of one 32-deep dependent chain.
+__device__ __forceinline__ uint32_t gather_msb16(const uint32_t (&w)[16])
+{
+    uint32_t a[4] = { 0u, 0u, 0u, 0u };
+#pragma unroll
+    for (int j = 0; j < 16; ++j) a[j & 3] |= (w[j] >> (15 - j)) & (0x00010001u << j);
+    return (a[0] | a[1]) | (a[2] | a[3]);
+}
+
 }  // namespace ptx
 }  // namespace eld

@@ -238,3 +238,26 @@ def test_srgb_channel_variants(torch, io):
     # BASELINE's shape (6.5e-4 there, up to 6.5e-3 here); an indexing / channel-count bug moves a tensor by >= 1e-1
     bad = [(k, _rel(mine[k], gem[k])) for k in mine if _rel(mine[k], gem[k]) > 1.5e-2]
     assert not bad, bad
+
+
+def test_pool_ties_route_like_max_pool2d(torch):
+    """Frames made of constant 8 x 8 blocks: a quarter of all 2 x 2 pool windows hold four EQUAL bf16 activations.  The
+    pool backward works from the 1-byte code the forward tile leaves (argmax + signs, conv_umma.cuh / unet_ew.cu) and
+    must route the gradient of a tie to the first element in window order, as nn.MaxPool2d does (Unet.py:13); the
+    LeakyReLU' masks come from the sign words.  Every gradient tensor against the bf16-emulated backward."""
+    from eld_b200 import arch
+    from oracle.unet_ref import UNetSeeInDarkRef
+    from tests.unet_emul import emulated_train_step, fp32_cuda
+    torch.manual_seed(2018)
+    ours = arch.unet(4, 4).cuda()
+    torch.manual_seed(2018)
+    ref = UNetSeeInDarkRef(4, 4).cuda()
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand(2, 4, H // 8, W // 8, generator=g).repeat_interleave(8, 2).repeat_interleave(8, 3).cuda()
+    t = torch.rand(2, 4, H, W, generator=g).cuda()
+    out, loss = ours.train_step(x, t)
+    mine = {k: p.grad.detach().clone() for k, p in ours.named_parameters()}
+    oem, lem, gem = fp32_cuda(lambda: emulated_train_step(ref, x, t))
+    assert _rel(out, oem) <= 3e-3 and abs(loss.item() - lem.item()) <= 2e-3 * lem.item()
+    bad = [(k, _rel(mine[k], gem[k])) for k in mine if _rel(mine[k], gem[k]) > 1.5e-2]
+    assert not bad, bad
