@@ -38,6 +38,9 @@ struct FirstConvParams {
     float* db;                  // wgrad: f32 [32]
     int stages;
     int epi_groups;             // fprop: 1 or 2 epilogue groups (alternate tiles)
+    int groups;                 // wgrad: builder groups taking alternate tiles (1..2, or 3 with the joint producer)
+    int split_prod;             // wgrad: the dZ tiles have a TMA producer of their own (warp 8)
+    long long* prof;            // PROF instantiations only (ELD_FC_PROF): per-role totals and barrier waits, 16 slots per CTA
 };
 
 // A builder group (4 warps, one pixel per thread) needs ~1000 cycles per tile (36 shared-memory loads, packing, six
@@ -54,6 +57,12 @@ constexpr int kFcRaw = 4 * 10 * 128;      // bytes of one raw patch: [4 planes][
 constexpr int kFcRawStages = 8;
 constexpr int kFcATile = 128 * 128;  // bytes
 constexpr int kFcAcc = 4;            // fprop TMEM accumulator ring (4 x 32 columns)
+
+#define FC_WAIT(bar, par, ctr)                                                                     \
+    do {                                                                                           \
+        if (PROF) { const long long t_ = clock64(); ptx::mbar_wait((bar), (par)); (ctr) += clock64() - t_; } \
+        else ptx::mbar_wait((bar), (par));                                                         \
+    } while (0)
 
 __device__ __forceinline__ uint32_t fc_pack(float a, float b)
 {
@@ -99,9 +108,12 @@ __device__ __forceinline__ void fc_tile_coords(const FirstConvParams& p, int til
 // ---------------------------------------------------------------------------------------------------------------------
 // fprop: a1_1 = lrelu(conv1_1(x) + b)
 // ---------------------------------------------------------------------------------------------------------------------
+template <bool PROF>
 __global__ void __launch_bounds__(kFcThreadsFprop, 1)
 first_conv_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const FirstConvParams p)
 {
+    long long w0 = 0, w1 = 0, t0 = 0;
+    if (PROF) t0 = clock64();
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = ptx::smem_u32(smem_raw);
     uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
@@ -144,8 +156,8 @@ first_conv_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const FirstConv
         for (int i = g; i < my_tiles; i += kFcGroups) {
             const int s = i % p.stages, rs = i % kFcRawStages;
             const uint32_t ph = (uint32_t)(i / p.stages) & 1u, rph = (uint32_t)(i / kFcRawStages) & 1u;
-            ptx::mbar_wait(&raw_full[rs], rph);
-            ptx::mbar_wait(&empty[s], ph ^ 1u);
+            FC_WAIT(&raw_full[rs], rph, w0);
+            FC_WAIT(&empty[s], ph ^ 1u, w1);
             fc_build_row(reinterpret_cast<const float*>(r_s + (size_t)rs * kFcRaw), a_s + (size_t)s * kFcATile, m, py, px);
             ptx::mbar_arrive(&raw_empty[rs]);              // this thread's patch reads are done (values are in the A tile)
             ptx::fence_proxy_async();                      // generic-proxy stores -> visible to the tensor core's async proxy
@@ -167,8 +179,8 @@ first_conv_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const FirstConv
         int s = 0;
         uint32_t ph = 0, acc = 0, acc_ph = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            ptx::mbar_wait(&tmem_empty[acc], acc_ph ^ 1u);
-            ptx::mbar_wait(&full[s], ph);
+            FC_WAIT(&tmem_empty[acc], acc_ph ^ 1u, w0);
+            FC_WAIT(&full[s], ph, w1);
             ptx::tc_fence_after();
             if (ptx::elect_one()) {
                 const uint32_t a_lo = (uint32_t)desc_hi | (((a_base + (uint32_t)s * kFcATile) & 0x3FFFFu) >> 4);
@@ -191,7 +203,7 @@ first_conv_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const FirstConv
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 int img, y0, x0;
                 fc_tile_coords(p, tile, img, y0, x0);
-                ptx::mbar_wait(&raw_empty[rs], rph ^ 1u);
+                FC_WAIT(&raw_empty[rs], rph ^ 1u, w0);
                 ptx::mbar_arrive_expect_tx(&raw_full[rs], (uint32_t)kFcRaw);
                 ptx::tma_load_5d(r_s + (size_t)rs * kFcRaw, &tmX, &raw_full[rs], 2 * (x0 - 4), y0 - 1, 0, img, 0);
                 if (++rs == kFcRawStages) { rs = 0; rph ^= 1u; }
@@ -207,7 +219,7 @@ first_conv_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const FirstConv
             const uint32_t acc = (uint32_t)i % kFcAcc, acc_ph = ((uint32_t)i / kFcAcc) & 1u;
             int img, y0, x0;
             fc_tile_coords(p, (int)blockIdx.x + i * (int)gridDim.x, img, y0, x0);
-            ptx::mbar_wait(&tmem_full[acc], acc_ph);
+            FC_WAIT(&tmem_full[acc], acc_ph, w0);
             ptx::tc_fence_after();
             uint32_t r[32];
             ptx::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * 32u, r);
@@ -237,6 +249,17 @@ first_conv_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const FirstConv
             }
         }
     }
+    if (PROF && lane == 0) {
+        // slots: 0-2 builders 0 (total, wait raw_full, wait empty) | 3-5 builders 1 | 6-8 MMA (total, wait tmem_empty, wait full)
+        //        9-10 producer (total, wait raw_empty) | 11-12 epilogue 0 (total, wait tmem_full) | 13-14 epilogue 1
+        const int base = warp == 0 ? 0 : warp == 4 ? 3 : warp == kFcBuilderWarps ? 6 : warp == kFcBuilderWarps + 5 ? 9
+                       : warp == kFcBuilderWarps + 1 ? 11 : warp == kFcBuilderWarps + 6 ? 13 : -1;
+        if (base >= 0) {
+            long long* o = p.prof + (size_t)blockIdx.x * 16 + base;
+            o[0] = clock64() - t0; o[1] = w0;
+            if (base <= 6) o[2] = w1;
+        }
+    }
     ptx::tc_fence_before();
     __syncthreads();
     if (warp == kFcBuilderWarps + 1) ptx::tmem_dealloc(tmem_base, 128);
@@ -246,10 +269,17 @@ first_conv_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const FirstConv
 // wgrad: dW[co][c][tap] += sum_px dZ[px][co] * x[px + tap][c] ; db[co] += sum_px dZ[px][co]
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int kFcQTile = 128 * 64;   // dZ tile: 128 pixel rows x 32 channels bf16 (SW64)
+// wgrad roles inside the same 14 warps: builders = warps [0, 4 * groups) with groups <= 3 (it has no per-tile epilogue, so the
+// four warps the fprop uses for one can build), MMA issuer = warp 12, TMA producer (+ TMEM allocation) = warp 13
+constexpr int kWgMmaWarp = 12, kWgProdWarp = 13, kWgDzWarp = 8;     // warp 8 builds when groups == 3 (joint producer only)
+static_assert(kFcThreads == 32 * 14, "wgrad role map assumes 14 warps");
 
+template <bool PROF>
 __global__ void __launch_bounds__(kFcThreads, 1)
 first_conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmQ, const FirstConvParams p)
 {
+    long long w0 = 0, w1 = 0, t0 = 0;
+    if (PROF) t0 = clock64();
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = ptx::smem_u32(smem_raw);
     uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
@@ -277,7 +307,7 @@ first_conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
         ptx::mbar_init(acc_full, 1);
         ptx::fence_barrier_init();
     }
-    if (warp == kFcBuilderWarps + 1) ptx::tmem_alloc(tmem_slot, 32);
+    if (warp == kWgProdWarp) ptx::tmem_alloc(tmem_slot, 32);
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
@@ -285,13 +315,13 @@ first_conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
     ptx::grid_dep_wait();
     ptx::grid_dep_launch();
 
-    if (warp < kFcBuilderWarps) {
+    if (warp < 4 * p.groups) {
         const int g = warp >> 2, m = threadIdx.x & 127, py = m >> 4, px = m & 15;
-        for (int i = g; i < my_tiles; i += kFcGroups) {
+        for (int i = g; i < my_tiles; i += p.groups) {
             const int s = i % p.stages, rs = i % kFcRawStages;
             const uint32_t ph = (uint32_t)(i / p.stages) & 1u, rph = (uint32_t)(i / kFcRawStages) & 1u;
-            ptx::mbar_wait(&raw_full[rs], rph);
-            ptx::mbar_wait(&empty[s], ph ^ 1u);
+            FC_WAIT(&raw_full[rs], rph, w0);
+            FC_WAIT(&empty[s], ph ^ 1u, w1);
             fc_build_row(reinterpret_cast<const float*>(r_s + (size_t)rs * kFcRaw), ring + (size_t)s * stage_bytes, m, py, px);
             ptx::mbar_arrive(&raw_empty[rs]);
             ptx::fence_proxy_async();
@@ -316,7 +346,7 @@ first_conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
                 for (int co = 0; co < 32; ++co) atomicAdd(p.db + co, __uint_as_float(r[co]));
             }
         }
-    } else if (warp == kFcBuilderWarps) {
+    } else if (warp == kWgMmaWarp) {
         // ===================== MMA issuer: D[k][co] += A^T (MN-major) * dZ (MN-major), K = 128 pixels per tile ==========
         const uint32_t idesc = ptx::make_idesc_bf16(128, 32, 1, 1);
         // A: 64 k-slots = one 128-byte M block per pixel row, 8-row groups 1024 B apart; M = 128 reads a second block
@@ -328,8 +358,8 @@ first_conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
         int s = 0;
         uint32_t ph = 0;
         for (int i = 0; i < my_tiles; ++i) {
-            ptx::mbar_wait(&full_a[s], ph);
-            ptx::mbar_wait(&full_q[s], ph);
+            FC_WAIT(&full_a[s], ph, w0);
+            FC_WAIT(&full_q[s], ph, w1);
             ptx::tc_fence_after();
             if (ptx::elect_one()) {
                 const uint32_t st = base + (uint32_t)s * (uint32_t)stage_bytes;
@@ -345,8 +375,39 @@ first_conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
             __syncwarp();
             if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
-    } else if (warp == kFcBuilderWarps + 1) {
-        // ===================== TMA producer: raw halo patches (ring of 8) and dZ tiles (ring of `stages`) =====================
+    } else if (warp == kWgProdWarp && p.split_prod) {
+        // ===================== TMA producer of the raw halo patches (its own warp: see below) =====================
+        if (lane == 0) {
+            int rs = 0;
+            uint32_t rph = 0;
+            for (int i = 0; i < my_tiles; ++i) {
+                int img, y0, x0;
+                fc_tile_coords(p, (int)blockIdx.x + i * (int)gridDim.x, img, y0, x0);
+                FC_WAIT(&raw_empty[rs], rph ^ 1u, w0);
+                ptx::mbar_arrive_expect_tx(&raw_full[rs], (uint32_t)kFcRaw);
+                ptx::tma_load_5d(r_s + (size_t)rs * kFcRaw, &tmX, &raw_full[rs], 2 * (x0 - 4), y0 - 1, 0, img, 0);
+                if (++rs == kFcRawStages) { rs = 0; rph ^= 1u; }
+            }
+        }
+    } else if (warp == kWgDzWarp && p.split_prod) {
+        // ===================== TMA producer of the dZ tiles =====================
+        // One thread used to feed both rings.  The in-kernel profile showed the convoy: blocked on a raw-ring slot (which
+        // the builders free only after they got an A stage, i.e. after the MMAs advanced) it did not issue the dZ tile the
+        // MMAs were waiting for - the issuer spent 44 % of the kernel waiting for dZ, the builders 45 % for patches.
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            for (int i = 0; i < my_tiles; ++i) {
+                int img, y0, x0;
+                fc_tile_coords(p, (int)blockIdx.x + i * (int)gridDim.x, img, y0, x0);
+                FC_WAIT(&empty[s], ph ^ 1u, w1);
+                ptx::mbar_arrive_expect_tx(&full_q[s], (uint32_t)kFcQTile);
+                ptx::tma_load_5d(ring + (size_t)s * stage_bytes + kFcATile, &tmQ, &full_q[s], 0, x0, y0, img, 0);
+                if (++s == p.stages) { s = 0; ph ^= 1u; }
+            }
+        }
+    } else if (warp == kWgProdWarp) {
+        // ===================== one TMA producer for both rings =====================
         if (lane == 0) {
             int s = 0, rs = 0;
             uint32_t ph = 0, rph = 0;
@@ -356,7 +417,7 @@ first_conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
             auto issue_raw = [&]() {
                 int img, y0, x0;
                 fc_tile_coords(p, t_raw, img, y0, x0);
-                ptx::mbar_wait(&raw_empty[rs], rph ^ 1u);
+                FC_WAIT(&raw_empty[rs], rph ^ 1u, w0);
                 ptx::mbar_arrive_expect_tx(&raw_full[rs], (uint32_t)kFcRaw);
                 ptx::tma_load_5d(r_s + (size_t)rs * kFcRaw, &tmX, &raw_full[rs], 2 * (x0 - 4), y0 - 1, 0, img, 0);
                 if (++rs == kFcRawStages) { rs = 0; rph ^= 1u; }
@@ -366,16 +427,26 @@ first_conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
                 while (n_raw < my_tiles && n_raw <= i + lead - 1) issue_raw();
                 int img, y0, x0;
                 fc_tile_coords(p, (int)blockIdx.x + i * (int)gridDim.x, img, y0, x0);
-                ptx::mbar_wait(&empty[s], ph ^ 1u);
+                FC_WAIT(&empty[s], ph ^ 1u, w1);
                 ptx::mbar_arrive_expect_tx(&full_q[s], (uint32_t)kFcQTile);
                 ptx::tma_load_5d(ring + (size_t)s * stage_bytes + kFcATile, &tmQ, &full_q[s], 0, x0, y0, img, 0);
                 if (++s == p.stages) { s = 0; ph ^= 1u; }
             }
         }
     }
+    if (PROF && lane == 0) {
+        // slots: 0-2 builders 0 (total incl. the final epilogue, wait raw_full, wait empty) | 3-5 builders 1
+        //        6-8 MMA (total, wait full_a, wait full_q) | 9-11 producer (total, wait raw_empty, wait empty) | 12-14 dZ producer
+        const int base = warp == 0 ? 0 : warp == 4 ? 3 : warp == kWgMmaWarp ? 6 : warp == kWgProdWarp ? 9
+                       : (warp == kWgDzWarp && p.split_prod) ? 12 : -1;
+        if (base >= 0) {
+            long long* o = p.prof + (size_t)blockIdx.x * 16 + base;
+            o[0] = clock64() - t0; o[1] = w0; o[2] = w1;
+        }
+    }
     ptx::tc_fence_before();
     __syncthreads();
-    if (warp == kFcBuilderWarps + 1) ptx::tmem_dealloc(tmem_base, 32);
+    if (warp == kWgProdWarp) ptx::tmem_dealloc(tmem_base, 32);
 }
 
 }  // namespace eld

@@ -202,6 +202,35 @@ static int encode_frame(eld_ctx* ctx, CUtensorMap* map, const float* x, int cin,
 }
 
 // conv1_1 (4 -> 32): software-im2col tcgen05 tiles on the fp32 NCHW frame (first_conv.cuh)
+// debugging (ELD_FC_PROF): per-role totals and barrier-wait cycles of one first-layer launch, printed to stderr
+template <typename Launch>
+static int fc_prof_launch(eld_ctx* ctx, const char* what, int grid, double tiles_per_cta, cudaStream_t st, FirstConvParams p, Launch launch)
+{
+    long long* d = nullptr;
+    ELD_CHECK_CUDA(cudaMalloc(&d, (size_t)grid * 16 * sizeof(long long)));
+    ELD_CHECK_CUDA(cudaMemsetAsync(d, 0, (size_t)grid * 16 * sizeof(long long), st));
+    p.prof = d;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, st);
+    launch(p);
+    cudaEventRecord(e1, st);
+    ELD_CHECK_CUDA(cudaStreamSynchronize(st));
+    float ev_ms = 0.f;
+    cudaEventElapsedTime(&ev_ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    std::vector<long long> h((size_t)grid * 16);
+    ELD_CHECK_CUDA(cudaMemcpy(h.data(), d, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    double m[16] = { 0 };
+    for (int b = 0; b < grid; ++b) for (int k = 0; k < 16; ++k) m[k] += (double)h[(size_t)b * 16 + k] / grid / 1e3;
+    fprintf(stderr, "[first conv prof] %s event time %.1f us tiles/cta %.1f stages %d | kclk: bld0 tot %.1f wRF %.1f wE %.1f | bld1 tot %.1f wRF %.1f wE %.1f | "
+                    "mma tot %.1f w0 %.1f w1 %.1f | slots 9.. (fprop: prod tot wRE, epi0 tot wTF, epi1 tot wTF; wgrad: prod tot wRE wE, dz-prod tot - wE): %.1f %.1f %.1f %.1f %.1f %.1f\n",
+            what, ev_ms * 1e3, tiles_per_cta, p.stages, m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], m[8], m[9], m[10], m[11], m[12], m[13], m[14]);
+    count_launch(ctx);
+    return ELD_OK;
+}
+
 int launch_first_conv(eld_ctx* ctx, const float* x, int cin, const void* w_img, const float* bias, void* out, int out_pitch,
                       int n, int H, int W, cudaStream_t st, void* sign_out)
 {
@@ -218,7 +247,9 @@ int launch_first_conv(eld_ctx* ctx, const float* x, int cin, const void* w_img, 
     CUtensorMap tmX;
     { int rc = encode_frame(ctx, &tmX, x, cin, n, H, W); if (rc) return rc; }
     const size_t smem = 1024 + 4096 + (size_t)p.stages * kFcATile + ((kFcRawStages * kFcRaw + 1023) & ~1023) + 1024;
-    ELD_CHECK_CUDA(launch_pdl(first_conv_fprop_kernel, grid, kFcThreadsFprop, smem, st, tmX, p));
+    if (getenv("ELD_FC_PROF")) return fc_prof_launch(ctx, "fprop", grid, (double)total / grid, st, p, [&](const FirstConvParams& q) {
+        first_conv_fprop_kernel<true><<<grid, kFcThreadsFprop, smem, st>>>(tmX, q); });
+    ELD_CHECK_CUDA(launch_pdl(first_conv_fprop_kernel<false>, grid, kFcThreadsFprop, smem, st, tmX, p));
     ELD_CHECK_CUDA(cudaGetLastError());
     count_launch(ctx);
     return ELD_OK;
@@ -232,6 +263,11 @@ int launch_first_conv_wgrad(eld_ctx* ctx, const float* x, int cin, const void* d
     p.x = x; p.n_img = n; p.H = H; p.W = W; p.tiles_x = W / 16; p.tiles_y = H / 8; p.cin = cin;
     p.dw = dw; p.db = db;
     p.stages = 6;
+    static const int split = getenv("ELD_FC_WGRAD_SPLIT") != nullptr;                               // (A/B: a TMA producer per ring)
+    static const int groups = getenv("ELD_FC_WGRAD_GROUPS") ? atoi(getenv("ELD_FC_WGRAD_GROUPS")) : 2;
+    ELD_REQUIRE(groups >= 1 && groups <= (split ? 2 : 3), "first conv wgrad: 1..2 builder groups (3 with the joint producer)");
+    p.split_prod = split;
+    p.groups = groups;
     CUtensorMap tmQ;
     const cuuint64_t eb = 2;
     cuuint64_t dims[5] = { (cuuint64_t)dz_pitch, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n, 1 };
@@ -244,7 +280,9 @@ int launch_first_conv_wgrad(eld_ctx* ctx, const float* x, int cin, const void* d
     CUtensorMap tmX;
     { int rc = encode_frame(ctx, &tmX, x, cin, n, H, W); if (rc) return rc; }
     const size_t smem = 1024 + (size_t)p.stages * (kFcATile + kFcQTile) + kFcATile + ((kFcRawStages * kFcRaw + 1023) & ~1023) + 1024;
-    ELD_CHECK_CUDA(launch_pdl(first_conv_wgrad_kernel, grid, kFcThreads, smem, st, tmX, tmQ, p));
+    if (getenv("ELD_FC_PROF")) return fc_prof_launch(ctx, "wgrad", grid, (double)total / grid, st, p, [&](const FirstConvParams& q) {
+        first_conv_wgrad_kernel<true><<<grid, kFcThreads, smem, st>>>(tmX, tmQ, q); });
+    ELD_CHECK_CUDA(launch_pdl(first_conv_wgrad_kernel<false>, grid, kFcThreads, smem, st, tmX, tmQ, p));
     ELD_CHECK_CUDA(cudaGetLastError());
     count_launch(ctx);
     return ELD_OK;
@@ -253,8 +291,10 @@ int launch_first_conv_wgrad(eld_ctx* ctx, const float* x, int cin, const void* d
 int init_gemm_kernels(eld_ctx* ctx)
 {
     ELD_CHECK_CUDA(cudaSetDevice(ctx->device));
-    ELD_CHECK_CUDA(cudaFuncSetAttribute(first_conv_fprop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    ELD_CHECK_CUDA(cudaFuncSetAttribute(first_conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    ELD_CHECK_CUDA(cudaFuncSetAttribute(first_conv_fprop_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    ELD_CHECK_CUDA(cudaFuncSetAttribute(first_conv_wgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    ELD_CHECK_CUDA(cudaFuncSetAttribute(first_conv_fprop_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    ELD_CHECK_CUDA(cudaFuncSetAttribute(first_conv_wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     ELD_CHECK_CUDA(cudaFuncSetAttribute(conv_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     ELD_CHECK_CUDA(cudaFuncSetAttribute(conv_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     ELD_CHECK_CUDA(cudaFuncSetAttribute(wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
