@@ -407,7 +407,7 @@ first_conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
             }
         }
     } else if (warp == kWgProdWarp) {
-        // ===================== one TMA producer for both rings =====================
+        // ===================== one TMA producer for both rings (ELD_FC_WGRAD_JOINT=1: the A/B arm) =====================
         if (lane == 0) {
             int s = 0, rs = 0;
             uint32_t ph = 0, rph = 0;

@@ -263,7 +263,7 @@ int launch_first_conv_wgrad(eld_ctx* ctx, const float* x, int cin, const void* d
     p.x = x; p.n_img = n; p.H = H; p.W = W; p.tiles_x = W / 16; p.tiles_y = H / 8; p.cin = cin;
     p.dw = dw; p.db = db;
     p.stages = 6;
-    static const int split = getenv("ELD_FC_WGRAD_SPLIT") != nullptr;                               // (A/B: a TMA producer per ring)
+    static const int split = getenv("ELD_FC_WGRAD_JOINT") == nullptr;                               // (A/B: one producer for both rings)
     static const int groups = getenv("ELD_FC_WGRAD_GROUPS") ? atoi(getenv("ELD_FC_WGRAD_GROUPS")) : 2;
     ELD_REQUIRE(groups >= 1 && groups <= (split ? 2 : 3), "first conv wgrad: 1..2 builder groups (3 with the joint producer)");
     p.split_prod = split;
