@@ -62,7 +62,10 @@ int eld_deconv2x2_wgrad_bf16(eld_ctx* ctx, const void* x, int x_pitch, int x_c0,
 typedef struct eld_unet eld_unet;
 size_t eld_unet_param_count(void);                                   /* 7,760,484 for UNetSeeInDark(4,4) */
 int    eld_unet_param_offset(const char* layer, int is_bias, size_t* offset, size_t* count);
-size_t eld_unet_workspace_bytes(int n, int h, int w, int train);     /* activations (+gradients) + packed weights */
+size_t eld_unet_workspace_bytes(int n, int h, int w, int train);     /* activations (+gradients) + packed weights; train = 1 also
+                                                                      * holds what the forward tiles leave for the backward: sign
+                                                                      * words (1 bit per masked activation element) and pool codes
+                                                                      * (1 byte per pooled element: argmax + signs) */
 /* Inference (train = 0): h % 16 == 0 and w % 16 == 0, as for the reference network.  Training (train = 1):
  * h % 128 == 0, w % 256 == 0.  The caller owns `workspace` (device memory) for the lifetime of the object. */
 int    eld_unet_create(eld_ctx* ctx, int n, int h, int w, int train, void* workspace, size_t bytes, eld_unet** out);
